@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE — regenerate tests/golden/*.npz from the LIVE reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.gen_golden
+
+The reference has no golden vectors for this path, so the pin is
+the unmodified reference code itself executed here, with numpy.random.normal patched
+to pop from a recorded standard-normal stream.  Library versions are stored in every
+file.  Inputs (actions, init, noise stream seeds) are stored too, so the parity tests
+on the GPU box need nothing but these files.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import live_reference as lr
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+KEEP = ("pos", "obs", "done", "counter", "state_prime", "cursor", "attempts", "carry_f", "carry_h", "t", "rew",
+        "reset_obs", "reset_cursor", "reset_carry_f", "reset_carry_h", "reset_state_prime")
+
+
+def versions():
+    import scipy
+    import sklearn
+    return np.array([f"numpy {np.__version__}", f"scipy {scipy.__version__}", f"scikit-learn {sklearn.__version__}"])
+
+
+def random_actions(T, seed=1):
+    """f~U[0,20), alpha~U[0,2pi), columns drawn f then alpha."""
+    rng = np.random.default_rng(seed)
+    f = rng.uniform(0, 20, size=T)
+    al = rng.uniform(0, 2 * np.pi, size=T)
+    return np.stack([f, al], axis=1)
+
+
+def circle_actions(T, freq=4.0):
+    """main.py:27-29 circle sweep."""
+    a = np.zeros((T, 3))
+    a[:, 0] = freq
+    a[:, 1] = np.linspace(-np.pi, np.pi, T)
+    return a
+
+
+def single_env_cases():
+    """name -> (actions, init, noise_var, a0, is_mismatched, z_seed, z_len, prior)
+
+    ``prior`` = an episode run on the same env object before the recorded one, to expose
+    the reset-ordering quirk (MR_env.py:181 before :183)."""
+    T = 500
+    ra = random_actions(T)
+    return {
+        "c1_sigma0": (ra, [110.0, 105.0], 0.0, 1.0, False, 0, 64 * T, None),
+        "c1_sigma1": (ra, [110.0, 105.0], 1.0, 1.0, False, 0, 64 * T, None),
+        "c1_mismatch_circle": (circle_actions(T), np.array([0, 0]), 0.5, 1.5, True, 0, 64 * T, None),
+        "c1_mismatch_idle": (np.zeros((100, 3)), np.array([0, 0]), 0.5, 1.5, True, 3, 100 * 1200, None),
+        "c1_default_sim_params": (ra[:60], [110.0, 105.0], 0.0, 0.0, False, 0, 256 * 60, None),
+        "near_goal": (ra[:60], [25.0, 20.0], 1.0, 1.0, False, 4, 256 * 60, None),
+        "out_of_bounds": (np.tile([[20.0, 0.0]], (60, 1)), [4999.5, 20.0], 1.0, 1.0, False, 5, 256 * 60, None),
+        "float32_init": (ra[:120], np.array([113.37, 101.91], dtype=np.float32), 1.0, 1.0, False, 6, 256 * 120, None),
+        "reset_after_mismatch": (ra[:80], [110.0, 105.0], 1.0, 1.0, False, 7, 256 * 100, "mismatched"),
+        "reset_into_mismatch": (ra[:80], [110.0, 105.0], 0.5, 1.5, True, 8, 256 * 100, "matched"),
+        "noisefree_mismatch": (ra[:120], [110.0, 105.0], 0.0, 1.5, True, 9, 256 * 120, None),
+    }
+
+
+def gen_single():
+    lr.load()
+    out = {"versions": versions()}
+    for name, (acts, init, sig, a0, mism, zseed, zlen, prior) in single_env_cases().items():
+        z = np.random.default_rng(zseed).standard_normal(zlen)
+        env = lr.new_env()
+        z_used = z
+        if prior is not None:
+            # run a short prior episode on the SAME env so simulator.is_mismatched is stale at reset
+            zp = np.random.default_rng(100 + zseed).standard_normal(4096)
+            lr.rollout(random_actions(5, seed=11), [105.0, 105.0], 1.0, 1.0, prior == "mismatched", zp, env=env)
+        rec = lr.rollout(acts, init, sig, a0, mism, z_used, env=env)
+        used = int(rec["cursor"][-1])
+        out[f"{name}/actions"] = np.asarray(acts, dtype=np.float64)
+        out[f"{name}/init"] = np.asarray(init)
+        out[f"{name}/params"] = np.array([sig, a0, float(mism), float(prior == "mismatched")])
+        out[f"{name}/z"] = z[:used + 8]
+        for k in KEEP:
+            out[f"{name}/{k}"] = rec[k]
+        print(f"{name}: T={len(acts)} draws={used} max_attempts={rec['attempts'].max()} first_done="
+              f"{int(np.argmax(rec['done'])) if rec['done'].any() else -1}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "single_env.npz"), **out)
+
+
+def gen_batch(n_env=48, T=96, zlen_per=80 * 96):
+    """SURVEY §8d C2 subset: float32-rounded inits ~U[100,120)^2 (default_rng(2)), per-env
+    noise streams, per-env random actions; sigma in {0, 1} and one mismatched set."""
+    lr.load()
+    rng = np.random.default_rng(2)
+    init = rng.uniform(100, 120, size=(n_env, 2)).astype(np.float32)
+    arng = np.random.default_rng(12)
+    acts = np.stack([arng.uniform(0, 20, size=(T, n_env)), arng.uniform(0, 2 * np.pi, size=(T, n_env))], axis=-1)
+    z = np.random.default_rng(22).standard_normal((n_env, zlen_per))
+    out = {"versions": versions(), "init": init, "actions": acts}
+    used_max = 0
+    for tag, (sig, a0, mism) in {"sigma0": (0.0, 1.0, False), "sigma1": (1.0, 1.0, False),
+                                 "mismatch": (0.5, 1.5, True)}.items():
+        recs = [lr.rollout(acts[:, e], init[e], sig, a0, mism, z[e]) for e in range(n_env)]
+        out[f"{tag}/params"] = np.array([sig, a0, float(mism), 0.0])
+        for k in KEEP:
+            if k.startswith("reset_"):
+                out[f"{tag}/{k}"] = np.stack([np.asarray(r[k]) for r in recs], axis=0)   # [n_env, ...]
+            else:
+                out[f"{tag}/{k}"] = np.stack([r[k] for r in recs], axis=1)               # [T, n_env, ...]
+        used_max = max(used_max, max(int(r["cursor"][-1]) for r in recs))
+        print(f"batch {tag}: draws max={max(int(r['cursor'][-1]) for r in recs)} "
+              f"max_attempts={max(int(r['attempts'].max()) for r in recs)}")
+    out["z"] = z[:, :used_max + 8]
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "batch_env.npz"), **out)
+
+
+def gen_gp():
+    """SURVEY §8d C4 at reduced size (N_train=300) through the reference's own LearningModule
+    object: fixed-kernel sklearn GPRs installed on it, outputs of .error() and objective()."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+
+    mods = lr.load()
+    LM = mods["Learning_module"]
+    rng = np.random.default_rng(0)
+    n = 300
+    X = np.sort(rng.uniform(-np.pi, np.pi, n))
+    yx = 0.2 + 0.5 * np.cos(X + 0.3) + 0.09 * rng.standard_normal(n)
+    yy = -0.1 + 0.4 * np.sin(X - 0.2) + 0.09 * rng.standard_normal(n)
+    lm = LM.LearningModule()
+    lm.gprX = GaussianProcessRegressor(kernel=RBF(0.2) + WhiteKernel(0.008), optimizer=None)
+    lm.gprY = GaussianProcessRegressor(kernel=RBF(0.25) + WhiteKernel(0.008), optimizer=None)
+    lm.gprX.fit(X.reshape(-1, 1), yx)
+    lm.gprY.fit(X.reshape(-1, 1), yy)
+    lm.a0, lm.freq, lm.Dx, lm.Dy = 1.4, 4.0, 0.21, -0.12
+    qrng = np.random.default_rng(5)
+    vd = qrng.standard_normal((64, 2)) * 5
+    err = np.array([np.concatenate(lm.error(v)) for v in vd])              # Learning_module.py:186-196
+    alphas = qrng.uniform(-np.pi, np.pi, 64)
+    obj = np.array([float(np.ravel(LM.objective(a, lm.a0, lm.freq, vd[i], lm.gprX, lm.gprY, lm.Dx, lm.Dy))[0])
+                    for i, a in enumerate(alphas)])                         # Learning_module.py:10-24
+    q = np.linspace(-np.pi, np.pi, 257).reshape(-1, 1)
+    mx, sx = lm.gprX.predict(q, return_std=True)
+    my, sy = lm.gprY.predict(q, return_std=True)
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, "gp.npz"), versions=versions(), X=X, yx=yx, yy=yy,
+        lsx=0.2, lsy=0.25, noise=0.008, alpha_x=lm.gprX.alpha_, alpha_y=lm.gprY.alpha_,
+        hyper=np.array([lm.a0, lm.freq, lm.Dx, lm.Dy]), vd=vd, error=err, obj_alpha=alphas, objective=obj,
+        grid=q.ravel(), grid_mx=mx, grid_sx=sx, grid_my=my, grid_sy=sy)
+    print("gp: error() rows", err.shape, "sigma range", err[:, 2].min(), err[:, 2].max())
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    gen_single()
+    gen_batch()
+    gen_gp()
