@@ -1,0 +1,218 @@
+/*
+ * mr_rl_b200 — C ABI of the B200-native rolling-microrobot environment.
+ *
+ * This is the drop-in boundary for the hot path of SuhailSama/MR_RL.  The reference has
+ * no FFI of its own (it is pure Python); the entry points below are what a ctypes/cffi
+ * binding placed behind the reference's classes would call, one per reference method:
+ *
+ *   mr_env_reset     <- MR_Env.reset            (MR_env.py:164-201)
+ *                       Simulator.reset_start_pos (MR_simulator.py:21-34)
+ *   mr_env_step      <- MR_Env.step             (MR_env.py:70-98)
+ *                       Simulator.step / simulate (MR_simulator.py:36-88)
+ *                       scipy RK45.__init__/_step_impl as driven from MR_simulator.py:42-50,90-91
+ *                       MR_Env.convert_state / end / calculate_reward (MR_env.py:100-152)
+ *   mr_env_rollout   <- utils.run_sim           (utils.py:43-61)   open-loop K-step rollout
+ *                       RL/MR_ddpg.py:268-311   closed loop with ActorNetwork.predict (:124-149)
+ *   mr_gp_predict    <- LearningModule.error / objective / predict -> sklearn GPR.predict
+ *                       (Learning_module.py:10-24,186-224)
+ *   mr_actor_forward <- ActorNetwork.predict    (RL/MR_ddpg.py:124-149)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the library never
+ *     allocates or frees caller memory and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions return 0 on success, a negative mr_status on argument / launch errors and
+ *     never throw; mr_last_error() gives the message for the calling thread;
+ *   - per-env failures (solver failed, non-finite state, noise table exhausted) are OR-ed
+ *     into the sticky per-env `status` byte instead of raising like scipy does;
+ *   - `dtype` selects the STORAGE type of state/action/observation buffers (MR_F64/MR_F32);
+ *     step-size control and the integrator always run in fp64 registers.
+ *
+ * There is no CPU fallback: every entry point launches CUDA kernels built for sm_100a.
+ */
+#ifndef MR_RL_B200_H
+#define MR_RL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_ABI_VERSION 1
+
+enum mr_status {
+    MR_OK = 0,
+    MR_ERR_ARG = -1,      /* bad argument (null pointer, n < 0, misaligned buffer, ...) */
+    MR_ERR_CUDA = -2,     /* kernel launch / CUDA runtime error */
+    MR_ERR_UNSUPPORTED = -3
+};
+
+enum mr_dtype { MR_F64 = 0, MR_F32 = 1 };
+
+enum mr_noise_mode {
+    MR_NOISE_NONE = 0,    /* sigma == 0: no draws are consumed */
+    MR_NOISE_TABLE = 1,   /* shared pre-generated standard-normal tensor (parity mode) */
+    MR_NOISE_PHILOX = 2   /* counter-based in-kernel generator (throughput mode) */
+};
+
+enum mr_env_flag {        /* bits of the per-env status byte */
+    MR_ENV_SOLVER_FAILED = 1,   /* scipy would return TOO_SMALL_STEP and then raise RuntimeError */
+    MR_ENV_NONFINITE = 2,       /* scipy check_arguments would raise ValueError */
+    MR_ENV_NOISE_OVERFLOW = 4,  /* the table noise stream of this env ran out */
+    MR_ENV_ATTEMPT_CAP = 8      /* more than the attempt cap in one env step */
+};
+
+enum mr_reward_mode {
+    MR_REWARD_CONST10 = 0,      /* MR_env.py:89  rew = 10 */
+    MR_REWARD_SHAPED = 1        /* MR_env.py:118-134 calculate_reward (defined, unused by step) */
+};
+
+enum mr_action_source {
+    MR_ACTIONS_TENSOR = 0,      /* actions[K][n][2] */
+    MR_ACTIONS_PHILOX = 1,      /* uniform in action_space, generated in-kernel */
+    MR_ACTIONS_ACTOR = 2,       /* DDPG actor MLP evaluated in-kernel on the observation */
+    MR_ACTIONS_BROADCAST = 3    /* actions[K][2], the same action for every env (utils.run_sim) */
+};
+
+/* Simulator + env parameters (MR_simulator.py:12-19, MR_env.py:34-63).  Launch scalars. */
+typedef struct mr_sim_params {
+    double a0;              /* Simulator.a0 */
+    double noise_var;       /* Simulator.noise_var (used as the STANDARD DEVIATION, MR_simulator.py:72) */
+    int32_t is_mismatched;  /* Simulator.is_mismatched */
+    int32_t mism_at_reset;  /* value of is_mismatched while reset builds the integrator
+                               (MR_env.py:181 runs before :183) */
+    double time_span;       /* 0.030 */
+    double rtol;            /* time_span / number_iterations = 3e-4 */
+    double atol;            /* 1e-4 */
+    int32_t max_timesteps;  /* 50 */
+    int32_t reward_mode;    /* mr_reward_mode */
+    double min_dist2goal;   /* 30 */
+    double bound_xy;        /* 5000  (observation_space, MR_env.py:37-39) */
+    double bound_d;         /* 80000 */
+    int32_t auto_reset;     /* rollout only: re-initialise an env after done */
+    int32_t reserved;
+    double init_low[2];     /* init_space, MR_env.py:40-42 */
+    double init_high[2];
+    double action_high[2];  /* action_space.high, MR_env.py:34-36 */
+} mr_sim_params;
+
+/* Per-env state, structure-of-arrays: one row of n elements per field. */
+typedef struct mr_env_state {
+    void* x;            /* position (storage dtype) */
+    void* y;
+    void* fx;           /* carried derivative integrator.f (stage K0 of the next step) */
+    void* fy;
+    void* h;            /* carried integrator.h_abs */
+    int32_t* counter;   /* MR_Env.counter == env steps since reset (t = t_table[counter]) */
+    int32_t* cursor;    /* table-noise draws consumed so far (MR_NOISE_TABLE only; else may be NULL) */
+    uint8_t* status;    /* sticky mr_env_flag bits */
+} mr_env_state;
+
+typedef struct mr_noise {
+    int32_t mode;          /* mr_noise_mode */
+    int32_t reserved;
+    const double* table;   /* [table_len][n]: draw-major, env-minor standard normals (fp64) */
+    int64_t table_len;     /* draws available per env */
+    uint64_t seed;         /* Philox key */
+    uint64_t offset;       /* Philox: global env-step index of this launch (caller increments) */
+    uint64_t env_base;     /* global index of local env 0 (multi-GPU sharding) */
+} mr_noise;
+
+/* t_k after k env steps since reset, t_k = fl(t_{k-1} + time_span) (MR_simulator.py:46-50). */
+typedef struct mr_time_table {
+    const double* t;       /* device, [len] */
+    int32_t len;
+    int32_t reserved;
+} mr_time_table;
+
+typedef struct mr_step_out {
+    void* obs;          /* [5][n] rows x, y, goal_x, goal_y, d (storage dtype); may be NULL */
+    void* rew;          /* [n] storage dtype; may be NULL */
+    uint8_t* done;      /* [n]; may be NULL */
+    void* state_prime;  /* [2][n] Simulator.state_prime (MR_simulator.py:87); may be NULL */
+    int64_t row_stride; /* elements between rows of obs / state_prime (0 = n) */
+} mr_step_out;
+
+int mr_abi_version(void);
+const char* mr_last_error(void);
+void mr_default_params(mr_sim_params* p);
+
+/* Fill t[0..len) on the HOST with the accumulated step times. */
+void mr_fill_time_table_host(double* t_host, int32_t len, double time_span);
+
+/*
+ * MR_Env.reset for every env with mask[i] != 0 (mask == NULL: all).  init_xy is [n][2]
+ * (storage dtype) or NULL to sample init_space with Philox (float32-rounded like
+ * gym.spaces.Box.sample).  reset_cursor != 0 rewinds the table-noise cursor to 0.
+ */
+int mr_env_reset(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
+                 const mr_noise* nz, const void* init_xy, const uint8_t* mask, int32_t reset_cursor,
+                 const mr_step_out* out, void* stream);
+
+/* MR_Env.step for n envs.  actions is [n][2] (f_t, alpha_t), storage dtype. */
+int mr_env_step(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
+                const mr_noise* nz, const mr_time_table* tt, const void* actions,
+                const mr_step_out* out, void* stream);
+
+typedef struct mr_rollout_io {
+    int32_t action_source;   /* mr_action_source */
+    int32_t k_steps;         /* env steps fused in this launch, state held in registers */
+    const void* actions;     /* TENSOR: [K][n][2]; BROADCAST: [K][2]; storage dtype */
+    const float* actor;      /* ACTOR: packed weights, see mr_actor_param_count() */
+    void* traj_xy;           /* optional [K][2][n] positions after each step (run_sim X, Y) */
+    void* traj_state_prime;  /* optional [K][2][n] */
+    uint8_t* traj_done;      /* optional [K][n] */
+    double* stats;           /* optional [MR_STATS_LEN] device accumulators (atomically added) */
+} mr_rollout_io;
+
+enum { MR_STAT_EPISODES = 0, MR_STAT_SUM_LENGTH = 1, MR_STAT_SUM_REWARD = 2, MR_STAT_GOAL = 3,
+       MR_STAT_OUT_OF_BOUNDS = 4, MR_STAT_TIMEOUT = 5, MR_STAT_ENV_STEPS = 6, MR_STAT_FAILED = 7,
+       MR_STATS_LEN = 8 };
+
+/* K fused MR_Env.step calls (utils.run_sim / the DDPG acting loop).  `out` receives the
+ * outputs of the LAST step. */
+int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
+                   const mr_noise* nz, const mr_time_table* tt, const mr_rollout_io* io,
+                   const mr_step_out* out, void* stream);
+
+/* ---- Gaussian-process inference (Learning_module.py -> sklearn GPR.predict) ----------
+ * The fitted model (GPR.X_train_, alpha_, L_, kernel_ = RBF(length_scale) + WhiteKernel(noise_level))
+ * is prepared once on the host: arrays are zero-padded from n_train to n_pad (a multiple of
+ * MR_GP_PAD) so the tiled kernels need no bounds checks.  Padded training points carry
+ * alpha = 0 and zero rows/columns of linv, so they contribute nothing. */
+#define MR_GP_PAD 128
+
+typedef struct mr_gp_model {
+    const double* x_train_scaled; /* [n_pad][dim]  GPR.X_train_ / length_scale (sklearn RBF scales first) */
+    const double* alpha;     /* [n_pad]  GPR.alpha_ (0 in the padding) */
+    const double* linv;      /* [n_pad][n_pad] row-major inverse of the lower Cholesky factor GPR.L_,
+                                upper triangle and padding zero; NULL if std is never requested */
+    int32_t n_train;
+    int32_t n_pad;
+    int32_t dim;             /* 1 (Learning_module.py) or 2 (Learning_module_2d.py) */
+    int32_t reserved;
+    double length_scale;     /* kernel_.k1.length_scale */
+    double noise_level;      /* kernel_.k2.noise_level */
+} mr_gp_model;
+
+/* mean[i] = k(q_i, X) . alpha ;  std[i] = sqrt(max(0, 1 + noise_level - |linv k(q_i, X)|^2)).
+ * q is [n_q][dim].  std may be NULL (mean only, Learning_module.py:17-18,207-208); then no
+ * workspace is needed.  workspace must hold mr_gp_workspace_bytes() bytes. */
+int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* mean, double* std,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mr_gp_workspace_bytes(const mr_gp_model* gp, int64_t n_q, int32_t want_std);
+
+/* ---- DDPG actor forward (RL/MR_ddpg.py:124-149) --------------------------------------
+ * Packed float32 parameters (input-major matrices W[in][out]):
+ *   w1[5][64] b1[64] gamma1[64] beta1[64] mean1[64] var1[64]
+ *   w2[64][64] b2[64] gamma2[64] beta2[64] mean2[64] var2[64]   w3[64][2] b3[2]          */
+int32_t mr_actor_param_count(void);
+/* obs is [5][obs_row_stride] (storage dtype), actions out is [n][2] (storage dtype). */
+int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
+                     const double action_high[2], void* actions, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MR_RL_B200_H */

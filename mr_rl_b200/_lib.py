@@ -1,0 +1,127 @@
+"""ctypes binding of libmr_rl_b200.so (the C ABI in include/mr_rl_b200.h).
+
+There is deliberately no fallback: if the CUDA library has not been built, importing any
+compute entry point raises.  Build it with ``python -m mr_rl_b200.build`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libmr_rl_b200.so")
+
+MR_F64, MR_F32 = 0, 1
+NOISE_NONE, NOISE_TABLE, NOISE_PHILOX = 0, 1, 2
+ACTIONS_TENSOR, ACTIONS_PHILOX, ACTIONS_ACTOR, ACTIONS_BROADCAST = 0, 1, 2, 3
+REWARD_CONST10, REWARD_SHAPED = 0, 1
+ENV_SOLVER_FAILED, ENV_NONFINITE, ENV_NOISE_OVERFLOW, ENV_ATTEMPT_CAP = 1, 2, 4, 8
+STATS_LEN = 8
+STAT_NAMES = ("episodes", "sum_length", "sum_reward", "goal", "out_of_bounds", "timeout", "env_steps", "failed")
+
+
+class SimParams(C.Structure):
+    _fields_ = [
+        ("a0", C.c_double), ("noise_var", C.c_double),
+        ("is_mismatched", C.c_int32), ("mism_at_reset", C.c_int32),
+        ("time_span", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
+        ("max_timesteps", C.c_int32), ("reward_mode", C.c_int32),
+        ("min_dist2goal", C.c_double), ("bound_xy", C.c_double), ("bound_d", C.c_double),
+        ("auto_reset", C.c_int32), ("reserved", C.c_int32),
+        ("init_low", C.c_double * 2), ("init_high", C.c_double * 2), ("action_high", C.c_double * 2),
+    ]
+
+
+class EnvState(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("fx", C.c_void_p), ("fy", C.c_void_p), ("h", C.c_void_p),
+                ("counter", C.c_void_p), ("cursor", C.c_void_p), ("status", C.c_void_p)]
+
+
+class Noise(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("table", C.c_void_p), ("table_len", C.c_int64),
+                ("seed", C.c_uint64), ("offset", C.c_uint64), ("env_base", C.c_uint64)]
+
+
+class TimeTable(C.Structure):
+    _fields_ = [("t", C.c_void_p), ("len", C.c_int32), ("reserved", C.c_int32)]
+
+
+class StepOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p), ("state_prime", C.c_void_p),
+                ("row_stride", C.c_int64)]
+
+
+class RolloutIO(C.Structure):
+    _fields_ = [("action_source", C.c_int32), ("k_steps", C.c_int32), ("actions", C.c_void_p), ("actor", C.c_void_p),
+                ("traj_xy", C.c_void_p), ("traj_state_prime", C.c_void_p), ("traj_done", C.c_void_p),
+                ("stats", C.c_void_p)]
+
+
+class GPModel(C.Structure):
+    _fields_ = [("x_train_scaled", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p), ("n_train", C.c_int32),
+                ("n_pad", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+                ("length_scale", C.c_double), ("noise_level", C.c_double)]
+
+
+GP_PAD = 128
+
+
+EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time_table_host", "mr_env_reset",
+           "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_actor_param_count",
+           "mr_actor_forward")
+
+_lib = None
+
+
+class MRLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises MRLibraryError if it is missing (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MRLibraryError(
+            f"{LIB_PATH} not found: mr_rl_b200 has no CPU fallback — build the CUDA library with "
+            "`python -m mr_rl_b200.build` (needs nvcc; targets sm_100a)")
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.mr_abi_version.restype = C.c_int
+    lib.mr_last_error.restype = C.c_char_p
+    lib.mr_default_params.argtypes = [P(SimParams)]
+    lib.mr_default_params.restype = None
+    lib.mr_fill_time_table_host.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+    lib.mr_fill_time_table_host.restype = None
+    lib.mr_env_reset.argtypes = [P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), C.c_void_p, C.c_void_p,
+                                 C.c_int32, P(StepOut), C.c_void_p]
+    lib.mr_env_step.argtypes = [P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), P(TimeTable), C.c_void_p,
+                                P(StepOut), C.c_void_p]
+    lib.mr_env_rollout.argtypes = [P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), P(TimeTable),
+                                   P(RolloutIO), P(StepOut), C.c_void_p]
+    lib.mr_gp_predict.argtypes = [P(GPModel), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p]
+    lib.mr_gp_workspace_bytes.argtypes = [P(GPModel), C.c_int64, C.c_int32]
+    lib.mr_gp_workspace_bytes.restype = C.c_int64
+    lib.mr_actor_param_count.restype = C.c_int32
+    lib.mr_actor_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double * 2, C.c_void_p,
+                                     C.c_void_p]
+    for f in ("mr_env_reset", "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_actor_forward"):
+        getattr(lib, f).restype = C.c_int
+    if lib.mr_abi_version() != 1:
+        raise MRLibraryError(f"ABI version mismatch: library {lib.mr_abi_version()}, binding 1")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mr_last_error().decode(errors="replace")
+        raise MRLibraryError(f"{what or 'mr_rl_b200'} failed ({rc}): {msg}")
+
+
+def default_params() -> SimParams:
+    p = SimParams()
+    load().mr_default_params(C.byref(p))
+    return p

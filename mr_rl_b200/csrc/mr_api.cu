@@ -1,0 +1,213 @@
+// Exported C ABI of the env path (include/mr_rl_b200.h): argument checks and dispatch to the
+// per-(storage dtype, noise mode) launchers.  No CPU fallback exists: every call launches CUDA.
+#include <cstdarg>
+#include <cstdio>
+
+#include "mr_common.cuh"
+
+namespace mr {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return MR_OK;
+}
+
+static Params to_params(const mr_sim_params& s) {
+    Params p;
+    p.a0 = s.a0; p.sigma = s.noise_var;
+    p.dt = s.time_span; p.rtol = s.rtol; p.atol = s.atol;
+    p.min_dist = s.min_dist2goal; p.bound_xy = s.bound_xy; p.bound_d = s.bound_d;
+    for (int i = 0; i < 2; ++i) { p.init_lo[i] = s.init_low[i]; p.init_hi[i] = s.init_high[i]; p.act_hi[i] = s.action_high[i]; }
+    p.mism = s.is_mismatched; p.mism_reset = s.mism_at_reset; p.max_steps = s.max_timesteps;
+    p.reward_mode = s.reward_mode; p.auto_reset = s.auto_reset;
+    return p;
+}
+
+template <class T>
+static StateView<T> state_view(const mr_env_state& s) {
+    StateView<T> v;
+    v.x = (T*)s.x; v.y = (T*)s.y; v.fx = (T*)s.fx; v.fy = (T*)s.fy; v.h = (T*)s.h;
+    v.counter = s.counter; v.cursor = s.cursor; v.status = s.status;
+    return v;
+}
+
+template <class T>
+static OutView<T> out_view(const mr_step_out* o, int64_t n) {
+    OutView<T> v;
+    if (!o) { v.obs = nullptr; v.rew = nullptr; v.done = nullptr; v.sp = nullptr; v.stride = n; return v; }
+    v.obs = (T*)o->obs; v.rew = (T*)o->rew; v.done = o->done; v.sp = (T*)o->state_prime;
+    v.stride = o->row_stride ? o->row_stride : n;
+    return v;
+}
+
+static NoiseView noise_view(const mr_noise* nz) {
+    NoiseView v{nullptr, 0, 0, 0, 0};
+    if (nz) { v.table = nz->table; v.table_len = nz->table_len; v.seed = nz->seed; v.offset = nz->offset; v.env_base = nz->env_base; }
+    return v;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// every row the vectorised step kernel touches must start on a 16-byte boundary
+template <class T>
+static bool rows_aligned(const mr_env_state& s, const mr_step_out* o, const void* actions, int64_t n) {
+    bool ok = aligned16(s.x) && aligned16(s.y) && aligned16(s.fx) && aligned16(s.fy) && aligned16(s.h) &&
+              aligned16(s.counter) && aligned16(actions);
+    if (o) {
+        const int64_t stride = o->row_stride ? o->row_stride : n;
+        const bool stride_ok = (stride * (int64_t)sizeof(T)) % 16 == 0;
+        if (o->obs) ok = ok && aligned16(o->obs) && stride_ok;
+        if (o->state_prime) ok = ok && aligned16(o->state_prime) && stride_ok;
+        if (o->rew) ok = ok && aligned16(o->rew);
+        if (o->done) ok = ok && aligned16(o->done);
+    }
+    return ok;
+}
+
+static int check_common(const char* fn, const mr_env_state* st, int64_t n, int dtype, const mr_sim_params* p, const mr_noise* nz) {
+    if (!st || !p) return fail(MR_ERR_ARG, "%s: null state/params", fn);
+    if (n < 0 || n > ((int64_t)1 << 31) - 1) return fail(MR_ERR_ARG, "%s: bad n=%lld", fn, (long long)n);
+    if (dtype != MR_F64 && dtype != MR_F32) return fail(MR_ERR_ARG, "%s: bad dtype %d", fn, dtype);
+    if (n > 0 && (!st->x || !st->y || !st->fx || !st->fy || !st->h || !st->counter || !st->status))
+        return fail(MR_ERR_ARG, "%s: null state row", fn);
+    const int mode = nz ? nz->mode : MR_NOISE_NONE;
+    if (mode != MR_NOISE_NONE && mode != MR_NOISE_TABLE && mode != MR_NOISE_PHILOX)
+        return fail(MR_ERR_ARG, "%s: unknown noise mode %d", fn, mode);
+    if (mode == MR_NOISE_TABLE) {
+        if (!nz->table || nz->table_len <= 0) return fail(MR_ERR_ARG, "%s: table noise without a table", fn);
+        if (!st->cursor) return fail(MR_ERR_ARG, "%s: table noise needs state.cursor", fn);
+    }
+    if (mode == MR_NOISE_NONE && p->noise_var != 0.0)
+        return fail(MR_ERR_ARG, "%s: noise_var=%g needs a noise source (table or philox)", fn, p->noise_var);
+    if (!(p->time_span > 0.0)) return fail(MR_ERR_ARG, "%s: time_span must be positive", fn);
+    return MR_OK;
+}
+
+template <class T>
+static int do_step(const mr_env_state& st, int64_t n, const Params& p, const mr_noise* nz, const TimeView& tv,
+                   const void* actions, const mr_step_out* out, cudaStream_t s) {
+    const StateView<T> sv = state_view<T>(st);
+    const OutView<T> ov = out_view<T>(out, n);
+    const NoiseView nv = noise_view(nz);
+    const bool vec_ok = rows_aligned<T>(st, out, actions, n);
+    switch (nz ? nz->mode : MR_NOISE_NONE) {
+        case MR_NOISE_TABLE: return launch_step<T, MR_NOISE_TABLE>(sv, (const T*)actions, ov, nv, tv, p, n, vec_ok, s);
+        case MR_NOISE_PHILOX: return launch_step<T, MR_NOISE_PHILOX>(sv, (const T*)actions, ov, nv, tv, p, n, vec_ok, s);
+        default: return launch_step<T, MR_NOISE_NONE>(sv, (const T*)actions, ov, nv, tv, p, n, vec_ok, s);
+    }
+}
+
+template <class T>
+static int do_reset(const mr_env_state& st, int64_t n, const Params& p, const mr_noise* nz, const void* init_xy,
+                    const uint8_t* mask, int reset_cursor, const mr_step_out* out, cudaStream_t s) {
+    const StateView<T> sv = state_view<T>(st);
+    const OutView<T> ov = out_view<T>(out, n);
+    const NoiseView nv = noise_view(nz);
+    switch (nz ? nz->mode : MR_NOISE_NONE) {
+        case MR_NOISE_TABLE: return launch_reset<T, MR_NOISE_TABLE>(sv, (const T*)init_xy, mask, reset_cursor, ov, nv, p, n, s);
+        case MR_NOISE_PHILOX: return launch_reset<T, MR_NOISE_PHILOX>(sv, (const T*)init_xy, mask, reset_cursor, ov, nv, p, n, s);
+        default: return launch_reset<T, MR_NOISE_NONE>(sv, (const T*)init_xy, mask, reset_cursor, ov, nv, p, n, s);
+    }
+}
+
+template <class T>
+static int do_rollout(const mr_env_state& st, int64_t n, const Params& p, const mr_noise* nz, const TimeView& tv,
+                      const mr_rollout_io& io, const mr_step_out* out, cudaStream_t s) {
+    RolloutView<T> rv;
+    rv.actions = (const T*)io.actions; rv.actor = io.actor; rv.traj_xy = (T*)io.traj_xy;
+    rv.traj_sp = (T*)io.traj_state_prime; rv.traj_done = io.traj_done; rv.stats = io.stats;
+    rv.k_steps = io.k_steps; rv.action_source = io.action_source;
+    const StateView<T> sv = state_view<T>(st);
+    const OutView<T> ov = out_view<T>(out, n);
+    const NoiseView nv = noise_view(nz);
+    switch (nz ? nz->mode : MR_NOISE_NONE) {
+        case MR_NOISE_TABLE: return launch_rollout<T, MR_NOISE_TABLE>(sv, rv, ov, nv, tv, p, n, s);
+        case MR_NOISE_PHILOX: return launch_rollout<T, MR_NOISE_PHILOX>(sv, rv, ov, nv, tv, p, n, s);
+        default: return launch_rollout<T, MR_NOISE_NONE>(sv, rv, ov, nv, tv, p, n, s);
+    }
+}
+
+}  // namespace mr
+
+extern "C" {
+
+int mr_abi_version(void) { return MR_ABI_VERSION; }
+const char* mr_last_error(void) { return mr::g_err; }
+
+void mr_default_params(mr_sim_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->a0 = 1.0; p->noise_var = 1.0;                 /* MR_Env.reset defaults, MR_env.py:167-168 */
+    p->time_span = 0.030; p->rtol = 0.030 / 100; p->atol = 1e-4;   /* MR_simulator.py:12-13,91 */
+    p->max_timesteps = 50; p->min_dist2goal = 30;    /* MR_env.py:62-63 */
+    p->bound_xy = 5000; p->bound_d = 80000;          /* MR_env.py:37-39 */
+    p->init_low[0] = p->init_low[1] = 100; p->init_high[0] = p->init_high[1] = 120;   /* :40-42 */
+    p->action_high[0] = 20; p->action_high[1] = 2 * 3.141592653589793;                /* :34-36 */
+}
+
+void mr_fill_time_table_host(double* t, int32_t len, double time_span) {
+    if (!t || len <= 0) return;
+    t[0] = 0.0;
+    for (int32_t k = 1; k < len; ++k) t[k] = t[k - 1] + time_span;
+}
+
+int mr_env_reset(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
+                 const void* init_xy, const uint8_t* mask, int32_t reset_cursor, const mr_step_out* out, void* stream) {
+    int rc = mr::check_common("mr_env_reset", st, n, dtype, p, nz);
+    if (rc) return rc;
+    if (n == 0) return MR_OK;
+    const mr::Params pp = mr::to_params(*p);
+    cudaStream_t s = (cudaStream_t)stream;
+    return dtype == MR_F64 ? mr::do_reset<double>(*st, n, pp, nz, init_xy, mask, reset_cursor, out, s)
+                           : mr::do_reset<float>(*st, n, pp, nz, init_xy, mask, reset_cursor, out, s);
+}
+
+int mr_env_step(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
+                const mr_time_table* tt, const void* actions, const mr_step_out* out, void* stream) {
+    int rc = mr::check_common("mr_env_step", st, n, dtype, p, nz);
+    if (rc) return rc;
+    if (n == 0) return MR_OK;
+    if (!actions) return mr::fail(MR_ERR_ARG, "mr_env_step: null actions");
+    if (!tt || !tt->t || tt->len < 2) return mr::fail(MR_ERR_ARG, "mr_env_step: time table missing");
+    const mr::Params pp = mr::to_params(*p);
+    mr::TimeView tv{tt->t, tt->len};
+    cudaStream_t s = (cudaStream_t)stream;
+    return dtype == MR_F64 ? mr::do_step<double>(*st, n, pp, nz, tv, actions, out, s)
+                           : mr::do_step<float>(*st, n, pp, nz, tv, actions, out, s);
+}
+
+int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
+                   const mr_time_table* tt, const mr_rollout_io* io, const mr_step_out* out, void* stream) {
+    int rc = mr::check_common("mr_env_rollout", st, n, dtype, p, nz);
+    if (rc) return rc;
+    if (!io || io->k_steps < 0) return mr::fail(MR_ERR_ARG, "mr_env_rollout: bad io");
+    if (n == 0 || io->k_steps == 0) return MR_OK;
+    if (!tt || !tt->t || tt->len < 2) return mr::fail(MR_ERR_ARG, "mr_env_rollout: time table missing");
+    if (io->action_source < 0 || io->action_source > MR_ACTIONS_BROADCAST)
+        return mr::fail(MR_ERR_ARG, "mr_env_rollout: unknown action source %d", io->action_source);
+    if ((io->action_source == MR_ACTIONS_TENSOR || io->action_source == MR_ACTIONS_BROADCAST) && !io->actions)
+        return mr::fail(MR_ERR_ARG, "mr_env_rollout: null actions");
+    if (io->action_source == MR_ACTIONS_ACTOR && !io->actor) return mr::fail(MR_ERR_ARG, "mr_env_rollout: null actor");
+    if (io->action_source == MR_ACTIONS_TENSOR && !mr::aligned16(io->actions))
+        return mr::fail(MR_ERR_ARG, "mr_env_rollout: actions must be 16-byte aligned");
+    if (p->auto_reset && nz == nullptr)
+        return mr::fail(MR_ERR_ARG, "mr_env_rollout: auto_reset needs mr_noise (seed) for the init sampler");
+    const mr::Params pp = mr::to_params(*p);
+    mr::TimeView tv{tt->t, tt->len};
+    cudaStream_t s = (cudaStream_t)stream;
+    return dtype == MR_F64 ? mr::do_rollout<double>(*st, n, pp, nz, tv, *io, out, s)
+                           : mr::do_rollout<float>(*st, n, pp, nz, tv, *io, out, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// Shared device-side views and helpers of the env kernels (step / reset / rollout).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/mr_rl_b200.h"
+#include "mr_core.cuh"
+
+namespace mr {
+
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+// ---- device-side views ---------------------------------------------------------------------
+template <class T>
+struct StateView {
+    T *x, *y, *fx, *fy, *h;
+    int32_t* counter;
+    int32_t* cursor;
+    uint8_t* status;
+};
+
+template <class T>
+struct OutView {
+    T* obs;           // [5][stride]
+    T* rew;
+    uint8_t* done;
+    T* sp;            // [2][stride]
+    int64_t stride;
+};
+
+struct NoiseView {
+    const double* table;
+    int64_t table_len;
+    uint64_t seed, offset, env_base;
+};
+
+struct TimeView { const double* t; int len; };
+
+__device__ __forceinline__ double time_at(const TimeView& tv, int c, double dt) {
+    if (c < tv.len) return __ldg(tv.t + c);
+    double t = __ldg(tv.t + tv.len - 1);                 // beyond the table: keep accumulating exactly
+    for (int k = tv.len - 1; k < c; ++k) t += dt;
+    return t;
+}
+
+// 16-byte vector access helpers: VEC consecutive envs of one SoA row per thread.
+template <class T, int VEC> struct Pack { T v[VEC]; };
+
+template <class T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> load_pack(const T* row, int64_t i0) {
+    Pack<T, VEC> p;
+    if constexpr (VEC == 1) { p.v[0] = row[i0]; }
+    else if constexpr (sizeof(T) * VEC == 16) {
+        const int4 raw = *reinterpret_cast<const int4*>(row + i0);
+        memcpy(&p, &raw, 16);
+    } else if constexpr (sizeof(T) * VEC == 8) {
+        const int2 raw = *reinterpret_cast<const int2*>(row + i0);
+        memcpy(&p, &raw, 8);
+    } else if constexpr (sizeof(T) * VEC == 4) {
+        const int raw = *reinterpret_cast<const int*>(row + i0);
+        memcpy(&p, &raw, 4);
+    } else if constexpr (sizeof(T) * VEC == 2) {
+        const short raw = *reinterpret_cast<const short*>(row + i0);
+        memcpy(&p, &raw, 2);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) p.v[j] = row[i0 + j];
+    }
+    return p;
+}
+
+template <class T, int VEC>
+__device__ __forceinline__ void store_pack(T* row, int64_t i0, const Pack<T, VEC>& p) {
+    if constexpr (VEC == 1) { row[i0] = p.v[0]; }
+    else if constexpr (sizeof(T) * VEC == 16) {
+        int4 raw; memcpy(&raw, &p, 16);
+        *reinterpret_cast<int4*>(row + i0) = raw;
+    } else if constexpr (sizeof(T) * VEC == 8) {
+        int2 raw; memcpy(&raw, &p, 8);
+        *reinterpret_cast<int2*>(row + i0) = raw;
+    } else if constexpr (sizeof(T) * VEC == 4) {
+        int raw; memcpy(&raw, &p, 4);
+        *reinterpret_cast<int*>(row + i0) = raw;
+    } else if constexpr (sizeof(T) * VEC == 2) {
+        short raw; memcpy(&raw, &p, 2);
+        *reinterpret_cast<short*>(row + i0) = raw;
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) row[i0 + j] = p.v[j];
+    }
+}
+
+template <int MODE> struct NoiseOf;
+template <> struct NoiseOf<MR_NOISE_NONE> { using type = NoNoise; };
+template <> struct NoiseOf<MR_NOISE_TABLE> { using type = TableNoise; };
+template <> struct NoiseOf<MR_NOISE_PHILOX> { using type = PhiloxNoise; };
+
+template <int MODE>
+__device__ __forceinline__ typename NoiseOf<MODE>::type make_noise(const NoiseView& nv, int64_t n, int64_t env,
+                                                                   int32_t cursor, uint64_t step) {
+    typename NoiseOf<MODE>::type nz;
+    if constexpr (MODE == MR_NOISE_TABLE) {
+        nz.col = nv.table + env; nz.stride = n; nz.cursor = cursor;
+        nz.len = (int32_t)nv.table_len; nz.overflow = 0;
+    } else if constexpr (MODE == MR_NOISE_PHILOX) {
+        nz.seek(nv.seed, nv.env_base + (uint64_t)env, step);
+    }
+    return nz;
+}
+
+
+// gym-style auto reset after a terminal step: the env restarts from a Philox-sampled
+// init_space position (float32-rounded like gym.spaces.Box.sample, MR_env.py:172-173).
+template <int MODE, bool MISM>
+__device__ __forceinline__ void auto_reset_env(Env& e, const NoiseView& nv, int64_t n, int64_t i, int32_t& cur,
+                                               uint64_t step, const Params& p, int& overflow) {
+    double u[4];
+    philox_uniform4(nv.seed, nv.env_base + (uint64_t)i, step, kPurposeInit, u);
+    const double x0 = (double)(float)(p.init_lo[0] + (p.init_hi[0] - p.init_lo[0]) * u[0]);
+    const double y0 = (double)(float)(p.init_lo[1] + (p.init_hi[1] - p.init_lo[1]) * u[1]);
+    const int keep = e.status;
+    auto nzr = make_noise<MODE>(nv, n, i, cur, step ^ 0x8000000000000000ull);
+    env_reset<MISM>(e, x0, y0, p.dt, p, nzr);
+    e.status |= keep;
+    if constexpr (MODE == MR_NOISE_TABLE) { cur = nzr.cursor; overflow |= nzr.overflow; }
+}
+
+
+// ---- host-side launchers, one translation unit per (storage dtype, noise mode) -----------
+template <class T, int MODE>
+int launch_step(const StateView<T>& sv, const T* actions, const OutView<T>& ov, const NoiseView& nv, const TimeView& tv,
+                const Params& p, int64_t n, bool vec_ok, cudaStream_t s);
+template <class T, int MODE>
+int launch_reset(const StateView<T>& sv, const T* init_xy, const uint8_t* mask, int reset_cursor, const OutView<T>& ov,
+                 const NoiseView& nv, const Params& p, int64_t n, cudaStream_t s);
+
+template <class T>
+struct RolloutView {
+    const T* actions;          // TENSOR [K][n][2] | BROADCAST [K][2]
+    const float* actor;        // packed actor weights
+    T* traj_xy;                // [K][2][n]
+    T* traj_sp;                // [K][2][n]
+    uint8_t* traj_done;        // [K][n]
+    double* stats;             // [MR_STATS_LEN]
+    int k_steps;
+    int action_source;
+};
+template <class T, int MODE>
+int launch_rollout(const StateView<T>& sv, const RolloutView<T>& rv, const OutView<T>& ov, const NoiseView& nv,
+                   const TimeView& tv, const Params& p, int64_t n, cudaStream_t s);
+
+}  // namespace mr

@@ -1,0 +1,253 @@
+// Gaussian-process inference for Learning_module's disturbance model (sklearn GPR.predict with
+// kernel RBF(l) + WhiteKernel(noise), normalize_y=False) and the standalone DDPG actor forward.
+//
+//   K_q[i][j]  = exp(-0.5 * |q_i/l - X_j/l|^2)                (kernels.RBF.__call__)
+//   mean[i]    = sum_j K_q[i][j] * alpha_[j]                  (_gpr.py: K_trans @ alpha_)
+//   V          = L^-1 K_q^T  ->  V[i][r] = sum_{c<=r} Linv[r][c] K_q[i][c]
+//   std[i]     = sqrt(max(0, (1 + noise) - sum_r V[i][r]^2))  (_gpr.py: diag - einsum(V.T, V))
+//
+// Kernel 1 (gp_kq_mean): FP64/SFU pipe; one warp per query row, lanes stride the training
+//   points so the K_q row is written coalesced; the mean falls out of the same exps.
+// Kernel 2 (gp_var): the variance term is a dense triangular contraction
+//   [n_q x n] x [n x n]^T, 2 * n_q * n^2 / 2 flops — the only GEMM-shaped work on the hot path.
+//   It runs on the FP64 tensor pipe (mma.sync m8n8k4 f64 = DMMA; tcgen05 has no fp64 kind),
+//   128x128 CTA tiles, cp.async double-buffered shared-memory staging, fused square-sum epilogue.
+#include <cuda_runtime.h>
+
+#include "mr_actor.cuh"
+#include "mr_common.cuh"
+
+namespace mr {
+
+// ---- kernel 1: K_q rows + mean ------------------------------------------------------------
+template <int DIM, bool WRITE_KQ>
+__global__ void __launch_bounds__(256)
+gp_kq_mean_kernel(const double* __restrict__ q, int64_t n_q, const double* __restrict__ xtr /* X_train / l */,
+                  const double* __restrict__ alpha, int n_pad, int n_train, double ls,
+                  double* __restrict__ kq /*[n_q][n_pad]*/, double* __restrict__ mean) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per query
+    if (row >= n_q) return;
+    double q0 = q[row * DIM] / ls, q1 = 0.0;             // sklearn: cdist(X / l, Y / l, "sqeuclidean")
+    if (DIM == 2) q1 = q[row * DIM + 1] / ls;
+    double acc = 0.0;
+    double* out = kq + row * (int64_t)n_pad;
+    for (int j = lane; j < n_pad; j += 32) {
+        double d2;
+        if (DIM == 1) { const double d = q0 - xtr[j]; d2 = d * d; }
+        else { const double d0 = q0 - xtr[2 * j], d1 = q1 - xtr[2 * j + 1]; d2 = d0 * d0 + d1 * d1; }
+        double k = exp(-0.5 * d2);
+        if (j >= n_train) k = 0.0;                       // padding contributes nothing
+        if (WRITE_KQ) out[j] = k;
+        acc = fma(k, alpha[j], acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) mean[row] = acc;
+}
+
+// ---- kernel 2: triangular contraction + square-sum ---------------------------------------
+constexpr int GP_BM = 128, GP_BN = 128, GP_BK = 16, GP_LD = GP_BK + 4;   // +4 doubles: conflict-free fragments
+constexpr int GP_STAGE = (GP_BM + GP_BN) * GP_LD;                         // doubles per pipeline stage
+constexpr int GP_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+gp_var_kernel(const double* __restrict__ kq, const double* __restrict__ linv, int n_pad, int64_t n_q_pad,
+              double* __restrict__ ssq) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_m = warp >> 2, warp_n = warp & 3;            // 2 x 4 warps: each 64 (M) x 32 (N)
+    const int g = lane >> 2, t4 = lane & 3;
+    const int bn = (int)gridDim.y - 1 - (int)blockIdx.y;        // heaviest column blocks first
+    const int64_t m0 = (int64_t)blockIdx.x * GP_BM;
+    const int r0 = bn * GP_BN;
+    const int k_tiles = (r0 + GP_BN) / GP_BK;                   // c <= r: columns beyond the diagonal block are zero
+
+    const double* a_src = kq + m0 * n_pad;                      // A[m][c]
+    const double* b_src = linv + (int64_t)r0 * n_pad;           // B[r][c]
+
+    auto load_stage = [&](int stage, int kt) {
+        double* As = smem + stage * GP_STAGE;
+        double* Bs = As + GP_BM * GP_LD;
+        const int c0 = kt * GP_BK;
+        // 128 rows x 16 doubles = 1024 16-byte chunks per operand; 256 threads x 4
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int chunk = tid + it * 256;
+            const int r = chunk >> 3, cc = (chunk & 7) * 2;
+            cp_async16(As + r * GP_LD + cc, a_src + (int64_t)r * n_pad + c0 + cc);
+            cp_async16(Bs + r * GP_LD + cc, b_src + (int64_t)r * n_pad + c0 + cc);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < GP_STAGES - 1; ++s) {
+        if (s < k_tiles) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < k_tiles; ++kt) {
+        cp_async_wait<GP_STAGES - 2>();
+        __syncthreads();
+        const int nxt = kt + GP_STAGES - 1;
+        if (nxt < k_tiles) load_stage(nxt % GP_STAGES, nxt);
+        cp_async_commit();
+        const double* As = smem + (kt % GP_STAGES) * GP_STAGE + (warp_m * 64) * GP_LD;
+        const double* Bs = smem + (kt % GP_STAGES) * GP_STAGE + GP_BM * GP_LD + (warp_n * 32) * GP_LD;
+#pragma unroll
+        for (int k4 = 0; k4 < GP_BK / 4; ++k4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = As[(i * 8 + g) * GP_LD + k4 * 4 + t4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[(j * 8 + g) * GP_LD + k4 * 4 + t4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: sum of squares over this CTA's 128 columns, per query row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const int64_t row = m0 + warp_m * 64 + i * 8 + g;
+        if (t4 == 0 && row < n_q_pad) atomicAdd(ssq + row, s);
+    }
+}
+
+__global__ void gp_std_finish_kernel(const double* __restrict__ ssq, int64_t n_q, double diag, double* __restrict__ std) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_q) return;
+    double v = diag - ssq[i];
+    if (v < 0.0) v = 0.0;                                      // sklearn clips negative variances to 0
+    std[i] = sqrt(v);
+}
+
+constexpr int64_t kGpChunk = 16384;   // queries per pass of the variance pipeline (K_q chunk = chunk * n_pad * 8 B)
+
+static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---- standalone actor forward -------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(128)
+actor_forward_kernel(const float* __restrict__ actor, const T* __restrict__ obs, int64_t stride, int64_t n, float hi0,
+                     float hi1, T* __restrict__ actions) {
+    extern __shared__ __align__(16) float s_actor[];
+    for (int k = threadIdx.x; k < kActorParams; k += blockDim.x) s_actor[k] = actor[k];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o5[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) o5[k] = (float)obs[k * stride + i];
+    float a2[2];
+    actor_forward_smem(s_actor, o5, hi0, hi1, a2);
+    actions[2 * i] = (T)a2[0];
+    actions[2 * i + 1] = (T)a2[1];
+}
+
+}  // namespace mr
+
+extern "C" {
+
+int64_t mr_gp_workspace_bytes(const mr_gp_model* gp, int64_t n_q, int32_t want_std) {
+    if (!gp || !want_std || n_q <= 0) return 0;
+    const int64_t chunk = mr::round_up(n_q < mr::kGpChunk ? n_q : mr::kGpChunk, mr::GP_BM);
+    return chunk * (int64_t)gp->n_pad * 8 + chunk * 8;
+}
+
+int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* mean, double* std, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+    using namespace mr;
+    if (!gp || !gp->x_train_scaled || !gp->alpha) return fail(MR_ERR_ARG, "mr_gp_predict: null model");
+    if (n_q < 0) return fail(MR_ERR_ARG, "mr_gp_predict: bad n_q");
+    if (n_q == 0) return MR_OK;
+    if (!q || !mean) return fail(MR_ERR_ARG, "mr_gp_predict: null q/mean");
+    if (gp->dim != 1 && gp->dim != 2) return fail(MR_ERR_UNSUPPORTED, "mr_gp_predict: dim must be 1 or 2");
+    if (gp->n_pad % MR_GP_PAD != 0 || gp->n_train > gp->n_pad || gp->n_train <= 0)
+        return fail(MR_ERR_ARG, "mr_gp_predict: n_pad must be a multiple of %d and >= n_train", MR_GP_PAD);
+    if (!(gp->length_scale > 0)) return fail(MR_ERR_ARG, "mr_gp_predict: bad length_scale");
+    cudaStream_t s = (cudaStream_t)stream;
+    const double inv_ls = gp->length_scale;   // kernels divide by the length scale like sklearn
+    const int threads = 256;
+    if (!std) {
+        const unsigned blocks = (unsigned)((n_q * 32 + threads - 1) / threads);
+        if (gp->dim == 1) gp_kq_mean_kernel<1, false><<<blocks, threads, 0, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, nullptr, mean);
+        else gp_kq_mean_kernel<2, false><<<blocks, threads, 0, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, nullptr, mean);
+        return check_launch("mr_gp_predict(mean)");
+    }
+    if (!gp->linv) return fail(MR_ERR_ARG, "mr_gp_predict: std requested but model has no linv");
+    if (!workspace || workspace_bytes < mr_gp_workspace_bytes(gp, n_q, 1))
+        return fail(MR_ERR_ARG, "mr_gp_predict: workspace too small (%lld < %lld)", (long long)workspace_bytes,
+                    (long long)mr_gp_workspace_bytes(gp, n_q, 1));
+    if (((uintptr_t)workspace & 15u) || ((uintptr_t)gp->linv & 15u))
+        return fail(MR_ERR_ARG, "mr_gp_predict: workspace / linv must be 16-byte aligned");
+    const int64_t chunk_cap = round_up(n_q < kGpChunk ? n_q : kGpChunk, GP_BM);
+    double* kq = (double*)workspace;
+    double* ssq = kq + chunk_cap * gp->n_pad;
+    const size_t smem = (size_t)GP_STAGES * GP_STAGE * sizeof(double);
+    cudaFuncSetAttribute(gp_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int64_t q0 = 0; q0 < n_q; q0 += kGpChunk) {
+        const int64_t nq = (n_q - q0) < kGpChunk ? (n_q - q0) : kGpChunk;
+        const int64_t nq_pad = round_up(nq, GP_BM);
+        const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
+        if (nq_pad > nq) cudaMemsetAsync(kq + nq * gp->n_pad, 0, (size_t)(nq_pad - nq) * gp->n_pad * 8, s);
+        if (gp->dim == 1) gp_kq_mean_kernel<1, true><<<blocks, threads, 0, s>>>(q + q0, nq, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, kq, mean + q0);
+        else gp_kq_mean_kernel<2, true><<<blocks, threads, 0, s>>>(q + q0 * 2, nq, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, kq, mean + q0);
+        cudaMemsetAsync(ssq, 0, (size_t)nq_pad * 8, s);
+        dim3 grid((unsigned)(nq_pad / GP_BM), (unsigned)(gp->n_pad / GP_BN));
+        gp_var_kernel<<<grid, 256, smem, s>>>(kq, gp->linv, gp->n_pad, nq_pad, ssq);
+        gp_std_finish_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(ssq, nq, 1.0 + gp->noise_level, std + q0);
+        int rc = check_launch("mr_gp_predict");
+        if (rc) return rc;
+    }
+    return MR_OK;
+}
+
+int32_t mr_actor_param_count(void) { return mr::kActorParams; }
+
+int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
+                     const double action_high[2], void* actions, void* stream) {
+    using namespace mr;
+    if (!actor || !obs || !actions || !action_high) return fail(MR_ERR_ARG, "mr_actor_forward: null argument");
+    if (n < 0) return fail(MR_ERR_ARG, "mr_actor_forward: bad n");
+    if (n == 0) return MR_OK;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    const size_t smem = kActorParams * sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t stride = obs_row_stride ? obs_row_stride : n;
+    if (dtype == MR_F64)
+        actor_forward_kernel<double><<<blocks, threads, smem, s>>>(actor, (const double*)obs, stride, n, (float)action_high[0], (float)action_high[1], (double*)actions);
+    else if (dtype == MR_F32)
+        actor_forward_kernel<float><<<blocks, threads, smem, s>>>(actor, (const float*)obs, stride, n, (float)action_high[0], (float)action_high[1], (float*)actions);
+    else return fail(MR_ERR_ARG, "mr_actor_forward: bad dtype");
+    return check_launch("mr_actor_forward");
+}
+
+}  // extern "C"

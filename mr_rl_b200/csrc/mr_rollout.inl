@@ -1,0 +1,148 @@
+// Fused K-step rollout kernel.  Included by the per-(dtype, noise mode) instantiation units
+// with MR_T and MR_MODE defined.
+#include "mr_actor.cuh"
+#include "mr_common.cuh"
+
+namespace mr {
+
+// =============================================================================================
+// Fused rollout: K env steps per launch, state in registers, one env per thread.
+// FP64-pipe bound (no HBM traffic for state between steps).
+// =============================================================================================
+template <class T, int MODE, bool MISM, int SRC>
+__global__ void __launch_bounds__(128)
+env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView nv, TimeView tv, Params p, int64_t n) {
+    extern __shared__ __align__(16) float s_actor[];
+    __shared__ double s_stats[MR_STATS_LEN];
+    if constexpr (SRC == MR_ACTIONS_ACTOR) {
+        for (int k = threadIdx.x; k < kActorParams; k += blockDim.x) s_actor[k] = io.actor[k];
+    }
+    if (threadIdx.x < MR_STATS_LEN) s_stats[threadIdx.x] = 0.0;
+    __syncthreads();
+
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    double acc[MR_STATS_LEN];
+#pragma unroll
+    for (int k = 0; k < MR_STATS_LEN; ++k) acc[k] = 0.0;
+
+    if (live) {
+        Env e;
+        e.x = (double)st.x[i]; e.y = (double)st.y[i]; e.fx = (double)st.fx[i]; e.fy = (double)st.fy[i];
+        e.h = (double)st.h[i]; e.counter = st.counter[i]; e.status = 0; e.spx = e.spy = 0.0;
+        int32_t cur = 0;
+        if constexpr (MODE == MR_NOISE_TABLE) cur = st.cursor[i];
+        Observation o;
+        o.d = sqrt(e.x * e.x + e.y * e.y); o.rew = 0.0; o.done = false; o.why = 0;
+        bool overflow = false;
+
+        for (int k = 0; k < io.k_steps; ++k) {
+            double f_t, al;
+            if constexpr (SRC == MR_ACTIONS_TENSOR) {
+                const T* a = io.actions + ((int64_t)k * n + i) * 2;
+                if constexpr (sizeof(T) == 8) { const double2 v = *reinterpret_cast<const double2*>(a); f_t = v.x; al = v.y; }
+                else { const float2 v = *reinterpret_cast<const float2*>(a); f_t = v.x; al = v.y; }
+            } else if constexpr (SRC == MR_ACTIONS_BROADCAST) {
+                f_t = (double)io.actions[2 * k]; al = (double)io.actions[2 * k + 1];
+            } else if constexpr (SRC == MR_ACTIONS_PHILOX) {
+                double u[4];
+                philox_uniform4(nv.seed, nv.env_base + (uint64_t)i, nv.offset + (uint64_t)k, kPurposeAction, u);
+                f_t = p.act_hi[0] * u[0]; al = p.act_hi[1] * u[1];   // U[0,20) x U[0,2pi)
+            } else {
+                float obs5[5] = {(float)e.x, (float)e.y, 0.f, 0.f, (float)o.d};
+                float a2[2];
+                actor_forward_smem(s_actor, obs5, (float)p.act_hi[0], (float)p.act_hi[1], a2);
+                f_t = (double)a2[0]; al = (double)a2[1];
+            }
+            auto nz = make_noise<MODE>(nv, n, i, cur, nv.offset + (uint64_t)k);
+            const double t = time_at(tv, e.counter, p.dt);
+            const double tb = t + p.dt, tb2 = tb + p.dt;
+            e.counter += 1;
+            const ActionTerms a = action_terms<MISM>(f_t, al, p);
+            sim_step<MISM>(e, t, tb, tb2, a, p, nz);
+            o = observe(e, p);
+            if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; overflow |= nz.overflow != 0; }
+            if (io.traj_xy) {
+                io.traj_xy[((int64_t)k * 2) * n + i] = (T)e.x;
+                io.traj_xy[((int64_t)k * 2 + 1) * n + i] = (T)e.y;
+            }
+            if (io.traj_sp) {
+                io.traj_sp[((int64_t)k * 2) * n + i] = (T)e.spx;
+                io.traj_sp[((int64_t)k * 2 + 1) * n + i] = (T)e.spy;
+            }
+            if (io.traj_done) io.traj_done[(int64_t)k * n + i] = o.done ? 1 : 0;
+            acc[MR_STAT_ENV_STEPS] += 1.0;
+            acc[MR_STAT_SUM_REWARD] += o.rew;
+            if (o.done) {
+                acc[MR_STAT_EPISODES] += 1.0;
+                acc[MR_STAT_SUM_LENGTH] += (double)e.counter;
+                if (o.why == 1) acc[MR_STAT_GOAL] += 1.0;
+                else if (o.why == 2) acc[MR_STAT_OUT_OF_BOUNDS] += 1.0;
+                else acc[MR_STAT_TIMEOUT] += 1.0;
+                if (p.auto_reset) {
+                    int ov = 0;
+                    auto_reset_env<MODE, MISM>(e, nv, n, i, cur, nv.offset + (uint64_t)k, p, ov);
+                    overflow |= ov != 0;
+                }
+            }
+        }
+        if (overflow) e.status |= kNoiseOverflow;
+        if (e.status) acc[MR_STAT_FAILED] += 1.0;
+
+        st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy; st.h[i] = (T)e.h;
+        st.counter[i] = e.counter;
+        if constexpr (MODE == MR_NOISE_TABLE) st.cursor[i] = cur;
+        if (e.status) st.status[i] |= (uint8_t)e.status;
+        // outputs of the LAST step (terminal observation if that step ended an episode)
+        if (out.obs) {
+            // after an auto reset e.x/e.y are the fresh start; report them with their distance
+            out.obs[i] = (T)e.x; out.obs[out.stride + i] = (T)e.y;
+            out.obs[2 * out.stride + i] = (T)0; out.obs[3 * out.stride + i] = (T)0;
+            out.obs[4 * out.stride + i] = (T)sqrt(e.x * e.x + e.y * e.y);
+        }
+        if (out.rew) out.rew[i] = (T)o.rew;
+        if (out.done) out.done[i] = o.done ? 1 : 0;
+        if (out.sp) { out.sp[i] = (T)e.spx; out.sp[out.stride + i] = (T)e.spy; }
+    }
+
+    if (io.stats) {   // warp shuffle -> shared -> one atomic per block per statistic
+#pragma unroll
+        for (int k = 0; k < MR_STATS_LEN; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&s_stats[k], v);
+        }
+        __syncthreads();
+        if (threadIdx.x < MR_STATS_LEN && s_stats[threadIdx.x] != 0.0) atomicAdd(io.stats + threadIdx.x, s_stats[threadIdx.x]);
+    }
+}
+
+
+template <class T, int MODE, bool MISM>
+static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const OutView<T>& ov, const NoiseView& nv,
+                       const TimeView& tv, const Params& p, int64_t n, cudaStream_t s) {
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    switch (rv.action_source) {
+        case MR_ACTIONS_TENSOR:
+            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_TENSOR><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+        case MR_ACTIONS_BROADCAST:
+            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_BROADCAST><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+        case MR_ACTIONS_PHILOX:
+            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_PHILOX><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+        case MR_ACTIONS_ACTOR:
+            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_ACTOR><<<blocks, threads, kActorParams * sizeof(float), s>>>(sv, rv, ov, nv, tv, p, n); break;
+        default: return fail(MR_ERR_ARG, "mr_env_rollout: unknown action source %d", rv.action_source);
+    }
+    return check_launch("mr_env_rollout");
+}
+
+template <>
+int launch_rollout<MR_T, MR_MODE>(const StateView<MR_T>& sv, const RolloutView<MR_T>& rv, const OutView<MR_T>& ov,
+                                  const NoiseView& nv, const TimeView& tv, const Params& p, int64_t n, cudaStream_t s) {
+    return p.mism ? rollout_src<MR_T, MR_MODE, true>(sv, rv, ov, nv, tv, p, n, s)
+                  : rollout_src<MR_T, MR_MODE, false>(sv, rv, ov, nv, tv, p, n, s);
+}
+
+}  // namespace mr

@@ -1,0 +1,199 @@
+// Single-step and reset kernels.  Included by the per-(dtype, noise mode) instantiation units
+// with MR_T and MR_MODE defined.
+#include "mr_common.cuh"
+
+namespace mr {
+
+// =============================================================================================
+// Single step: one launch = MR_Env.step for n envs.  HBM-bound: 60 B read + 93 B written per
+// env-step in fp64 storage; VEC consecutive envs per thread so every row access is 16 bytes.
+// =============================================================================================
+template <class T, int VEC, int MODE, bool MISM>
+__global__ void __launch_bounds__(256)
+env_step_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
+                Params p, int64_t n) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (i0 >= n) return;
+    if (VEC > 1 && i0 + VEC > n) return;   // host launches a VEC=1 tail kernel for the remainder
+
+    // all loads first: independent 16-byte requests in flight per thread
+    const Pack<T, VEC> px = load_pack<T, VEC>(st.x, i0), py = load_pack<T, VEC>(st.y, i0);
+    const Pack<T, VEC> pfx = load_pack<T, VEC>(st.fx, i0), pfy = load_pack<T, VEC>(st.fy, i0);
+    const Pack<T, VEC> ph = load_pack<T, VEC>(st.h, i0);
+    const Pack<int32_t, VEC> pc = load_pack<int32_t, VEC>(st.counter, i0);
+    const Pack<T, VEC> pa0 = load_pack<T, VEC>(actions, 2 * i0);           // [n][2] -> 2*VEC values
+    Pack<T, VEC> pa1;
+    if constexpr (VEC > 1) pa1 = load_pack<T, VEC>(actions, 2 * i0 + VEC); else pa1.v[0] = actions[2 * i0 + 1];
+    Pack<int32_t, VEC> pcur;
+    if constexpr (MODE == MR_NOISE_TABLE) pcur = load_pack<int32_t, VEC>(st.cursor, i0);
+
+    Pack<T, VEC> ox, oy, ofx, ofy, oh, od, orew, ospx, ospy;
+    Pack<int32_t, VEC> oc, ocur;
+    Pack<uint8_t, VEC> odone;
+    int any_status = 0;
+    int status_v[VEC];
+
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        Env e;
+        e.x = (double)px.v[j]; e.y = (double)py.v[j]; e.fx = (double)pfx.v[j]; e.fy = (double)pfy.v[j];
+        e.h = (double)ph.v[j]; e.counter = pc.v[j]; e.status = 0; e.spx = e.spy = 0.0;
+        double f_t, al;
+        if constexpr (VEC == 1) { f_t = (double)pa0.v[0]; al = (double)pa1.v[0]; }
+        else {
+            const int q = 2 * j;   // position inside the 2*VEC action values of this thread
+            f_t = (double)(q < VEC ? pa0.v[q] : pa1.v[q - VEC]);
+            al = (double)(q + 1 < VEC ? pa0.v[q + 1] : pa1.v[q + 1 - VEC]);
+        }
+        auto nz = make_noise<MODE>(nv, n, i0 + j, MODE == MR_NOISE_TABLE ? pcur.v[j] : 0,
+                                   nv.offset);
+        const double t = time_at(tv, e.counter, p.dt);
+        const double tb = t + p.dt, tb2 = tb + p.dt;
+        e.counter += 1;                                               // MR_env.py:80
+        const ActionTerms a = action_terms<MISM>(f_t, al, p);
+        sim_step<MISM>(e, t, tb, tb2, a, p, nz);
+        const Observation o = observe(e, p);
+        int32_t cur = 0;
+        if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; if (nz.overflow) e.status |= kNoiseOverflow; }
+        double d_out = o.d;
+        if (p.auto_reset && o.done) {   // reported obs = first obs of the new episode; done/rew = terminal step
+            int ov = 0;
+            auto_reset_env<MODE, MISM>(e, nv, n, i0 + j, cur, nv.offset, p, ov);
+            if (ov) e.status |= kNoiseOverflow;
+            d_out = sqrt(e.x * e.x + e.y * e.y);
+        }
+        if constexpr (MODE == MR_NOISE_TABLE) ocur.v[j] = cur;
+        ox.v[j] = (T)e.x; oy.v[j] = (T)e.y; ofx.v[j] = (T)e.fx; ofy.v[j] = (T)e.fy; oh.v[j] = (T)e.h;
+        oc.v[j] = e.counter; od.v[j] = (T)d_out; orew.v[j] = (T)o.rew; odone.v[j] = o.done ? 1 : 0;
+        ospx.v[j] = (T)e.spx; ospy.v[j] = (T)e.spy;
+        status_v[j] = e.status; any_status |= e.status;
+    }
+
+    store_pack<T, VEC>(st.x, i0, ox); store_pack<T, VEC>(st.y, i0, oy);
+    store_pack<T, VEC>(st.fx, i0, ofx); store_pack<T, VEC>(st.fy, i0, ofy);
+    store_pack<T, VEC>(st.h, i0, oh);
+    store_pack<int32_t, VEC>(st.counter, i0, oc);
+    if constexpr (MODE == MR_NOISE_TABLE) store_pack<int32_t, VEC>(st.cursor, i0, ocur);
+    if (out.obs) {
+        Pack<T, VEC> zero;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) zero.v[j] = (T)0;
+        store_pack<T, VEC>(out.obs, i0, ox);
+        store_pack<T, VEC>(out.obs + out.stride, i0, oy);
+        store_pack<T, VEC>(out.obs + 2 * out.stride, i0, zero);       // goal is always (0,0), MR_env.py:57
+        store_pack<T, VEC>(out.obs + 3 * out.stride, i0, zero);
+        store_pack<T, VEC>(out.obs + 4 * out.stride, i0, od);
+    }
+    if (out.rew) store_pack<T, VEC>(out.rew, i0, orew);
+    if (out.done) store_pack<uint8_t, VEC>(out.done, i0, odone);
+    if (out.sp) { store_pack<T, VEC>(out.sp, i0, ospx); store_pack<T, VEC>(out.sp + out.stride, i0, ospy); }
+    if (any_status) {                                                 // rare: sticky flags
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) if (status_v[j]) st.status[i0 + j] |= (uint8_t)status_v[j];
+    }
+}
+
+// =============================================================================================
+// Reset: MR_Env.reset for the masked envs.
+// =============================================================================================
+template <class T, int MODE>
+__global__ void __launch_bounds__(256)
+env_reset_kernel(StateView<T> st, const T* __restrict__ init_xy, const uint8_t* __restrict__ mask, int reset_cursor,
+                 OutView<T> out, NoiseView nv, Params p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mask && !mask[i]) return;
+    double x0, y0;
+    if (init_xy) { x0 = (double)init_xy[2 * i]; y0 = (double)init_xy[2 * i + 1]; }
+    else {
+        double u[4];
+        philox_uniform4(nv.seed, nv.env_base + (uint64_t)i, nv.offset, kPurposeInit, u);
+        // gym Box.sample: uniform(low, high).astype(float32)
+        x0 = (double)(float)(p.init_lo[0] + (p.init_hi[0] - p.init_lo[0]) * u[0]);
+        y0 = (double)(float)(p.init_lo[1] + (p.init_hi[1] - p.init_lo[1]) * u[1]);
+    }
+    int32_t cur = 0;
+    if constexpr (MODE == MR_NOISE_TABLE) cur = reset_cursor ? 0 : st.cursor[i];
+    auto nz = make_noise<MODE>(nv, n, i, cur, nv.offset ^ 0x8000000000000000ull);
+    Env e;
+    e.spx = e.spy = 0.0;
+    if (p.mism_reset) env_reset<true>(e, x0, y0, p.dt, p, nz);
+    else env_reset<false>(e, x0, y0, p.dt, p, nz);
+    if constexpr (MODE == MR_NOISE_TABLE) { st.cursor[i] = nz.cursor; if (nz.overflow) e.status |= kNoiseOverflow; }
+    st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy; st.h[i] = (T)e.h;
+    st.counter[i] = 0;
+    st.status[i] = (uint8_t)e.status;
+    if (out.obs) {
+        out.obs[i] = (T)e.x; out.obs[out.stride + i] = (T)e.y;
+        out.obs[2 * out.stride + i] = (T)0; out.obs[3 * out.stride + i] = (T)0;
+        out.obs[4 * out.stride + i] = (T)sqrt(e.x * e.x + e.y * e.y);
+    }
+    if (out.rew) out.rew[i] = (T)0;
+    if (out.done) out.done[i] = 0;
+    if (out.sp) { out.sp[i] = (T)e.spx; out.sp[out.stride + i] = (T)e.spy; }
+}
+
+
+template <class T, int VEC, int MODE, bool MISM>
+static void launch_step_range(const StateView<T>& sv, const T* actions, const OutView<T>& ov, const NoiseView& nv,
+                              const TimeView& tv, const Params& p, int64_t n, cudaStream_t s) {
+    const int threads = 256;
+    const int64_t items = (n + VEC - 1) / VEC;
+    const int64_t blocks = (items + threads - 1) / threads;
+    if (blocks > 0)
+        env_step_kernel<T, VEC, MODE, MISM><<<(unsigned)blocks, threads, 0, s>>>(sv, actions, ov, nv, tv, p, n);
+}
+
+template <class T>
+static StateView<T> offset_state(StateView<T> v, int64_t o) {
+    v.x += o; v.y += o; v.fx += o; v.fy += o; v.h += o; v.counter += o;
+    if (v.cursor) v.cursor += o;
+    v.status += o;
+    return v;
+}
+
+template <class T>
+static OutView<T> offset_out(OutView<T> v, int64_t o) {
+    if (v.obs) v.obs += o;
+    if (v.rew) v.rew += o;
+    if (v.done) v.done += o;
+    if (v.sp) v.sp += o;
+    return v;
+}
+
+template <class T, int MODE, bool MISM>
+static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& ov, const NoiseView& nv, const TimeView& tv,
+                        const Params& p, int64_t n, bool vec_ok, cudaStream_t s) {
+    constexpr int VEC = 16 / sizeof(T);
+    // table-noise columns are addressed by (env, n), so that mode keeps one scalar launch
+    if (vec_ok && MODE != MR_NOISE_TABLE && n >= VEC) {
+        const int64_t n_vec = (n / VEC) * VEC;
+        launch_step_range<T, VEC, MODE, MISM>(sv, act, ov, nv, tv, p, n_vec, s);
+        if (n_vec < n) {
+            NoiseView nv2 = nv; nv2.env_base += (uint64_t)n_vec;
+            launch_step_range<T, 1, MODE, MISM>(offset_state(sv, n_vec), act + 2 * n_vec, offset_out(ov, n_vec), nv2, tv,
+                                                p, n - n_vec, s);
+        }
+    } else {
+        launch_step_range<T, 1, MODE, MISM>(sv, act, ov, nv, tv, p, n, s);
+    }
+}
+
+template <>
+int launch_step<MR_T, MR_MODE>(const StateView<MR_T>& sv, const MR_T* actions, const OutView<MR_T>& ov, const NoiseView& nv,
+                               const TimeView& tv, const Params& p, int64_t n, bool vec_ok, cudaStream_t s) {
+    if (p.mism) step_ranges<MR_T, MR_MODE, true>(sv, actions, ov, nv, tv, p, n, vec_ok, s);
+    else step_ranges<MR_T, MR_MODE, false>(sv, actions, ov, nv, tv, p, n, vec_ok, s);
+    return check_launch("mr_env_step");
+}
+
+template <>
+int launch_reset<MR_T, MR_MODE>(const StateView<MR_T>& sv, const MR_T* init_xy, const uint8_t* mask, int reset_cursor,
+                                const OutView<MR_T>& ov, const NoiseView& nv, const Params& p, int64_t n, cudaStream_t s) {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    env_reset_kernel<MR_T, MR_MODE><<<blocks, threads, 0, s>>>(sv, init_xy, mask, reset_cursor, ov, nv, p, n);
+    return check_launch("mr_env_reset");
+}
+
+}  // namespace mr

@@ -1,0 +1,80 @@
+"""Device Gaussian-process inference for Learning_module's disturbance model.
+
+``DeviceGP`` holds what sklearn's fitted ``GaussianProcessRegressor`` holds (X_train_, alpha_, L_,
+kernel_ = RBF(l) + WhiteKernel(noise); Learning_module.py:30-33,122-123) in HBM, padded for the
+tiled kernels, and evaluates ``predict(q, return_std)`` with the CUDA kernels in csrc/mr_gp.cu.
+Fitting stays on the host (sklearn), exactly where the reference does it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class DeviceGP:
+    def __init__(self, X_train, alpha, L_chol, length_scale, noise_level, device="cuda"):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.MRLibraryError("DeviceGP needs a CUDA device: there is no CPU fallback")
+        X = np.asarray(X_train, dtype=np.float64)
+        X = X.reshape(len(X), -1)
+        n, d = X.shape
+        if d not in (1, 2):
+            raise ValueError("GP input dimension must be 1 (Learning_module) or 2 (Learning_module_2d)")
+        self.n_train, self.dim = n, d
+        self.n_pad = (n + L.GP_PAD - 1) // L.GP_PAD * L.GP_PAD
+        self.length_scale = float(length_scale)
+        self.noise_level = float(noise_level)
+        xs = np.zeros((self.n_pad, d))
+        xs[:n] = X / self.length_scale                      # kernels.RBF scales both operands first
+        al = np.zeros(self.n_pad)
+        al[:n] = np.asarray(alpha, dtype=np.float64).ravel()
+        self._xs = torch.from_numpy(xs).to(self.device)
+        self._alpha = torch.from_numpy(al).to(self.device)
+        self._linv = None
+        if L_chol is not None:
+            from scipy.linalg import solve_triangular
+            Linv = solve_triangular(np.asarray(L_chol, dtype=np.float64), np.eye(n), lower=True, check_finite=False)
+            W = np.zeros((self.n_pad, self.n_pad))
+            W[:n, :n] = np.tril(Linv)
+            self._linv = torch.from_numpy(W).to(self.device)
+        self._c = L.GPModel(self._xs.data_ptr(), self._alpha.data_ptr(),
+                            self._linv.data_ptr() if self._linv is not None else None,
+                            n, self.n_pad, d, 0, self.length_scale, self.noise_level)
+        self._ws = None
+        self.kernel_launches = 0
+
+    @classmethod
+    def from_sklearn(cls, gpr, device="cuda", with_std=True):
+        """From a fitted sklearn GaussianProcessRegressor with kernel_ = RBF + WhiteKernel."""
+        k = gpr.kernel_
+        if getattr(gpr, "_y_train_std", 1.0) != 1.0 or np.any(np.asarray(getattr(gpr, "_y_train_mean", 0.0)) != 0.0):
+            raise ValueError("normalize_y=True models are not supported (the reference uses the default False)")
+        return cls(gpr.X_train_, gpr.alpha_, gpr.L_ if with_std else None, k.k1.length_scale, k.k2.noise_level, device)
+
+    def predict(self, q, return_std=False):
+        """q: [n_q] or [n_q, dim] float64 (device tensor or array).  Returns mean[, std] device tensors."""
+        qt = torch.as_tensor(q) if not torch.is_tensor(q) else q
+        qt = qt.to(device=self.device, dtype=torch.float64).reshape(-1, self.dim).contiguous()
+        n_q = qt.shape[0]
+        mean = torch.empty(n_q, dtype=torch.float64, device=self.device)
+        std = torch.empty(n_q, dtype=torch.float64, device=self.device) if return_std else None
+        ws_ptr, ws_bytes = None, 0
+        if return_std:
+            if self._linv is None:
+                raise ValueError("model was built without the Cholesky factor; std is unavailable")
+            ws_bytes = int(self.lib.mr_gp_workspace_bytes(C.byref(self._c), n_q, 1))
+            if self._ws is None or self._ws.numel() * 8 < ws_bytes:
+                self._ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)
+            ws_ptr = self._ws.data_ptr()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.mr_gp_predict(C.byref(self._c), qt.data_ptr(), n_q, mean.data_ptr(),
+                                    std.data_ptr() if std is not None else None, ws_ptr, ws_bytes, stream)
+        L.check(rc, "mr_gp_predict")
+        self.kernel_launches += 1
+        return (mean, std) if return_std else mean

@@ -1,0 +1,134 @@
+"""``LearningModule`` (Learning_module.py:27-224) with GP inference on the device.
+
+Same attribute / method surface as the reference (gprX, gprY, X, Yx, Yy, a0, freq, Dx, Dy;
+estimateDisturbance, learn, error, predict) plus batched entry points for the vectorised
+control loop.  Fitting (sklearn GPR with 5 optimiser restarts) stays on the host exactly as in
+the reference; the fitted model is uploaded once and every inference call runs on the GPU.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .gp import DeviceGP
+
+
+class LearningModule:
+    def __init__(self, device="cuda"):
+        from sklearn.gaussian_process import GaussianProcessRegressor
+        from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+        kernel = RBF(length_scale=1.0, length_scale_bounds=(1e-2, 10.0)) + WhiteKernel()     # Learning_module.py:30
+        self.gprX = GaussianProcessRegressor(kernel=kernel, n_restarts_optimizer=5)
+        self.gprY = GaussianProcessRegressor(kernel=kernel, n_restarts_optimizer=5)
+        self.device = device
+        self.X, self.Yx, self.Yy = [], [], []
+        self.a0 = 0
+        self.f = 0
+        self.Dx = 0
+        self.Dy = 0
+        self.freq = 0
+        self._dx = self._dy = None
+
+    # ---- host-side preprocessing, as in the reference ------------------------------------------
+    @staticmethod
+    def _velocities(px, py, time):
+        from scipy.ndimage import uniform_filter1d
+        N = int(1 / 0.035 / 2)                                   # Learning_module.py:47,74
+        px = uniform_filter1d(px, N, mode="nearest")
+        py = uniform_filter1d(py, N, mode="nearest")
+        vx = uniform_filter1d(np.gradient(px, time), int(N / 2), mode="nearest")
+        vy = uniform_filter1d(np.gradient(py, time), int(N / 2), mode="nearest")
+        return N, px, py, vx, vy
+
+    def estimateDisturbance(self, px, py, time):
+        """Learning_module.py:46-59: drift = mean filtered velocity of an idle run."""
+        N, _, _, vx, vy = self._velocities(np.asarray(px, float), np.asarray(py, float), np.asarray(time, float))
+        self.Dx = np.mean(vx[N:-N])
+        self.Dy = np.mean(vy[N:-N])
+
+    def learn(self, px, py, alpha_sim, time, actions):
+        """Learning_module.py:63-140: a0 estimate + two GPR fits (host), then upload to the device."""
+        actions = np.asarray(actions, float)
+        freq = actions[0, 0]
+        alpha = actions[:, 1]
+        time = np.asarray(time, float) - time[0]
+        N, px, py, vx, vy = self._velocities(np.asarray(px, float), np.asarray(py, float), time)
+        speed = np.sqrt((vx - self.Dx) ** 2 + (vy - self.Dy) ** 2)
+        alpha_sim = np.asarray(alpha_sim, float)
+        off = np.argwhere(alpha >= 500)                          # controller-off frames, :89-100
+        if len(off) > 0:
+            cut = int(off[0]) - 1
+            alpha_sim, vx, vy, speed = alpha_sim[:cut], vx[:cut], vy[:cut], speed[:cut]
+        alpha_sim, vx, vy, speed = alpha_sim[N:-N], vx[N:-N], vy[N:-N], speed[N:-N]
+        a0 = np.median(speed / freq)
+        X = alpha_sim.reshape(-1, 1)
+        Yx = vx - a0 * freq * np.cos(alpha_sim)
+        Yy = vy - a0 * freq * np.sin(alpha_sim)
+        self.gprX.fit(X, Yx)
+        self.gprY.fit(X, Yy)
+        self.X, self.Yx, self.Yy = X, Yx, Yy
+        self.a0, self.freq = a0, freq
+        self.upload()
+        return a0
+
+    def upload(self):
+        """Copy the fitted sklearn models into HBM."""
+        self._dx = DeviceGP.from_sklearn(self.gprX, self.device)
+        self._dy = DeviceGP.from_sklearn(self.gprY, self.device)
+
+    def set_models(self, gprX, gprY, a0, freq, Dx=0.0, Dy=0.0):
+        """Install already-fitted sklearn GPRs (e.g. fixed kernels, optimizer=None)."""
+        self.gprX, self.gprY, self.a0, self.freq, self.Dx, self.Dy = gprX, gprY, a0, freq, Dx, Dy
+        self.X = gprX.X_train_
+        self.upload()
+
+    # ---- batched device inference ------------------------------------------------------------------
+    def gp_batch(self, alpha, return_std=True):
+        """GP posterior at headings alpha [N] -> (muX, muY[, sigX, sigY]) device tensors."""
+        if return_std:
+            mx, sx = self._dx.predict(alpha, True)
+            my, sy = self._dy.predict(alpha, True)
+            return mx, my, sx, sy
+        return self._dx.predict(alpha), self._dy.predict(alpha)
+
+    def error_batch(self, vd):
+        """LearningModule.error for vd [N, 2] (device tensor)."""
+        vd = torch.as_tensor(vd, dtype=torch.float64, device=self.device)
+        return self.gp_batch(torch.atan2(vd[:, 1], vd[:, 0]), True)
+
+    def velocity_model(self, f, alpha):
+        """v_pred = a0*f*[cos a, sin a] + [muX, muY]  (main.py:154-155), batched."""
+        alpha = torch.as_tensor(alpha, dtype=torch.float64, device=self.device)
+        f = torch.as_tensor(f, dtype=torch.float64, device=self.device)
+        mx, my = self.gp_batch(alpha, False)
+        return self.a0 * f * torch.cos(alpha) + mx, self.a0 * f * torch.sin(alpha) + my
+
+    # ---- the reference's scalar surface ----------------------------------------------------------------
+    def error(self, vd):
+        """Learning_module.py:186-196 -> (muX, muY, sigX, sigY), each shape (1,)."""
+        a = torch.tensor([math.atan2(vd[1], vd[0])], dtype=torch.float64, device=self.device)
+        out = torch.stack(self.gp_batch(a, True)).cpu().numpy()
+        return out[0], out[1], out[2], out[3]
+
+    def _objective(self, alpha, vd):
+        """objective, Learning_module.py:10-24, with the GP means evaluated on the device."""
+        a = torch.tensor([float(alpha)], dtype=torch.float64, device=self.device)
+        mu = torch.stack(self.gp_batch(a, False)).cpu().numpy()
+        mux, muy = mu[0], mu[1]
+        a0f = self.a0 * self.freq
+        return (a0f ** 2 + (mux + self.Dx - vd[0]) ** 2 + 2 * a0f * np.cos(alpha) * (mux + self.Dx - vd[0])
+                + (muy + self.Dy - vd[1]) ** 2 + 2 * a0f * np.sin(alpha) * (muy + self.Dy - vd[1]))
+
+    def predict(self, vd):
+        """Learning_module.py:198-224: bounded scalar minimisation of the objective over alpha, then
+        the posterior at the minimiser.  The minimiser itself runs on the host (scipy), each objective
+        evaluation on the device."""
+        from scipy.optimize import minimize_scalar
+        result = minimize_scalar(lambda a: float(np.ravel(self._objective(a, vd))[0]), method="Bounded",
+                                 bounds=[-np.pi, np.pi])
+        X = np.array(result.x)
+        a = torch.tensor([float(result.x)], dtype=torch.float64, device=self.device)
+        out = torch.stack(self.gp_batch(a, True)).cpu().numpy()
+        return X, out[0], out[1], out[2], out[3]

@@ -1,0 +1,392 @@
+"""VecMREnv — the batched, device-resident MR_Env (reference: MR_env.py:21-229, MR_simulator.py:8-94).
+
+Same gym surface as the reference (``reset`` / ``step`` / ``observation_space`` / ``action_space`` /
+``init_space`` / ``last_pos`` / ``state_prime`` / ``counter``), vectorised over ``num_envs`` envs
+whose state lives structure-of-arrays in HBM.  Every method launches hand-written sm_100a
+kernels through the C ABI (include/mr_rl_b200.h); there is no CPU path.
+
+PyTorch is used for device memory, streams and (optionally) torch.distributed — nothing else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .spaces import Box
+
+_DT = {torch.float64: L.MR_F64, torch.float32: L.MR_F32}
+_NOISE = {"none": L.NOISE_NONE, "table": L.NOISE_TABLE, "philox": L.NOISE_PHILOX}
+_PAD = 16          # rows are padded so every SoA row starts 16-byte aligned for any dtype
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class VecMREnv:
+    """``num_envs`` independent MR_Env instances stepped by one kernel launch.
+
+    Parameters
+    ----------
+    num_envs : int
+    device : torch device (must be CUDA)
+    dtype : torch.float64 (parity: 1e-9) or torch.float32 (storage only; 1e-4)
+    noise : "philox" (in-kernel counter-based generator), "table" (shared pre-generated
+        standard-normal tensor ``noise_table[L, num_envs]`` — the parity mode) or "none"
+    seed, env_base : Philox key and the global index of local env 0 (sharding across GPUs
+        keeps trajectories independent of the number of ranks)
+    auto_reset : restart an env from ``init_space`` right after a terminal step
+    reward_mode : "const" (rew = 10, MR_env.py:89) or "shaped" (calculate_reward, MR_env.py:118-134)
+    """
+
+    def __init__(self, num_envs, device="cuda", dtype=torch.float64, noise="philox", seed=0, env_base=0,
+                 auto_reset=False, reward_mode="const", noise_table=None, time_table_len=4096):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.MRLibraryError("VecMREnv needs a CUDA device: there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if dtype not in _DT:
+            raise ValueError("dtype must be torch.float64 or torch.float32")
+        self.num_envs = int(num_envs)
+        self.dtype = dtype
+        self._dt = _DT[dtype]
+        n = self.num_envs
+        self._np = npad = (n + _PAD - 1) // _PAD * _PAD
+        dev = self.device
+
+        # --- spaces and constants, MR_env.py:34-63 -------------------------------------------
+        self.action_space = Box(low=np.array([0, 0]), high=np.array([20, np.pi * 2]))
+        self.observation_space = Box(low=np.array([-5000, -5000, -5000, -5000, 0]),
+                                     high=np.array([5000, 5000, 5000, 5000, 80000]))
+        self.init_space = Box(low=np.array([100, 100]), high=np.array([120, 120]))
+        self.max_timesteps = 50
+        self.min_dist2goal = 30
+        self.init_goal = np.zeros(2)
+
+        # --- Simulator parameters, MR_simulator.py:12-19 --------------------------------------
+        self.params = L.default_params()
+        self.params.a0 = 0.0
+        self.params.noise_var = 0.0
+        self.params.auto_reset = 1 if auto_reset else 0
+        self.params.reward_mode = {"const": L.REWARD_CONST10, "shaped": L.REWARD_SHAPED}[reward_mode]
+        self.number_iterations = 100
+
+        # --- device state: SoA rows --------------------------------------------------------------
+        self._state = torch.zeros(5, npad, dtype=dtype, device=dev)          # x, y, fx, fy, h
+        self._counter = torch.zeros(npad, dtype=torch.int32, device=dev)
+        self._cursor = torch.zeros(npad, dtype=torch.int32, device=dev)
+        self._status = torch.zeros(npad, dtype=torch.uint8, device=dev)
+        self._obs = torch.zeros(5, npad, dtype=dtype, device=dev)            # x, y, gx, gy, d
+        self._rew = torch.zeros(npad, dtype=dtype, device=dev)
+        self._done = torch.zeros(npad, dtype=torch.uint8, device=dev)
+        self._sp = torch.zeros(2, npad, dtype=dtype, device=dev)             # Simulator.state_prime
+        self._stats = torch.zeros(L.STATS_LEN, dtype=torch.float64, device=dev)
+        tt = np.zeros(int(time_table_len), dtype=np.float64)
+        self.lib.mr_fill_time_table_host(tt.ctypes.data_as(C.c_void_p), len(tt), self.params.time_span)
+        self._tt = torch.from_numpy(tt).to(dev)
+
+        self._c_state = L.EnvState(*[_ptr(self._state[i]) for i in range(5)], _ptr(self._counter),
+                                   _ptr(self._cursor), _ptr(self._status))
+        self._c_tt = L.TimeTable(_ptr(self._tt), len(tt), 0)
+        self._c_out = L.StepOut(_ptr(self._obs), _ptr(self._rew), _ptr(self._done), _ptr(self._sp), npad)
+        self._c_out_lean = L.StepOut(_ptr(self._obs), _ptr(self._rew), _ptr(self._done), C.c_void_p(0), npad)
+
+        # --- noise -----------------------------------------------------------------------------
+        self.noise_kind = noise
+        self._noise_table = None
+        self._c_noise = L.Noise(_NOISE[noise], 0, C.c_void_p(0), 0, int(seed) & (2**64 - 1), 0, int(env_base))
+        if noise == "table":
+            if noise_table is None:
+                raise ValueError("noise='table' needs noise_table[L, num_envs] (standard normals, float64)")
+            self.set_noise_table(noise_table)
+        self._step_index = 0
+        self.want_state_prime = True
+        self._pinned = {}
+        self.kernel_launches = 0
+
+    # ---- properties mirroring the reference attributes ------------------------------------
+    @property
+    def a0(self):
+        return self.params.a0
+
+    @property
+    def noise_var(self):
+        return self.params.noise_var
+
+    @property
+    def is_mismatched(self):
+        return bool(self.params.is_mismatched)
+
+    @property
+    def time_span(self):
+        return self.params.time_span
+
+    @property
+    def last_pos(self):
+        """[N, 2] positions (MR_Env.last_pos / Simulator.last_state)."""
+        return self._state[:2, :self.num_envs].t()
+
+    @property
+    def state_prime(self):
+        """[N, 2] last RHS evaluation (Simulator.state_prime, MR_simulator.py:87)."""
+        return self._sp[:, :self.num_envs].t()
+
+    @property
+    def counter(self):
+        return self._counter[:self.num_envs]
+
+    @property
+    def obs(self):
+        """[N, 5] view of the SoA observation rows [x, y, goal_x, goal_y, distance]."""
+        return self._obs[:, :self.num_envs].t()
+
+    @property
+    def status(self):
+        return self._status[:self.num_envs]
+
+    @property
+    def stats(self):
+        return self._stats
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_noise_table(self, table):
+        t = torch.as_tensor(table, dtype=torch.float64).to(self.device).contiguous()
+        if t.dim() != 2 or t.shape[1] != self.num_envs:
+            raise ValueError(f"noise_table must be [L, {self.num_envs}] (draw-major), got {tuple(t.shape)}")
+        self._noise_table = t
+        self._c_noise.table = t.data_ptr()
+        self._c_noise.table_len = t.shape[0]
+
+    def _noise_for(self, sigma):
+        """sigma == 0 consumes no draws unless the parity table is in use (cursor discipline)."""
+        nz = self._c_noise
+        if self.noise_kind == "table":
+            nz.mode = L.NOISE_TABLE
+        elif sigma == 0.0:
+            nz.mode = L.NOISE_NONE
+        elif self.noise_kind == "philox":
+            nz.mode = L.NOISE_PHILOX
+        else:
+            raise ValueError("noise_var != 0 needs noise='philox' or noise='table'")
+        nz.offset = self._step_index
+        return nz
+
+    # ---- MR_Env.reset, MR_env.py:164-201 -----------------------------------------------------
+    def reset(self, init=None, noise_var=1, a0=1, is_mismatched=False, mask=None, reset_cursor=True):
+        """Reset all envs (or those with ``mask[i] != 0``).  ``init``: None (sample init_space on
+        device), a (2,) position for every env, or an [N, 2] tensor.  Returns obs [N, 5]."""
+        n = self.num_envs
+        p = self.params
+        if mask is not None and (float(noise_var) != p.noise_var or float(a0) != p.a0
+                                 or bool(is_mismatched) != bool(p.is_mismatched)):
+            raise ValueError("a masked reset cannot change noise_var / a0 / is_mismatched (launch scalars)")
+        p.mism_at_reset = p.is_mismatched          # the integrator is built before the flag changes (:181 vs :183)
+        p.noise_var = float(noise_var)
+        p.a0 = float(a0)
+        init_t = None
+        if init is not None:
+            init_t = torch.as_tensor(np.asarray(init) if not torch.is_tensor(init) else init)
+            init_t = init_t.to(device=self.device, dtype=self.dtype)
+            if init_t.dim() == 1:
+                init_t = init_t.reshape(1, 2).expand(n, 2)
+            init_t = init_t.contiguous()
+            if tuple(init_t.shape) != (n, 2):
+                raise ValueError(f"init must be (2,) or ({n}, 2)")
+        mask_t = None
+        if mask is not None:
+            mask_t = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        nz = self._noise_for(p.noise_var)
+        rc = self.lib.mr_env_reset(C.byref(self._c_state), n, self._dt, C.byref(p), C.byref(nz), _ptr(init_t),
+                                   _ptr(mask_t), 1 if reset_cursor else 0, C.byref(self._c_out), self._stream())
+        L.check(rc, "mr_env_reset")
+        self.kernel_launches += 1
+        self._step_index += 1
+        p.is_mismatched = 1 if is_mismatched else 0
+        p.mism_at_reset = p.is_mismatched
+        return self.obs
+
+    # ---- MR_Env.step, MR_env.py:70-98 -----------------------------------------------------------
+    def step(self, actions):
+        """actions: [N, 2] (f_t, alpha_t) device tensor.  Returns (obs [N,5], rew [N], done [N] uint8, info).
+        The returned tensors are views of buffers that the next step overwrites."""
+        n = self.num_envs
+        if not torch.is_tensor(actions):
+            return self.step_host(actions)
+        a = actions
+        if a.device != self.device or a.dtype != self.dtype or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=self.dtype).contiguous()
+        if a.numel() != 2 * n:
+            raise ValueError(f"actions must be [{n}, 2]")
+        nz = self._noise_for(self.params.noise_var)
+        out = self._c_out if self.want_state_prime else self._c_out_lean
+        rc = self.lib.mr_env_step(C.byref(self._c_state), n, self._dt, C.byref(self.params), C.byref(nz),
+                                  C.byref(self._c_tt), _ptr(a), C.byref(out), self._stream())
+        L.check(rc, "mr_env_step")
+        self.kernel_launches += 1
+        self._step_index += 1
+        return self.obs, self._rew[:n], self._done[:n], {}
+
+    def _pinned_buf(self, key, shape, dtype):
+        b = self._pinned.get(key)
+        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
+            b = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[key] = b
+        return b
+
+    def step_host(self, actions):
+        """The reference-facing call with HOST buffers: numpy actions [N, 2] in, numpy
+        (obs [N,5], rew [N], done [N] bool) out.  Copies go through pinned staging buffers on the
+        current stream; the call returns after the device->host copies have completed."""
+        n = self.num_envs
+        a_np = np.ascontiguousarray(np.asarray(actions, dtype=np.float64 if self.dtype == torch.float64 else np.float32))
+        if a_np.size != 2 * n:
+            raise ValueError(f"actions must be [{n}, 2]")
+        a_pin = self._pinned_buf("act", (n, 2), self.dtype)
+        a_pin.numpy()[...] = a_np.reshape(n, 2)
+        a_dev = self._pinned.get("act_dev")
+        if a_dev is None:
+            a_dev = self._pinned["act_dev"] = torch.empty(n, 2, dtype=self.dtype, device=self.device)
+        a_dev.copy_(a_pin, non_blocking=True)
+        self.step(a_dev)
+        o_pin = self._pinned_buf("obs", (5, n), self.dtype)
+        r_pin = self._pinned_buf("rew", (n,), self.dtype)
+        d_pin = self._pinned_buf("done", (n,), torch.uint8)
+        o_pin.copy_(self._obs[:, :n], non_blocking=True)
+        r_pin.copy_(self._rew[:n], non_blocking=True)
+        d_pin.copy_(self._done[:n], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return o_pin.numpy().T, r_pin.numpy(), d_pin.numpy().astype(bool), {}
+
+    # ---- fused K-step rollout: utils.run_sim (utils.py:43-61) / the DDPG acting loop --------------
+    def rollout(self, actions=None, k_steps=None, policy=None, record=False, record_state_prime=False,
+                record_done=False, accumulate_stats=True):
+        """K env steps in ONE launch with the state held in registers.
+
+        actions : [K, N, 2] per-env actions, or [K, 2] / [K, >=2] one action row for every env
+                  (what utils.run_sim does), or None with ``policy``:
+        policy  : "random" -> U[0,20) x U[0,2pi) generated in-kernel (Philox);
+                  a packed float32 actor tensor (see actor.pack_actor) -> DDPG actor in the loop.
+        Returns dict(obs, rew, done[, xy [K,2,N], state_prime [K,2,N], done_traj [K,N]]).
+        """
+        n = self.num_envs
+        io = L.RolloutIO()
+        keep = []
+        if actions is not None:
+            a = torch.as_tensor(actions) if not torch.is_tensor(actions) else actions
+            a = a.to(device=self.device, dtype=self.dtype)
+            if a.dim() == 2:
+                a = a[:, :2].contiguous()
+                io.action_source = L.ACTIONS_BROADCAST
+            elif a.dim() == 3 and a.shape[1] == n and a.shape[2] == 2:
+                a = a.contiguous()
+                io.action_source = L.ACTIONS_TENSOR
+            else:
+                raise ValueError(f"actions must be [K, {n}, 2] or [K, 2]")
+            k = a.shape[0]
+            io.actions = a.data_ptr()
+            keep.append(a)
+        elif isinstance(policy, str) and policy == "random":
+            io.action_source = L.ACTIONS_PHILOX
+            k = int(k_steps)
+        elif torch.is_tensor(policy):
+            w = policy.to(device=self.device, dtype=torch.float32).contiguous()
+            if w.numel() != self.lib.mr_actor_param_count():
+                raise ValueError("actor tensor has the wrong number of parameters (use actor.pack_actor)")
+            io.action_source = L.ACTIONS_ACTOR
+            io.actor = w.data_ptr()
+            keep.append(w)
+            k = int(k_steps)
+        else:
+            raise ValueError("give actions or policy")
+        io.k_steps = k
+        res = {}
+        if record:
+            res["xy"] = torch.empty(k, 2, n, dtype=self.dtype, device=self.device)
+            io.traj_xy = res["xy"].data_ptr()
+        if record_state_prime:
+            res["state_prime"] = torch.empty(k, 2, n, dtype=self.dtype, device=self.device)
+            io.traj_state_prime = res["state_prime"].data_ptr()
+        if record_done:
+            res["done_traj"] = torch.empty(k, n, dtype=torch.uint8, device=self.device)
+            io.traj_done = res["done_traj"].data_ptr()
+        if accumulate_stats:
+            io.stats = self._stats.data_ptr()
+        nz = self._noise_for(self.params.noise_var)
+        rc = self.lib.mr_env_rollout(C.byref(self._c_state), n, self._dt, C.byref(self.params), C.byref(nz),
+                                     C.byref(self._c_tt), C.byref(io), C.byref(self._c_out), self._stream())
+        L.check(rc, "mr_env_rollout")
+        self.kernel_launches += 1
+        self._step_index += k
+        res.update(obs=self.obs, rew=self._rew[:n], done=self._done[:n])
+        return res
+
+    # ---- episode statistics (NCCL all-reduce is the only collective of the path) -------------------
+    def reset_stats(self):
+        self._stats.zero_()
+
+    def allreduce_stats(self, group=None):
+        """Sum the episode-statistics vector over all ranks (torch.distributed, NCCL on GPUs)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self._stats, op=dist.ReduceOp.SUM, group=group)
+        return self.stats_dict()
+
+    def stats_dict(self):
+        v = self._stats.tolist()
+        d = dict(zip(L.STAT_NAMES, v))
+        d["mean_episode_length"] = d["sum_length"] / d["episodes"] if d["episodes"] else math.nan
+        return d
+
+    # ---- failure reporting: the reference raises from scipy; kernels set sticky flags ---------------
+    def check_status(self):
+        bad = self._status[:self.num_envs]
+        flags = int(bad.max().item()) if self.num_envs else 0
+        if flags == 0:
+            return
+        idx = torch.nonzero(bad)[:8, 0].tolist()
+        if flags & L.ENV_NOISE_OVERFLOW:
+            raise L.MRLibraryError(f"noise table exhausted for envs {idx}")
+        if flags & L.ENV_NONFINITE:
+            raise ValueError(f"non-finite state in envs {idx} (scipy: 'All components of the initial state `y0` must be finite')")
+        raise RuntimeError(f"integrator failed in envs {idx} (scipy: 'Attempt to step on a failed or finished solver')")
+
+    # ---- checkpoint / resume ----------------------------------------------------------------------------
+    def state_dict(self):
+        p = self.params
+        return {
+            "state": self._state.clone(), "counter": self._counter.clone(), "cursor": self._cursor.clone(),
+            "status": self._status.clone(), "stats": self._stats.clone(), "step_index": self._step_index,
+            "params": {"a0": p.a0, "noise_var": p.noise_var, "is_mismatched": int(p.is_mismatched)},
+            "seed": int(self._c_noise.seed), "env_base": int(self._c_noise.env_base),
+        }
+
+    def load_state_dict(self, sd):
+        self._state.copy_(sd["state"]); self._counter.copy_(sd["counter"]); self._cursor.copy_(sd["cursor"])
+        self._status.copy_(sd["status"]); self._stats.copy_(sd["stats"])
+        self._step_index = int(sd["step_index"])
+        self.params.a0 = sd["params"]["a0"]; self.params.noise_var = sd["params"]["noise_var"]
+        self.params.is_mismatched = self.params.mism_at_reset = sd["params"]["is_mismatched"]
+        self._c_noise.seed = sd["seed"]; self._c_noise.env_base = sd["env_base"]
+
+    # ---- no-op hooks kept for drop-in compatibility (MR_env.py:203-229) --------------------------------
+    def render(self, mode="human"):
+        return None
+
+    def close(self):
+        return None
+
+
+def shard_range(num_envs_total, rank, world_size):
+    """Contiguous env-index shard of rank r: [r*N/G, (r+1)*N/G)."""
+    per = num_envs_total // world_size
+    rem = num_envs_total % world_size
+    start = rank * per + min(rank, rem)
+    return start, per + (1 if rank < rem else 0)

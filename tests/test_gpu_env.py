@@ -1,0 +1,338 @@
+"""GPU parity tests proper: the CUDA env path, called through the C ABI (ctypes, via VecMREnv),
+against (a) the golden vectors recorded from the live reference and (b) the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): done flags, step counters and noise-draw
+counts bit-exact; positions / observations / rewards within 1e-9 relative in fp64 storage and
+1e-4 in fp32 storage."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import mr_oracle as mo
+from test_oracle_golden import SINGLE_CASES
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-9
+FP32_TOL = 1e-4
+
+
+def make_env(n, **kw):
+    from mr_rl_b200 import VecMREnv
+    return VecMREnv(n, device="cuda:0", **kw)
+
+
+def step_through(env, actions, record_cursor=True):
+    """actions [T, N, 2] -> dict of [T, N, ...] numpy arrays using the single-step kernel."""
+    T, N = actions.shape[:2]
+    out = {k: [] for k in ("pos", "obs", "done", "counter", "sp", "cursor", "rew", "carry")}
+    a_dev = torch.as_tensor(actions, device=env.device, dtype=env.dtype)
+    for k in range(T):
+        obs, rew, done, _ = env.step(a_dev[k])
+        out["pos"].append(env.last_pos.cpu().numpy().copy())
+        out["obs"].append(obs.cpu().numpy().copy())
+        out["done"].append(done.cpu().numpy().copy())
+        out["rew"].append(rew.cpu().numpy().copy())
+        out["counter"].append(env.counter.cpu().numpy().copy())
+        out["sp"].append(env.state_prime.cpu().numpy().copy())
+        out["cursor"].append(env._cursor[:N].cpu().numpy().copy())
+        out["carry"].append(env._state[2:5, :N].t().cpu().numpy().copy())
+    return {k: np.stack(v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_single_env_step_kernel_matches_live_reference(golden_single, name):
+    g = golden_single.case(name)
+    sig, a0, mism, prior = g["params"]
+    z = g["z"]
+    env = make_env(1, noise="table", noise_table=z[:, None])
+    env.params.is_mismatched = int(prior)           # stale flag from a previous episode (MR_env.py:181 vs :183)
+    obs0 = env.reset(init=np.asarray(g["init"], dtype=np.float64), noise_var=sig, a0=a0, is_mismatched=bool(mism))
+    assert rel_err(obs0.cpu().numpy()[0], g["reset_obs"]) < FP64_TOL
+    assert int(env._cursor[0]) == int(g["reset_cursor"])
+    assert rel_err(env._state[4, 0].item(), g["reset_carry_h"]) < FP64_TOL
+    assert rel_err(env.state_prime.cpu().numpy()[0], g["reset_state_prime"]) < FP64_TOL
+    r = step_through(env, g["actions"][:, None, :2])
+    assert np.array_equal(r["done"][:, 0], g["done"])
+    assert np.array_equal(r["counter"][:, 0], g["counter"])
+    assert np.array_equal(r["cursor"][:, 0], g["cursor"])           # same number of noise draws every step
+    assert np.all(r["rew"] == 10.0)
+    assert rel_err(r["pos"][:, 0], g["pos"]) < FP64_TOL
+    assert rel_err(r["obs"][:, 0], g["obs"]) < FP64_TOL
+    assert rel_err(r["sp"][:, 0], g["state_prime"]) < FP64_TOL
+    assert rel_err(r["carry"][:, 0, :2], g["carry_f"]) < FP64_TOL
+    assert rel_err(r["carry"][:, 0, 2], g["carry_h"]) < FP64_TOL
+    env.check_status()
+
+
+@pytest.mark.parametrize("name", ["c1_sigma1", "c1_mismatch_circle", "c1_sigma0", "noisefree_mismatch"])
+def test_fused_rollout_matches_live_reference(golden_single, name):
+    """utils.run_sim equivalent: ONE launch for the whole episode (broadcast action rows)."""
+    g = golden_single.case(name)
+    sig, a0, mism, prior = g["params"]
+    T = len(g["actions"])
+    env = make_env(1, noise="table", noise_table=g["z"][:, None], time_table_len=64)   # also exercises the t fallback
+    env.reset(init=np.asarray(g["init"], dtype=np.float64), noise_var=sig, a0=a0, is_mismatched=bool(mism))
+    res = env.rollout(actions=torch.as_tensor(g["actions"][:, :2]), record=True, record_state_prime=True, record_done=True)
+    assert rel_err(res["xy"][:, :, 0].cpu().numpy(), g["pos"]) < FP64_TOL
+    assert rel_err(res["state_prime"][:, :, 0].cpu().numpy(), g["state_prime"]) < FP64_TOL
+    assert np.array_equal(res["done_traj"][:, 0].cpu().numpy(), g["done"])
+    assert int(env._cursor[0]) == int(g["cursor"][-1])
+    assert int(env.counter[0]) == T
+    assert rel_err(res["obs"].cpu().numpy()[0], g["obs"][-1]) < FP64_TOL
+    st = env.stats_dict()
+    assert st["env_steps"] == T and st["episodes"] == int(g["done"].sum())
+
+
+@pytest.mark.parametrize("tag", ["sigma0", "sigma1", "mismatch"])
+def test_batch_step_and_rollout_match_live_reference(golden_batch, tag):
+    sig, a0, mism, _ = golden_batch[f"{tag}/params"]
+    acts, init, z = golden_batch["actions"], golden_batch["init"], golden_batch["z"]
+    T, N = acts.shape[:2]
+    table = np.ascontiguousarray(z.T)                                  # [L, N] draw-major
+    env = make_env(N, noise="table", noise_table=table)
+    env.reset(init=init.astype(np.float64), noise_var=sig, a0=a0, is_mismatched=bool(mism))
+    assert np.array_equal(env._cursor[:N].cpu().numpy(), golden_batch[f"{tag}/reset_cursor"])
+    r = step_through(env, acts)
+    assert np.array_equal(r["done"], golden_batch[f"{tag}/done"])
+    assert np.array_equal(r["counter"], golden_batch[f"{tag}/counter"])
+    assert np.array_equal(r["cursor"], golden_batch[f"{tag}/cursor"])
+    assert rel_err(r["pos"], golden_batch[f"{tag}/pos"]) < FP64_TOL
+    assert rel_err(r["obs"], golden_batch[f"{tag}/obs"]) < FP64_TOL
+    assert rel_err(r["sp"], golden_batch[f"{tag}/state_prime"]) < FP64_TOL
+
+    # the same episode through the fused kernel in 3 launches of K = 32
+    env2 = make_env(N, noise="table", noise_table=table)
+    env2.reset(init=init.astype(np.float64), noise_var=sig, a0=a0, is_mismatched=bool(mism))
+    xy, dn = [], []
+    a_dev = torch.as_tensor(acts, device=env2.device)
+    for k0 in range(0, T, 32):
+        res = env2.rollout(actions=a_dev[k0:k0 + 32], record=True, record_done=True)
+        xy.append(res["xy"].cpu().numpy()); dn.append(res["done_traj"].cpu().numpy())
+    xy = np.concatenate(xy).transpose(0, 2, 1)
+    assert rel_err(xy, golden_batch[f"{tag}/pos"]) < FP64_TOL
+    assert np.array_equal(np.concatenate(dn), golden_batch[f"{tag}/done"])
+    assert np.array_equal(env2._cursor[:N].cpu().numpy(), golden_batch[f"{tag}/cursor"][-1])
+    # bit-identical to the single-step kernel (same per-env code, state round-trips through HBM exactly in fp64)
+    assert np.array_equal(xy, r["pos"])
+
+
+def test_fp32_storage_mode_within_1e4(golden_batch):
+    """fp32 storage: positions / obs within 1e-4 of the reference; done flags and counters still exact
+    on these trajectories (decisions are taken in fp64 registers)."""
+    tag = "sigma1"
+    sig, a0, mism, _ = golden_batch[f"{tag}/params"]
+    acts, init, z = golden_batch["actions"], golden_batch["init"], golden_batch["z"]
+    T, N = acts.shape[:2]
+    env = make_env(N, dtype=torch.float32, noise="table", noise_table=np.ascontiguousarray(z.T))
+    env.reset(init=init, noise_var=sig, a0=a0, is_mismatched=bool(mism))
+    r = step_through(env, acts.astype(np.float32))
+    assert rel_err(r["pos"], golden_batch[f"{tag}/pos"]) < FP32_TOL
+    assert rel_err(r["obs"][..., 4], golden_batch[f"{tag}/obs"][..., 4]) < FP32_TOL
+    assert np.array_equal(r["done"], golden_batch[f"{tag}/done"])
+    assert np.array_equal(r["counter"], golden_batch[f"{tag}/counter"])
+    assert np.array_equal(r["cursor"], golden_batch[f"{tag}/cursor"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 4099, 8192])
+def test_vector_and_scalar_step_kernels_agree_noise_free(n):
+    """The 16-byte vectorised kernel (noise 'none', aligned rows) against the scalar kernel
+    (table mode keeps the scalar launch) and against the CPU oracle, ragged sizes included."""
+    rng = np.random.default_rng(n)
+    T = 12
+    init = rng.uniform(100, 120, (n, 2)).astype(np.float32).astype(np.float64)
+    acts = np.stack([rng.uniform(0, 20, (T, n)), rng.uniform(0, 2 * np.pi, (T, n))], -1)
+    env_v = make_env(n, noise="none")
+    env_s = make_env(n, noise="table", noise_table=np.zeros((400, n)))
+    for e in (env_v, env_s):
+        e.reset(init=init, noise_var=0.0, a0=1.0)
+    rv = step_through(env_v, acts)
+    rs = step_through(env_s, acts)
+    for k in ("pos", "obs", "done", "counter", "sp", "carry"):
+        assert np.array_equal(rv[k], rs[k]), k
+    for e in sorted({0, n // 2, n - 1}):
+        o = mo.rollout(acts[:, e], init[e], 0.0, 1.0, False, None)
+        assert rel_err(rv["pos"][:, e], o["pos"]) < FP64_TOL
+        assert np.array_equal(rv["done"][:, e], o["done"])
+        assert rel_err(rv["carry"][:, e, 2], o["carry_h"]) < FP64_TOL
+
+
+def test_empty_batch_and_argument_errors():
+    import ctypes as C
+    from mr_rl_b200 import _lib as L
+    env = make_env(4, noise="none")
+    lib = env.lib
+    p = L.default_params()
+    p.noise_var = 0.0
+    # n == 0 is a no-op
+    assert lib.mr_env_step(C.byref(env._c_state), 0, L.MR_F64, C.byref(p), None, C.byref(env._c_tt), None, None, None) == 0
+    # null actions
+    assert lib.mr_env_step(C.byref(env._c_state), 4, L.MR_F64, C.byref(p), None, C.byref(env._c_tt), None, None, None) == -1
+    assert b"null actions" in lib.mr_last_error()
+    # sigma != 0 without a noise source
+    p.noise_var = 1.0
+    a = torch.zeros(4, 2, dtype=torch.float64, device="cuda:0")
+    assert lib.mr_env_step(C.byref(env._c_state), 4, L.MR_F64, C.byref(p), None, C.byref(env._c_tt), C.c_void_p(a.data_ptr()), None, None) == -1
+    # bad dtype
+    assert lib.mr_env_step(C.byref(env._c_state), 4, 7, C.byref(p), None, C.byref(env._c_tt), C.c_void_p(a.data_ptr()), None, None) == -1
+    with pytest.raises(ValueError):
+        env.reset(noise_var=1.0)            # noise='none' env cannot take sigma != 0
+
+
+def test_noise_table_overflow_sets_status_flag():
+    env = make_env(3, noise="table", noise_table=np.zeros((10, 3)))
+    env.reset(init=np.array([110.0, 105.0]), noise_var=1.0, a0=1.0)
+    env.step(torch.ones(3, 2, dtype=torch.float64, device="cuda:0"))
+    with pytest.raises(Exception, match="noise table exhausted"):
+        env.check_status()
+
+
+def test_nonfinite_init_is_flagged_not_thrown_from_kernel():
+    env = make_env(2, noise="none")
+    env.reset(init=np.array([[np.nan, 1.0], [110.0, 105.0]]), noise_var=0.0, a0=1.0)
+    assert int(env.status[0]) & 2 and int(env.status[1]) == 0
+    with pytest.raises(ValueError):
+        env.check_status()
+
+
+def test_philox_noise_statistics_and_determinism():
+    """Throughput-mode noise: N(0, sigma) per RHS evaluation, reproducible from (seed, env, step),
+    independent of how envs are sharded over ranks."""
+    n = 1 << 16
+    acts = torch.zeros(n, 2, dtype=torch.float64, device="cuda:0")
+    acts[:, 0] = 5.0
+    acts[:, 1] = 0.3
+    env = make_env(n, noise="philox", seed=123)
+    env.reset(init=np.array([110.0, 105.0]), noise_var=2.0, a0=1.0)
+    env.step(acts)
+    sp = env.state_prime.cpu().numpy()
+    resid = sp - np.array([5.0 * np.cos(0.3), 5.0 * np.sin(0.3)])
+    assert abs(resid.mean()) < 0.03 and abs(resid.std() - 2.0) < 0.03
+    assert abs(np.corrcoef(resid[:, 0], resid[:, 1])[0, 1]) < 0.02
+    kurt = ((resid / resid.std()) ** 4).mean()
+    assert abs(kurt - 3.0) < 0.1
+    pos = env.last_pos.cpu().numpy()
+    # same seed, envs split into two shards with env_base offsets -> identical trajectories
+    half = n // 2
+    shards = []
+    for base in (0, half):
+        e2 = make_env(half, noise="philox", seed=123, env_base=base)
+        e2.reset(init=np.array([110.0, 105.0]), noise_var=2.0, a0=1.0)
+        e2.step(acts[:half])
+        shards.append(e2.last_pos.cpu().numpy())
+    assert np.array_equal(np.concatenate(shards), pos)
+    # a different seed gives different noise
+    e3 = make_env(half, noise="philox", seed=124)
+    e3.reset(init=np.array([110.0, 105.0]), noise_var=2.0, a0=1.0)
+    e3.step(acts[:half])
+    assert not np.array_equal(e3.last_pos.cpu().numpy(), pos[:half])
+
+
+def test_auto_reset_rollout_statistics_are_consistent():
+    """C3-style workload at reduced size: random in-kernel actions, auto reset, episode statistics."""
+    n, K = 8192, 64
+    env = make_env(n, noise="philox", seed=7, auto_reset=True)
+    env.reset(init=None, noise_var=1.0, a0=1.0)
+    init = env.last_pos.cpu().numpy()
+    assert init.min() >= 100.0 and init.max() <= 120.0
+    assert np.array_equal(init, init.astype(np.float32).astype(np.float64))       # Box.sample -> float32
+    total_done = 0
+    for _ in range(3):
+        res = env.rollout(policy="random", k_steps=K, record_done=True)
+        total_done += int(res["done_traj"].sum().item())
+    st = env.stats_dict()
+    assert st["env_steps"] == 3 * K * n
+    assert st["episodes"] == total_done
+    assert st["goal"] + st["out_of_bounds"] + st["timeout"] == st["episodes"]
+    assert st["sum_reward"] == 10.0 * st["env_steps"]
+    # random walk from (100..120)^2 never reaches d < 30 or leaves the box in 51 steps: all timeouts of length 51
+    assert st["timeout"] == st["episodes"] and st["sum_length"] == 51 * st["episodes"]
+    assert int(env.counter.max()) <= 51
+    env.check_status()
+
+
+def test_single_step_auto_reset_restarts_terminated_envs():
+    n = 64
+    env = make_env(n, noise="philox", seed=3, auto_reset=True)
+    env.reset(init=np.array([25.0, 20.0]), noise_var=0.5, a0=1.0)      # d = 32: a step toward the goal ends the episode
+    a = torch.zeros(n, 2, dtype=torch.float64, device="cuda:0")
+    a[:, 0] = 20.0
+    a[:, 1] = np.pi + np.arctan2(20.0, 25.0)                           # head for the origin
+    done_seen = np.zeros(n, bool)
+    for _ in range(10):
+        obs, rew, done, _ = env.step(a)
+        d = done.cpu().numpy().astype(bool)
+        o = obs.cpu().numpy()
+        c = env.counter.cpu().numpy()
+        assert np.all(c[d] == 0)                                       # restarted
+        assert np.all((o[d, 0] >= 100) & (o[d, 0] <= 120))
+        done_seen |= d
+    assert done_seen.all()
+
+
+def test_shaped_reward_mode():
+    env = make_env(3, noise="none", reward_mode="shaped")
+    env.reset(init=np.array([[25.0, 20.0], [110.0, 105.0], [4999.9, 0.0]]), noise_var=0.0, a0=1.0)
+    a = torch.tensor([[20.0, np.pi + np.arctan2(20.0, 25.0)], [1.0, 0.0], [20.0, 0.0]], dtype=torch.float64, device="cuda:0")
+    for _ in range(8):
+        obs, rew, done, _ = env.step(a)
+    r = rew.cpu().numpy(); d = done.cpu().numpy()
+    assert r[0] == 100.0 and d[0] == 1          # reached the goal radius
+    assert r[1] == -0.1 and d[1] == 0
+    assert r[2] == -100.0 and d[2] == 1         # left the observation box
+
+
+def test_checkpoint_resume_is_bit_exact():
+    n = 257
+    rng = np.random.default_rng(0)
+    acts = torch.as_tensor(np.stack([rng.uniform(0, 20, (20, n)), rng.uniform(0, 6.28, (20, n))], -1), device="cuda:0")
+    env = make_env(n, noise="philox", seed=11)
+    env.reset(init=None, noise_var=1.0, a0=1.0)
+    for k in range(10):
+        env.step(acts[k])
+    sd = env.state_dict()
+    for k in range(10, 20):
+        env.step(acts[k])
+    ref = env.last_pos.cpu().numpy().copy()
+    env2 = make_env(n, noise="philox", seed=999)
+    env2.load_state_dict(sd)
+    for k in range(10, 20):
+        env2.step(acts[k])
+    assert np.array_equal(env2.last_pos.cpu().numpy(), ref)
+
+
+def test_host_buffer_step_matches_device_step():
+    n = 1000
+    rng = np.random.default_rng(5)
+    acts = np.stack([rng.uniform(0, 20, n), rng.uniform(0, 6.28, n)], -1)
+    e1 = make_env(n, noise="none"); e2 = make_env(n, noise="none")
+    for e in (e1, e2):
+        e.reset(init=np.array([110.0, 105.0]), noise_var=0.0, a0=1.0)
+    o1, r1, d1, _ = e1.step_host(acts)
+    o2, r2, d2, _ = e2.step(torch.as_tensor(acts, device="cuda:0"))
+    assert isinstance(o1, np.ndarray) and o1.shape == (n, 5) and d1.dtype == bool
+    assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(r1, r2.cpu().numpy())
+
+
+def test_full_size_invariants_one_million_envs():
+    """BASELINE size (2^20 envs): size-independent properties + spot parity against the oracle."""
+    n = 1 << 20
+    rng = np.random.default_rng(42)
+    env = make_env(n, noise="none")
+    env.reset(init=None, noise_var=0.0, a0=1.0)
+    init = env.last_pos.cpu().numpy().copy()
+    T = 4
+    acts = np.stack([rng.uniform(0, 20, (T, n)), rng.uniform(0, 2 * np.pi, (T, n))], -1)
+    a_dev = torch.as_tensor(acts, device="cuda:0")
+    for k in range(T):
+        obs, rew, done, _ = env.step(a_dev[k])
+    o = obs.cpu().numpy()
+    assert np.array_equal(o[:, 2:4], np.zeros((n, 2)))                           # goal is (0, 0)
+    assert np.allclose(o[:, 4], np.hypot(o[:, 0], o[:, 1]), rtol=1e-15)
+    assert np.all(env.counter.cpu().numpy() == T) and not done.any() and np.all(rew.cpu().numpy() == 10.0)
+    # displacement is bounded by dt * a0 * f_max per step
+    assert np.all(np.hypot(*(o[:, :2] - init).T) <= T * 0.03 * 20.0 * (1 + 1e-12))
+    for e in (0, 12345, n - 1):
+        r = mo.rollout(acts[:, e], init[e], 0.0, 1.0, False, None)
+        assert rel_err(o[e, :2], r["pos"][-1]) < FP64_TOL
+    env.check_status()

@@ -1,0 +1,199 @@
+"""GPU parity: GP inference (Learning_module -> sklearn GPR.predict), the DDPG actor forward, and
+the single-env façades (MR_Env, run_sim, LearningModule) against golden vectors / the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import mr_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def fitted_pair(g):
+    gx = mo.fit_fixed_gp(g["X"], g["yx"], float(g["lsx"]), float(g["noise"]))
+    gy = mo.fit_fixed_gp(g["X"], g["yy"], float(g["lsy"]), float(g["noise"]))
+    return gx, gy
+
+
+def to_device(m):
+    from mr_rl_b200 import DeviceGP
+    return DeviceGP(m.X_train, m.alpha, m.L, m.length_scale, m.noise_level, device="cuda:0")
+
+
+def test_gp_predict_matches_reference_learning_module(golden_gp):
+    """mean and std on the golden grid recorded from the reference's LearningModule / sklearn."""
+    g = golden_gp
+    gx, gy = fitted_pair(g)
+    dx, dy = to_device(gx), to_device(gy)
+    mx, sx = dx.predict(g["grid"], return_std=True)
+    my, sy = dy.predict(g["grid"], return_std=True)
+    assert np.allclose(mx.cpu().numpy(), g["grid_mx"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(my.cpu().numpy(), g["grid_my"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(sx.cpu().numpy(), g["grid_sx"], rtol=1e-7, atol=1e-10)
+    assert np.allclose(sy.cpu().numpy(), g["grid_sy"], rtol=1e-7, atol=1e-10)
+    # mean-only path (the objective's calls, Learning_module.py:17-18)
+    assert np.array_equal(dx.predict(g["grid"]).cpu().numpy(), mx.cpu().numpy())
+    # LearningModule.error() rows
+    a = np.arctan2(g["vd"][:, 1], g["vd"][:, 0])
+    emx, esx = dx.predict(a, True)
+    emy, esy = dy.predict(a, True)
+    got = np.stack([emx.cpu().numpy(), emy.cpu().numpy(), esx.cpu().numpy(), esy.cpu().numpy()], 1)
+    assert np.allclose(got, g["error"], rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("n_train,n_q,dim", [(1, 5, 1), (37, 1, 1), (300, 1000, 1), (513, 700, 2), (2000, 4096, 1)])
+def test_gp_predict_matches_oracle_ragged_sizes(n_train, n_q, dim):
+    """SURVEY C4 kernels (RBF(0.2)+White(0.008)) incl. ragged sizes, the 2-D input variant
+    (Learning_module_2d.py) and the full N_train = 2000 of config 4."""
+    rng = np.random.default_rng(n_train)
+    X = np.sort(rng.uniform(-np.pi, np.pi, (n_train, dim)), axis=0)
+    y = 0.2 + 0.5 * np.cos(X[:, 0] + 0.3) + 0.09 * rng.standard_normal(n_train)
+    m = mo.fit_fixed_gp(X, y, 0.2 if dim == 1 else 0.6, 0.008)
+    q = rng.uniform(-np.pi, np.pi, (n_q, dim))
+    mean_o, std_o = mo.gp_predict(m, q)
+    d = to_device(m)
+    mean, std = d.predict(q, return_std=True)
+    assert np.allclose(mean.cpu().numpy(), mean_o, rtol=1e-8, atol=1e-9)
+    assert np.allclose(std.cpu().numpy(), std_o, rtol=1e-6, atol=1e-9)     # variance cancellation: 1+noise - |V|^2
+
+
+def test_gp_matches_sklearn_directly():
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    from mr_rl_b200 import DeviceGP
+    rng = np.random.default_rng(3)
+    X = np.sort(rng.uniform(-np.pi, np.pi, 400)).reshape(-1, 1)
+    y = -0.1 + 0.4 * np.sin(X[:, 0] - 0.2) + 0.09 * rng.standard_normal(400)
+    gpr = GaussianProcessRegressor(kernel=RBF(0.25) + WhiteKernel(0.008), optimizer=None).fit(X, y)
+    q = rng.uniform(-np.pi, np.pi, (999, 1))
+    m_ref, s_ref = gpr.predict(q, return_std=True)
+    d = DeviceGP.from_sklearn(gpr, device="cuda:0")
+    m, s = d.predict(q, True)
+    assert np.allclose(m.cpu().numpy(), m_ref, rtol=1e-8, atol=1e-10)
+    assert np.allclose(s.cpu().numpy(), s_ref, rtol=1e-6, atol=1e-9)
+
+
+def test_learning_module_facade_error_and_predict(golden_gp):
+    """Reference surface: error(vd) -> four (1,) arrays; predict(vd) -> (alpha, muX, muY, sigX, sigY)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    from mr_rl_b200 import LearningModule
+    g = golden_gp
+    X = g["X"].reshape(-1, 1)
+    gX = GaussianProcessRegressor(kernel=RBF(0.2) + WhiteKernel(0.008), optimizer=None).fit(X, g["yx"])
+    gY = GaussianProcessRegressor(kernel=RBF(0.25) + WhiteKernel(0.008), optimizer=None).fit(X, g["yy"])
+    a0, freq, Dx, Dy = g["hyper"]
+    lm = LearningModule(device="cuda:0")
+    lm.set_models(gX, gY, a0, freq, Dx, Dy)
+    for i in range(4):
+        out = lm.error(g["vd"][i])
+        assert all(o.shape == (1,) for o in out)
+        assert np.allclose(np.concatenate(out), g["error"][i], rtol=1e-7, atol=1e-10)
+    obj = [float(np.ravel(lm._objective(a, g["vd"][i]))[0]) for i, a in enumerate(g["obj_alpha"][:8])]
+    assert np.allclose(obj, g["objective"][:8], rtol=1e-8, atol=1e-9)
+    # predict: compare with the oracle objective minimised by the same scipy routine
+    from scipy.optimize import minimize_scalar
+    gx, gy = fitted_pair(g)
+    vd = g["vd"][0]
+    ref = minimize_scalar(lambda a: float(np.ravel(mo.lm_objective(a, a0, freq, vd, gx, gy, Dx, Dy))[0]),
+                          method="Bounded", bounds=[-np.pi, np.pi])
+    A, muX, muY, sigX, sigY = lm.predict(vd)
+    assert abs(float(A) - ref.x) < 1e-6
+    m_ref, s_ref = mo.gp_predict(gx, np.array([[ref.x]]))
+    assert np.allclose(muX, m_ref, rtol=1e-6, atol=1e-8) and np.allclose(sigX, s_ref, rtol=1e-5, atol=1e-8)
+    mx, my, sx, sy = lm.error_batch(torch.as_tensor(g["vd"], device="cuda:0"))
+    assert np.allclose(mx.cpu().numpy(), g["error"][:, 0], rtol=1e-7, atol=1e-10)
+
+
+def test_actor_forward_matches_torch_fp32_reference():
+    from mr_rl_b200 import actor_forward, init_actor, pack_actor
+    from mr_rl_b200.actor import torch_reference
+    params = init_actor(0)
+    # make BN non-trivial so the inference form is really exercised
+    g = torch.Generator().manual_seed(1)
+    for k in ("m1", "m2"):
+        params[k] = 0.05 * torch.randn(64, generator=g)
+    for k in ("v1", "v2"):
+        params[k] = 0.5 + torch.rand(64, generator=g)
+    for k in ("be1", "be2", "b1", "b2"):
+        params[k] = 0.01 * torch.randn(64, generator=g)
+    params["w3"] = 0.3 * torch.randn(64, 2, generator=g)
+    packed = pack_actor(params, "cuda:0")
+    n = 5000
+    rng = np.random.default_rng(0)
+    obs = np.zeros((n, 5))
+    obs[:, :2] = rng.uniform(-200, 200, (n, 2))
+    obs[:, 4] = np.hypot(obs[:, 0], obs[:, 1])
+    ref = torch_reference(params, obs).numpy()
+    for dt in (torch.float64, torch.float32):
+        soa = torch.as_tensor(obs.T.copy(), dtype=dt, device="cuda:0")
+        act = actor_forward(packed, soa).cpu().numpy()
+        assert act.shape == (n, 2)
+        assert np.allclose(act, ref, rtol=1e-4, atol=1e-4)        # fp32 kernel vs torch fp32
+    assert np.allclose(ref, mo.actor_forward({k: v.numpy() for k, v in params.items()}, obs), rtol=1e-4, atol=1e-4)
+
+
+def test_actor_in_the_rollout_loop_matches_stepwise_composition():
+    """Config-5 path at reduced size: fused rollout with the actor evaluated in-kernel ==
+    actor_forward kernel + single-step kernel composed on the host (noise-free)."""
+    from mr_rl_b200 import VecMREnv, actor_forward, init_actor, pack_actor
+    params = init_actor(0)
+    params["w3"] = 0.5 * torch.randn(64, 2, generator=torch.Generator().manual_seed(2))
+    packed = pack_actor(params, "cuda:0")
+    n, K = 777, 20
+    e1 = VecMREnv(n, device="cuda:0", noise="none"); e2 = VecMREnv(n, device="cuda:0", noise="none")
+    for e in (e1, e2):
+        e.reset(init=None, noise_var=0.0, a0=1.0)
+    e2._state.copy_(e1._state); e2._obs.copy_(e1._obs)
+    res = e1.rollout(policy=packed, k_steps=K, record=True)
+    xy = []
+    for _ in range(K):
+        a = actor_forward(packed, e2._obs, n)
+        e2.step(a)
+        xy.append(e2.last_pos.cpu().numpy().copy())
+    xy = np.stack(xy)
+    got = res["xy"].cpu().numpy().transpose(0, 2, 1)
+    assert rel_err(got, xy) < 1e-9
+    assert rel_err(e1.last_pos.cpu().numpy(), e2.last_pos.cpu().numpy()) < 1e-9
+
+
+def test_mr_env_facade_matches_live_reference(golden_single):
+    """The N = 1 drop-in class: numpy in / numpy out, python int reward, python bool done, dict info."""
+    from mr_rl_b200 import MR_Env
+    g = golden_single.case("c1_sigma1")
+    env = MR_Env(device="cuda:0", noise="table", noise_table=g["z"][:, None])
+    assert env.observation_space.shape[0] == 5 and env.action_space.shape[0] == 2
+    assert np.allclose(env.action_space.high, [20, 2 * np.pi])
+    obs = env.reset(init=np.asarray(g["init"]), noise_var=1, a0=1)
+    assert isinstance(obs, np.ndarray) and obs.shape == (5,) and obs.dtype == np.float64
+    assert rel_err(obs, g["reset_obs"]) < 1e-9
+    for k in range(60):
+        obs, rew, done, info = env.step(g["actions"][k])
+        assert rew == 10 and isinstance(done, bool) and info == {}
+        assert rel_err(obs, g["obs"][k]) < 1e-9
+        assert done == bool(g["done"][k]) and env.counter == int(g["counter"][k])
+        assert rel_err(env.state_prime, g["state_prime"][k]) < 1e-9
+        assert rel_err(np.asarray(env.last_pos), g["pos"][k]) < 1e-9
+
+
+def test_mr_env_facade_reset_ordering_quirk(golden_single):
+    from mr_rl_b200 import MR_Env
+    g = golden_single.case("reset_after_mismatch")
+    env = MR_Env(device="cuda:0", noise="table", noise_table=g["z"][:, None])
+    env.simulator.is_mismatched = True              # left over from a previous mismatched episode
+    env.reset(init=np.asarray(g["init"]), noise_var=1, a0=1, is_mismatched=False)
+    assert int(env._vec._cursor[0]) == int(g["reset_cursor"]) == 6     # 2 evaluations x 3 draws
+    for k in range(10):
+        obs, *_ = env.step(g["actions"][k])
+        assert rel_err(obs, g["obs"][k]) < 1e-9
+
+
+def test_run_sim_matches_live_reference(golden_single):
+    from mr_rl_b200 import run_sim
+    g = golden_single.case("c1_mismatch_circle")
+    X, Y, alpha, time, freq = run_sim(g["actions"], init_pos=np.array([0, 0]), noise_var=0.5, a0=1.5,
+                                      is_mismatched=True, device="cuda:0", noise="table", noise_table=g["z"][:, None])
+    assert rel_err(np.stack([X, Y], 1), g["pos"]) < 1e-9
+    assert np.array_equal(alpha, g["actions"][:, 1]) and np.array_equal(freq, g["actions"][:, 0])
+    assert np.allclose(time, np.linspace(0, (len(X) - 1) / 30.0, len(X)))
