@@ -1,0 +1,318 @@
+"""bench.py — env-steps/s of the batched MR_Env hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's CPU path (port)
+
+A "step" is ONE launch of the single-step kernel (MR_Env.step for every env of the rank) on
+synthetic random actions: 2^20 envs per GPU, fp64 storage, sigma = 1 (MR_Env.reset default) drawn
+by the in-kernel Philox generator, auto reset on done.  Envs shard by index across ranks with no
+data-path collective (weak scaling: per-GPU work fixed); NCCL only sums the episode statistics.
+`value` is whole-job env-steps/s with inputs resident in HBM; `e2e` is the same metric through the
+host-buffer call (numpy actions in, numpy obs/rew/done out, copies inside the timed region).
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+BYTES_PER_ENV_STEP = {"f64": 153, "f32": 81}     # algorithmic bytes, single-step path
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--sigma", type=float, default=1.0)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fused-rollout / small-batch side numbers")
+    return ap.parse_args()
+
+
+# ---- clocks during the timed region -----------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0 - 0.05) and (t1 is None or t <= t1 + 0.15)] or \
+               [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except Exception:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "B200_PROFILING.md fallback 6.65 TB/s"
+
+
+# ---- CPU legs -----------------------------------------------------------------------------------
+def cpu_port_throughput(budget_s, sigma):
+    """The reference's numpy/scipy env restated on the real scipy RK45 (oracle/scipy_env.py), one
+    process per host core, bounded sample.  Returns (value, cores, sample description, extras)."""
+    from oracle import scipy_env
+    cores = os.cpu_count() or 1
+    probe = scipy_env.throughput(1, 4, 50, sigma)                       # ~0.05 s calibration
+    per_core = max(probe["steps_per_s"], 1.0)
+    steps = 100
+    envs_per_proc = int(max(4, min(512, budget_s * per_core / steps)))
+    r = scipy_env.throughput(cores, envs_per_proc, steps, sigma)
+    sample = f"{cores} procs x {envs_per_proc} envs x {steps} steps, random actions, sigma={sigma}, auto reset"
+    return r["steps_per_s"], cores, sample, {"single_core_steps_per_s": per_core}
+
+
+def c_port_throughput(sigma):
+    try:
+        from oracle import c_oracle
+        r = c_oracle.throughput(1 << 16, 32, sigma)
+        return {"value": r["steps_per_s"], "unit": UNIT, "threads": r["threads"],
+                "sample": "plain-C oracle, 65536 envs x 32 steps"}
+    except Exception as e:   # no compiler on the box etc.
+        return {"unavailable": str(e)[:120]}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (Python + scipy RK45; the
+    reference sources cannot travel, so this is the oracle port pinned to them) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import scipy_env
+    cores = os.cpu_count() or 1
+    probe = scipy_env.throughput(1, 4, 50, args.sigma)
+    total = args.steps + args.warmup
+    envs_per_proc = int(max(2, min(256, 90.0 * probe["steps_per_s"] / max(total, 1))))
+    scipy_env.throughput(cores, envs_per_proc, max(args.warmup, 1), args.sigma)           # warm-up pass
+    t0 = time.perf_counter()
+    r = scipy_env.throughput(cores, envs_per_proc, args.steps, args.sigma)
+    wall = time.perf_counter() - t0
+    sample_envs = cores * envs_per_proc
+    value = r["steps_per_s"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["busy_s"] / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "1M batched MR_Env, single-step path, random actions (bounded CPU sample)",
+                   "sample_envs": sample_envs, "sigma": args.sigma, "a0": 1.0, "auto_reset": True},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} procs x {envs_per_proc} envs x {args.steps} steps (oracle/scipy_env.py on scipy RK45)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- this repo's arm ---------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mr_rl_b200 import VecMREnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    n = args.envs_per_gpu
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    noise = "philox" if args.sigma != 0 else "none"
+    env = VecMREnv(n, device=dev, dtype=tdt, noise=noise, seed=2024, env_base=rank * n, auto_reset=True)
+    env.want_state_prime = False                     # the 153 B/env-step accounting has no state_prime row
+    env.reset(init=None, noise_var=args.sigma, a0=1.0)
+
+    # synthetic random actions, resident in HBM: a pool of buffers, one per step modulo pool size
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = 8
+    acts = torch.rand(pool, n, 2, generator=gen, device=dev, dtype=torch.float64)
+    acts[..., 0] *= 20.0
+    acts[..., 1] *= 2 * np.pi
+    acts = acts.to(tdt)
+
+    for k in range(max(args.warmup, 3)):
+        env.step(acts[k % pool])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = env.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for k in range(args.steps):
+        env.step(acts[k % pool])
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = env.kernel_launches - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    env.check_status()
+
+    value = world * n * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+
+    # ---- roofline of the dominant (only) kernel: CUDA-event time per launch ------------------
+    peaks, peak_src = measured_peaks()
+    bytes_per_launch = BYTES_PER_ENV_STEP[args.dtype] * n
+    achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "env_step_kernel",
+                "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP[args.dtype], "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    prof = os.path.join(ROOT, "profiles", "traffic_step_kernel.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get(args.dtype + ("_philox" if args.sigma else "_none"))
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through the public call, copies inside the timed region -----------------
+    e2e_steps = max(3, args.e2e_steps)
+    host_acts = [acts[k % pool].cpu().numpy() for k in range(min(pool, e2e_steps))]
+    for k in range(2):
+        env.step_host(host_acts[k % len(host_acts)])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        o, r, d, _ = env.step_host(host_acts[k % len(host_acts)])
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    el = 8 if args.dtype == "f64" else 4
+    e2e = {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2 * el,
+           "d2h_bytes_per_step": n * (5 * el + el + 1), "steps": e2e_steps,
+           "api": "VecMREnv.step_host(numpy actions) -> numpy obs, rew, done"}
+
+    # ---- episode statistics: the path's only collective -----------------------------------------------
+    env.reset_stats()
+    env.rollout(policy="random", k_steps=8)
+    stats = env.allreduce_stats()
+
+    extras = {}
+    if not args.no_extras:
+        # fused K = 64 rollout on the same envs (state in registers; FP64-pipe bound)
+        env.rollout(policy="random", k_steps=64)
+        barrier()
+        ev0.record()
+        reps = 3
+        for _ in range(reps):
+            env.rollout(policy="random", k_steps=64)
+        ev1.record()
+        torch.cuda.synchronize()
+        fms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
+        extras["fused_rollout_k64"] = {"value": world * n * 64 / (fms * 1e-3), "unit": UNIT, "ms_per_launch": fms,
+                                       "envs_per_gpu": n, "actions": "in-kernel Philox", "sigma": args.sigma}
+        if rank == 0:
+            # BASELINE configs[1]: 4096 envs, fused K = 64
+            small = VecMREnv(4096, device=dev, dtype=tdt, noise=noise, seed=5, auto_reset=True)
+            small.reset(init=None, noise_var=args.sigma, a0=1.0)
+            small.rollout(policy="random", k_steps=64)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(20):
+                small.rollout(policy="random", k_steps=64)
+            ev1.record()
+            torch.cuda.synchronize()
+            sms = ev0.elapsed_time(ev1) / 20
+            extras["config1_4096_envs_k64"] = {"value": 4096 * 64 / (sms * 1e-3), "unit": UNIT, "ms_per_launch": sms}
+        barrier()
+
+    if rank == 0:
+        cpu_val, cores, sample, cpu_extra = cpu_port_throughput(args.cpu_seconds if world == 1 else 4.0, args.sigma)
+        cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                        "implementation": "oracle/scipy_env.py: reference env restated on scipy.integrate.RK45",
+                        **cpu_extra, "c_port": c_port_throughput(args.sigma)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "1M batched MR_Env per GPU, single-step path (configs[2]), random actions",
+                       "envs_per_gpu": n, "envs_total": world * n, "sigma": args.sigma, "a0": 1.0,
+                       "noise": "in-kernel Philox4x32-10 + Box-Muller" if args.sigma else "none (sigma=0)",
+                       "auto_reset": True, "sharding": f"env index ranges, {world} rank(s), no data-path collective",
+                       "l2_policy": "state+outputs per step = %.0f MB > 126 MB L2; 8 rotating action buffers" % (bytes_per_launch / 1e6)},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "episode_stats_allreduced": stats, **extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

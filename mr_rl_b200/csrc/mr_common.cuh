@@ -46,6 +46,16 @@ __device__ __forceinline__ double time_at(const TimeView& tv, int c, double dt) 
     return t;
 }
 
+// The carried step size decides how many RK45 attempts (hence noise draws) a step makes, so it
+// must survive storage exactly when it equals the interval length (the common case).  fp64
+// storage keeps h itself; fp32 storage keeps the ratio h / interval_length, where 1.0f is exact.
+template <class T> __device__ __forceinline__ double decode_h(T raw, double il) { return (double)raw; }
+template <> __device__ __forceinline__ double decode_h<float>(float raw, double il) {
+    return raw == 1.0f ? il : (double)raw * il;
+}
+template <class T> __device__ __forceinline__ T encode_h(double h, double il) { return (T)h; }
+template <> __device__ __forceinline__ float encode_h<float>(double h, double il) { return (float)(h / il); }
+
 // 16-byte vector access helpers: VEC consecutive envs of one SoA row per thread.
 template <class T, int VEC> struct Pack { T v[VEC]; };
 

@@ -29,7 +29,11 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     if (live) {
         Env e;
         e.x = (double)st.x[i]; e.y = (double)st.y[i]; e.fx = (double)st.fx[i]; e.fy = (double)st.fy[i];
-        e.h = (double)st.h[i]; e.counter = st.counter[i]; e.status = 0; e.spx = e.spy = 0.0;
+        e.counter = st.counter[i]; e.status = 0; e.spx = e.spy = 0.0;
+        {
+            const double t_in = time_at(tv, e.counter, p.dt);
+            e.h = decode_h<T>(st.h[i], (t_in + p.dt) - t_in);
+        }
         int32_t cur = 0;
         if constexpr (MODE == MR_NOISE_TABLE) cur = st.cursor[i];
         Observation o;
@@ -89,7 +93,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         if (overflow) e.status |= kNoiseOverflow;
         if (e.status) acc[MR_STAT_FAILED] += 1.0;
 
-        st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy; st.h[i] = (T)e.h;
+        const double t_out = time_at(tv, e.counter, p.dt);
+        st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy;
+        st.h[i] = encode_h<T>(e.h, (t_out + p.dt) - t_out);
         st.counter[i] = e.counter;
         if constexpr (MODE == MR_NOISE_TABLE) st.cursor[i] = cur;
         if (e.status) st.status[i] |= (uint8_t)e.status;

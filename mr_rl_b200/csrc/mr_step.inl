@@ -1,5 +1,7 @@
 // Single-step and reset kernels.  Included by the per-(dtype, noise mode) instantiation units
 // with MR_T and MR_MODE defined.
+#include <cstdlib>
+
 #include "mr_common.cuh"
 
 namespace mr {
@@ -37,7 +39,10 @@ env_step_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, 
     for (int j = 0; j < VEC; ++j) {
         Env e;
         e.x = (double)px.v[j]; e.y = (double)py.v[j]; e.fx = (double)pfx.v[j]; e.fy = (double)pfy.v[j];
-        e.h = (double)ph.v[j]; e.counter = pc.v[j]; e.status = 0; e.spx = e.spy = 0.0;
+        e.counter = pc.v[j]; e.status = 0; e.spx = e.spy = 0.0;
+        const double t = time_at(tv, e.counter, p.dt);
+        const double tb = t + p.dt, tb2 = tb + p.dt;
+        e.h = decode_h<T>(ph.v[j], tb - t);
         double f_t, al;
         if constexpr (VEC == 1) { f_t = (double)pa0.v[0]; al = (double)pa1.v[0]; }
         else {
@@ -47,23 +52,22 @@ env_step_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, 
         }
         auto nz = make_noise<MODE>(nv, n, i0 + j, MODE == MR_NOISE_TABLE ? pcur.v[j] : 0,
                                    nv.offset);
-        const double t = time_at(tv, e.counter, p.dt);
-        const double tb = t + p.dt, tb2 = tb + p.dt;
         e.counter += 1;                                               // MR_env.py:80
         const ActionTerms a = action_terms<MISM>(f_t, al, p);
         sim_step<MISM>(e, t, tb, tb2, a, p, nz);
         const Observation o = observe(e, p);
         int32_t cur = 0;
         if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; if (nz.overflow) e.status |= kNoiseOverflow; }
-        double d_out = o.d;
+        double d_out = o.d, il_next = tb2 - tb;
         if (p.auto_reset && o.done) {   // reported obs = first obs of the new episode; done/rew = terminal step
             int ov = 0;
             auto_reset_env<MODE, MISM>(e, nv, n, i0 + j, cur, nv.offset, p, ov);
             if (ov) e.status |= kNoiseOverflow;
             d_out = sqrt(e.x * e.x + e.y * e.y);
+            il_next = p.dt;
         }
         if constexpr (MODE == MR_NOISE_TABLE) ocur.v[j] = cur;
-        ox.v[j] = (T)e.x; oy.v[j] = (T)e.y; ofx.v[j] = (T)e.fx; ofy.v[j] = (T)e.fy; oh.v[j] = (T)e.h;
+        ox.v[j] = (T)e.x; oy.v[j] = (T)e.y; ofx.v[j] = (T)e.fx; ofy.v[j] = (T)e.fy; oh.v[j] = encode_h<T>(e.h, il_next);
         oc.v[j] = e.counter; od.v[j] = (T)d_out; orew.v[j] = (T)o.rew; odone.v[j] = o.done ? 1 : 0;
         ospx.v[j] = (T)e.spx; ospy.v[j] = (T)e.spy;
         status_v[j] = e.status; any_status |= e.status;
@@ -120,7 +124,7 @@ env_reset_kernel(StateView<T> st, const T* __restrict__ init_xy, const uint8_t* 
     if (p.mism_reset) env_reset<true>(e, x0, y0, p.dt, p, nz);
     else env_reset<false>(e, x0, y0, p.dt, p, nz);
     if constexpr (MODE == MR_NOISE_TABLE) { st.cursor[i] = nz.cursor; if (nz.overflow) e.status |= kNoiseOverflow; }
-    st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy; st.h[i] = (T)e.h;
+    st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy; st.h[i] = encode_h<T>(e.h, p.dt);
     st.counter[i] = 0;
     st.status[i] = (uint8_t)e.status;
     if (out.obs) {
@@ -165,8 +169,9 @@ template <class T, int MODE, bool MISM>
 static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& ov, const NoiseView& nv, const TimeView& tv,
                         const Params& p, int64_t n, bool vec_ok, cudaStream_t s) {
     constexpr int VEC = 16 / sizeof(T);
+    static const int force_scalar = [] { const char* e = getenv("MR_STEP_VEC"); return e && atoi(e) == 1; }();
     // table-noise columns are addressed by (env, n), so that mode keeps one scalar launch
-    if (vec_ok && MODE != MR_NOISE_TABLE && n >= VEC) {
+    if (vec_ok && !force_scalar && MODE != MR_NOISE_TABLE && n >= VEC) {
         const int64_t n_vec = (n / VEC) * VEC;
         launch_step_range<T, VEC, MODE, MISM>(sv, act, ov, nv, tv, p, n_vec, s);
         if (n_vec < n) {

@@ -113,8 +113,8 @@ def test_batch_step_and_rollout_match_live_reference(golden_batch, tag):
     assert rel_err(xy, golden_batch[f"{tag}/pos"]) < FP64_TOL
     assert np.array_equal(np.concatenate(dn), golden_batch[f"{tag}/done"])
     assert np.array_equal(env2._cursor[:N].cpu().numpy(), golden_batch[f"{tag}/cursor"][-1])
-    # bit-identical to the single-step kernel (same per-env code, state round-trips through HBM exactly in fp64)
-    assert np.array_equal(xy, r["pos"])
+    # same per-env code as the single-step kernel; only FMA contraction may differ between the two kernels
+    assert rel_err(xy, r["pos"]) < 1e-12
 
 
 def test_fp32_storage_mode_within_1e4(golden_batch):
@@ -148,8 +148,10 @@ def test_vector_and_scalar_step_kernels_agree_noise_free(n):
         e.reset(init=init, noise_var=0.0, a0=1.0)
     rv = step_through(env_v, acts)
     rs = step_through(env_s, acts)
-    for k in ("pos", "obs", "done", "counter", "sp", "carry"):
+    for k in ("done", "counter"):
         assert np.array_equal(rv[k], rs[k]), k
+    for k in ("pos", "obs", "sp", "carry"):          # two compilations of the same code: FMA contraction may differ
+        assert rel_err(rv[k], rs[k]) < 1e-13, k
     for e in sorted({0, n // 2, n - 1}):
         o = mo.rollout(acts[:, e], init[e], 0.0, 1.0, False, None)
         assert rel_err(rv["pos"][:, e], o["pos"]) < FP64_TOL
@@ -336,3 +338,22 @@ def test_full_size_invariants_one_million_envs():
         r = mo.rollout(acts[:, e], init[e], 0.0, 1.0, False, None)
         assert rel_err(o[e, :2], r["pos"][-1]) < FP64_TOL
     env.check_status()
+
+
+def test_nan_action_fails_fast_and_is_flagged():
+    """A non-finite action must not spin the attempt loop: scipy would shrink the step ~25 times and
+    fail; the kernel does the same, flags the env and leaves the others untouched."""
+    n = 1024
+    env = make_env(n, noise="philox", seed=1)
+    env.reset(init=np.array([110.0, 105.0]), noise_var=1.0, a0=1.0)
+    a = torch.ones(n, 2, dtype=torch.float64, device="cuda:0")
+    a[5, 0] = float("nan")
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(3):
+        env.step(a)
+    t1.record(); torch.cuda.synchronize()
+    assert t0.elapsed_time(t1) < 50.0
+    st = env.status.cpu().numpy()
+    assert st[5] & 1 and st[np.arange(n) != 5].max() == 0
+    assert np.isfinite(env.last_pos.cpu().numpy()[np.arange(n) != 5]).all()

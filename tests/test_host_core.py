@@ -13,12 +13,22 @@ from conftest import ROOT, rel_err
 from test_oracle_golden import SINGLE_CASES
 
 
+def _build(tmp_path_factory, name, extra):
+    out = tmp_path_factory.mktemp(name) / f"lib{name}.so"
+    src = os.path.join(ROOT, "tests", "host_core_harness.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *extra, src, "-o", str(out)], check=True)
+    return ctypes.CDLL(str(out))
+
+
 @pytest.fixture(scope="session")
 def host_core(tmp_path_factory):
-    out = tmp_path_factory.mktemp("hostcore") / "libhostcore.so"
-    src = os.path.join(ROOT, "tests", "host_core_harness.cpp")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", src, "-o", str(out)], check=True)
-    return ctypes.CDLL(str(out))
+    return _build(tmp_path_factory, "hostcore", [])
+
+
+@pytest.fixture(scope="session")
+def host_core_exact(tmp_path_factory):
+    """Same header with the division-free shortcuts disabled (margin so large they never fire)."""
+    return _build(tmp_path_factory, "hostcore_exact", ["-DMR_MARGIN=1e300"])
 
 
 def run_host(lib, g):
@@ -53,3 +63,24 @@ def test_core_header_matches_live_reference(host_core, golden_single, name):
     assert rel_err(r["carry"][:, 2], g["carry_h"]) < 1e-9
     assert rel_err(r["sp"], g["state_prime"]) < 1e-9
     assert rel_err(r["reset"][2], g["reset_carry_h"]) < 1e-9
+
+
+def test_division_free_shortcuts_equal_the_exact_formulas(host_core, host_core_exact):
+    """The shortcuts in ctor()/sim_step() skip divisions, square roots and pow only when the exact
+    scipy expression is decided by a 1e-9 margin; results must be BIT-identical to evaluating
+    everything, across regimes (near the origin, far away, tiny/huge actions, with/without noise)."""
+    rng = np.random.default_rng(7)
+    T = 40
+    for case in range(300):
+        scale = 10.0 ** rng.uniform(-6, 3.6)
+        init = rng.uniform(-1, 1, 2) * scale
+        acts = np.stack([rng.uniform(0, 20, T) * 10.0 ** rng.uniform(-4, 0), rng.uniform(0, 2 * np.pi, T)], 1)
+        sig = float(rng.choice([0.0, 0.01, 1.0, 5.0]))
+        mism = int(rng.integers(0, 2))
+        g = {"actions": acts, "init": init, "params": (sig, float(rng.uniform(0.5, 2)), mism, int(rng.integers(0, 2))),
+             "z": rng.standard_normal(T * 1500)}
+        a = run_host(host_core, g)
+        b = run_host(host_core_exact, g)
+        assert a["status"] == b["status"]
+        for k in ("pos", "d", "done", "counter", "cursor", "attempts", "carry", "sp", "reset"):
+            assert np.array_equal(a[k], b[k]), (case, k)

@@ -103,3 +103,27 @@ def test_actor_forward_shape_and_bounds():
     a = mo.actor_forward(p, obs)
     assert a.shape == (2, 2) and a.dtype == np.float32
     assert np.all(np.abs(a) <= np.array(mo.ACTION_HIGH, dtype=np.float32))
+
+
+@pytest.mark.parametrize("name", ["c1_sigma1", "c1_mismatch_circle", "reset_after_mismatch", "near_goal"])
+def test_scipy_env_port_matches_live_reference(golden_single, name):
+    """The CPU-baseline port built on the real scipy RK45 reproduces the live reference."""
+    from oracle.scipy_env import ScipyEnv
+    g = golden_single.case(name)
+    sig, a0, mism, prior = g["params"]
+    cur = [0]
+
+    def normal(mu, s, n):
+        v = mu + s * g["z"][cur[0]]
+        cur[0] += 1
+        return np.array([v])
+
+    env = ScipyEnv(normal=normal)
+    env.mism = bool(prior)
+    env.reset(g["init"], noise_var=sig, a0=a0, is_mismatched=bool(mism))
+    assert cur[0] == int(g["reset_cursor"])
+    T = min(len(g["actions"]), 120)
+    for k in range(T):
+        obs, rew, done, _ = env.step(g["actions"][k])
+        assert rel_err(obs, g["obs"][k]) < 1e-12
+        assert done == bool(g["done"][k]) and cur[0] == int(g["cursor"][k]) and rew == 10
