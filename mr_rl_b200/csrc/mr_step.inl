@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "mr_common.cuh"
+#include "mr_step_tma.cuh"
 
 namespace mr {
 
@@ -10,8 +11,11 @@ namespace mr {
 // Single step: one launch = MR_Env.step for n envs.  HBM-bound: 60 B read + 93 B written per
 // env-step in fp64 storage; VEC consecutive envs per thread so every row access is 16 bytes.
 // =============================================================================================
+#ifndef MR_STEP_MINB
+#define MR_STEP_MINB 1
+#endif
 template <class T, int VEC, int MODE, bool MISM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MR_STEP_MINB)
 env_step_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
                 Params p, int64_t n) {
     const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
@@ -165,22 +169,59 @@ static OutView<T> offset_out(OutView<T> v, int64_t o) {
     return v;
 }
 
+static int sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+// MR_STEP_PATH=tma|vec|scalar overrides the kernel choice (tuning / A-B measurements)
+static int step_path_override() {
+    static const int v = [] {
+        const char* e = getenv("MR_STEP_PATH");
+        if (!e) return 0;
+        return e[0] == 't' ? 1 : e[0] == 'v' ? 2 : e[0] == 's' ? 3 : 0;
+    }();
+    return v;
+}
+
 template <class T, int MODE, bool MISM>
 static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& ov, const NoiseView& nv, const TimeView& tv,
                         const Params& p, int64_t n, bool vec_ok, cudaStream_t s) {
     constexpr int VEC = 16 / sizeof(T);
-    static const int force_scalar = [] { const char* e = getenv("MR_STEP_VEC"); return e && atoi(e) == 1; }();
+    const int force = step_path_override();
+    int64_t done = 0;
     // table-noise columns are addressed by (env, n), so that mode keeps one scalar launch
-    if (vec_ok && !force_scalar && MODE != MR_NOISE_TABLE && n >= VEC) {
-        const int64_t n_vec = (n / VEC) * VEC;
-        launch_step_range<T, VEC, MODE, MISM>(sv, act, ov, nv, tv, p, n_vec, s);
-        if (n_vec < n) {
-            NoiseView nv2 = nv; nv2.env_base += (uint64_t)n_vec;
-            launch_step_range<T, 1, MODE, MISM>(offset_state(sv, n_vec), act + 2 * n_vec, offset_out(ov, n_vec), nv2, tv,
-                                                p, n - n_vec, s);
+    if constexpr (MODE != MR_NOISE_TABLE) {
+        if (vec_ok && n >= kTile && (force == 0 || force == 1)) {
+            // Blackwell path: persistent CTAs, TMA bulk copies through shared memory
+            const int64_t n_tiles = n / kTile;
+            const size_t smem = sizeof(StepSmem<T>);
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(env_step_tma_kernel<T, MODE, MISM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+            const int64_t max_ctas = (int64_t)sm_count() * (227 * 1024 / (int64_t)(smem + 1024));
+            const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
+            env_step_tma_kernel<T, MODE, MISM><<<grid, kTile, smem, s>>>(sv, act, ov, nv, tv, p, n_tiles, n);
+            done = n_tiles * kTile;
+        } else if (vec_ok && n >= VEC && force != 3 && force != 1) {
+            const int64_t n_vec = (n / VEC) * VEC;
+            launch_step_range<T, VEC, MODE, MISM>(sv, act, ov, nv, tv, p, n_vec, s);
+            done = n_vec;
         }
-    } else {
-        launch_step_range<T, 1, MODE, MISM>(sv, act, ov, nv, tv, p, n, s);
+    }
+    if (done < n) {
+        NoiseView nv2 = nv; nv2.env_base += (uint64_t)done;
+        if (done == 0) launch_step_range<T, 1, MODE, MISM>(sv, act, ov, nv, tv, p, n, s);
+        else launch_step_range<T, 1, MODE, MISM>(offset_state(sv, done), act + 2 * done, offset_out(ov, done), nv2, tv, p,
+                                                 n - done, s);
     }
 }
 

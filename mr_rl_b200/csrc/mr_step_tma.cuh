@@ -1,0 +1,187 @@
+// Single-step kernel, Blackwell form: a persistent CTA streams tiles of 256 envs through shared
+// memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) in BOTH directions.
+//
+//   HBM --cp.async.bulk--> smem in[stage]  --LDS--> registers (one env per thread) --STS-->
+//   smem out[stage] --cp.async.bulk--> HBM
+//
+// Loads of tile k+1..k+2 are in flight while tile k is integrated and the stores of tile k-1
+// drain, so the bytes in flight per SM no longer depend on occupancy or on how many registers
+// the fp64 RK45 controller needs.  Rows are SoA, so every bulk copy is one contiguous 1-4 KB
+// line; the goal rows (always 0, MR_env.py:57) are stored from one shared zero line.
+#pragma once
+
+#include "mr_common.cuh"
+
+namespace mr {
+
+constexpr int kTile = 256;          // envs per tile == threads per CTA
+constexpr int kStagesIn = 3;
+constexpr int kStagesOut = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class T>
+struct alignas(128) TileIn {
+    T x[kTile], y[kTile], fx[kTile], fy[kTile], h[kTile];
+    T act[2 * kTile];
+    int32_t counter[kTile];
+};
+
+template <class T>
+struct alignas(128) TileOut {
+    T x[kTile], y[kTile], fx[kTile], fy[kTile], h[kTile];
+    T d[kTile], rew[kTile], spx[kTile], spy[kTile];
+    int32_t counter[kTile];
+    uint8_t done[kTile];
+};
+
+template <class T>
+struct StepSmem {
+    TileIn<T> in[kStagesIn];
+    TileOut<T> out[kStagesOut];
+    alignas(128) T zero[kTile];
+    alignas(8) uint64_t full[kStagesIn];
+};
+
+template <class T, int MODE, bool MISM>
+__global__ void __launch_bounds__(kTile)
+env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
+                    Params p, int64_t n_tiles, int64_t n_total) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StepSmem<T>& sm = *reinterpret_cast<StepSmem<T>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStagesIn; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    sm.zero[tid] = (T)0;
+    fence_async_smem();
+    __syncthreads();
+
+    constexpr uint32_t kRow = kTile * sizeof(T);
+    constexpr uint32_t kInBytes = 5 * kRow + 2 * kRow + kTile * 4;
+
+    auto issue_loads = [&](int s, int64_t tile) {     // one elected thread
+        const int64_t i0 = tile * kTile;
+        uint64_t* bar = &sm.full[s];
+        mbar_expect_tx(bar, kInBytes);
+        TileIn<T>& b = sm.in[s];
+        bulk_load(b.x, st.x + i0, kRow, bar);
+        bulk_load(b.y, st.y + i0, kRow, bar);
+        bulk_load(b.fx, st.fx + i0, kRow, bar);
+        bulk_load(b.fy, st.fy + i0, kRow, bar);
+        bulk_load(b.h, st.h + i0, kRow, bar);
+        bulk_load(b.act, actions + 2 * i0, 2 * kRow, bar);
+        bulk_load(b.counter, st.counter + i0, kTile * 4, bar);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kStagesIn; ++s) {
+            const int64_t tile = first + (int64_t)s * stride;
+            if (tile < n_tiles) issue_loads(s, tile);
+        }
+    }
+
+    int it = 0;
+    for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
+        const int s = it % kStagesIn;
+        const uint32_t parity = (uint32_t)(it / kStagesIn) & 1u;
+        const int so = it % kStagesOut;
+        const int64_t i0 = tile * kTile;
+
+        mbar_wait(&sm.full[s], parity);
+        Env e;
+        const TileIn<T>& bi = sm.in[s];
+        e.x = (double)bi.x[tid]; e.y = (double)bi.y[tid]; e.fx = (double)bi.fx[tid]; e.fy = (double)bi.fy[tid];
+        const T h_raw = bi.h[tid];
+        e.counter = bi.counter[tid]; e.status = 0; e.spx = e.spy = 0.0;
+        double f_t, al;
+        if constexpr (sizeof(T) == 8) { const double2 a2 = reinterpret_cast<const double2*>(bi.act)[tid]; f_t = a2.x; al = a2.y; }
+        else { const float2 a2 = reinterpret_cast<const float2*>(bi.act)[tid]; f_t = a2.x; al = a2.y; }
+
+        if (tid == 0) bulk_wait_read<kStagesOut - 1>();     // out[so] (used kStagesOut tiles ago) has been read out
+        __syncthreads();                                    // [A] in[s] fully consumed, out[so] free
+        if (tid == 0) {
+            const int64_t nxt = tile + (int64_t)kStagesIn * stride;
+            if (nxt < n_tiles) issue_loads(s, nxt);
+        }
+
+        const double t = time_at(tv, e.counter, p.dt);
+        const double tb = t + p.dt, tb2 = tb + p.dt;
+        e.h = decode_h<T>(h_raw, tb - t);
+        auto nz = make_noise<MODE>(nv, n_total, i0 + tid, 0, nv.offset);
+        e.counter += 1;                                     // MR_env.py:80
+        const ActionTerms a = action_terms<MISM>(f_t, al, p);
+        sim_step<MISM>(e, t, tb, tb2, a, p, nz);
+        const Observation o = observe(e, p);
+        double d_out = o.d, il_next = tb2 - tb;
+        if (p.auto_reset && o.done) {                       // reported obs = first obs of the new episode
+            int32_t cur = 0; int ov = 0;
+            auto_reset_env<MODE, MISM>(e, nv, n_total, i0 + tid, cur, nv.offset, p, ov);
+            d_out = sqrt(e.x * e.x + e.y * e.y);
+            il_next = p.dt;
+        }
+
+        TileOut<T>& bo = sm.out[so];
+        bo.x[tid] = (T)e.x; bo.y[tid] = (T)e.y; bo.fx[tid] = (T)e.fx; bo.fy[tid] = (T)e.fy;
+        bo.h[tid] = encode_h<T>(e.h, il_next);
+        bo.counter[tid] = e.counter;
+        bo.d[tid] = (T)d_out; bo.rew[tid] = (T)o.rew; bo.done[tid] = o.done ? 1 : 0;
+        if (out.sp) { bo.spx[tid] = (T)e.spx; bo.spy[tid] = (T)e.spy; }
+        if (e.status) st.status[i0 + tid] |= (uint8_t)e.status;   // rare: sticky flags, plain store
+        fence_async_smem();
+        __syncthreads();                                    // [B] tile results complete in out[so]
+        if (tid == 0) {
+            bulk_store(st.x + i0, bo.x, kRow); bulk_store(st.y + i0, bo.y, kRow);
+            bulk_store(st.fx + i0, bo.fx, kRow); bulk_store(st.fy + i0, bo.fy, kRow);
+            bulk_store(st.h + i0, bo.h, kRow);
+            bulk_store(st.counter + i0, bo.counter, kTile * 4);
+            if (out.obs) {
+                bulk_store(out.obs + i0, bo.x, kRow);
+                bulk_store(out.obs + out.stride + i0, bo.y, kRow);
+                bulk_store(out.obs + 2 * out.stride + i0, sm.zero, kRow);   // goal is always (0,0), MR_env.py:57
+                bulk_store(out.obs + 3 * out.stride + i0, sm.zero, kRow);
+                bulk_store(out.obs + 4 * out.stride + i0, bo.d, kRow);
+            }
+            if (out.rew) bulk_store(out.rew + i0, bo.rew, kRow);
+            if (out.done) bulk_store(out.done + i0, bo.done, kTile);
+            if (out.sp) { bulk_store(out.sp + i0, bo.spx, kRow); bulk_store(out.sp + out.stride + i0, bo.spy, kRow); }
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();                      // smem must outlive the last bulk stores
+}
+
+}  // namespace mr
