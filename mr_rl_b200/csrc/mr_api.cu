@@ -31,6 +31,7 @@ static Params to_params(const mr_sim_params& s) {
     for (int i = 0; i < 2; ++i) { p.init_lo[i] = s.init_low[i]; p.init_hi[i] = s.init_high[i]; p.act_hi[i] = s.action_high[i]; }
     p.mism = s.is_mismatched; p.mism_reset = s.mism_at_reset; p.max_steps = s.max_timesteps;
     p.reward_mode = s.reward_mode; p.auto_reset = s.auto_reset;
+    finalize_params(p);
     return p;
 }
 
