@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libmr_rl_b200.so")
+LIB_PATH = os.environ.get("MR_LIB_PATH") or os.path.join(HERE, "_lib", "libmr_rl_b200.so")   # MR_LIB_PATH: tuning variants
 
 MR_F64, MR_F32 = 0, 1
 NOISE_NONE, NOISE_TABLE, NOISE_PHILOX = 0, 1, 2

@@ -38,8 +38,8 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def _compile(src, obj, verbose):
-    cmd = [NVCC, *ARCH_FLAGS, *COMMON, "-c", src, "-o", obj]
+def _compile(src, obj, verbose, extra_flags=()):
+    cmd = [NVCC, *ARCH_FLAGS, *COMMON, *extra_flags, "-c", src, "-o", obj]
     if verbose:
         cmd.insert(-4, "-Xptxas")
         cmd.insert(-4, "-v")
@@ -49,9 +49,18 @@ def _compile(src, obj, verbose):
     return r.stderr if verbose else ""
 
 
-def build(force=False, verbose=False, jobs=None):
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(force=False, verbose=False, jobs=None, extra_flags=(), variant=""):
+    """variant: build an experimental copy (extra -D flags) as libmr_rl_b200<variant>.so; load it with
+    MR_LIB_PATH.  The default build takes no extra flags."""
+    global OBJ_DIR, LIB_PATH
+    obj_dir = OBJ_DIR + variant
+    lib_path = LIB_PATH[:-3] + variant + ".so"
+    os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
+    return _build(force, verbose, jobs, list(extra_flags), obj_dir, lib_path)
+
+
+def _build(force, verbose, jobs, extra_flags, OBJ_DIR, LIB_PATH):
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = _deps()
     todo, objs = [], []
@@ -64,7 +73,7 @@ def build(force=False, verbose=False, jobs=None):
     log = []
     if todo:
         with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
-            for out in ex.map(lambda so: _compile(so[0], so[1], verbose), todo):
+            for out in ex.map(lambda so: _compile(so[0], so[1], verbose, extra_flags), todo):
                 log.append(out)
     if todo or force or _stale(LIB_PATH, objs):
         r = subprocess.run([NVCC, *ARCH_FLAGS, "-shared", "-o", LIB_PATH, *objs, "-lcudart"], capture_output=True, text=True)
@@ -76,5 +85,7 @@ def build(force=False, verbose=False, jobs=None):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    flags = [a for a in sys.argv[1:] if a.startswith("-D")]
+    variant = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--variant=")), "")
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, extra_flags=flags, variant=variant)
     print(path)

@@ -56,7 +56,21 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--rollout", action="store_true")
     a = ap.parse_args()
-    tag = os.environ.get("MR_STEP_VEC", "default")
+    tag = os.environ.get("MR_STEP_PATH", "default")
+    # box calibration: plain device copy of the same footprint (63 MB read + 97 MB written ~ 80 MB copy)
+    src = torch.empty(80 * 1024 * 1024, dtype=torch.uint8, device="cuda:0")
+    dst = torch.empty_like(src)
+    for _ in range(5):
+        dst.copy_(src)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        dst.copy_(src)
+    e1.record()
+    torch.cuda.synchronize()
+    cms = e0.elapsed_time(e1) / 50
+    print(f"calibration: 160 MB copy traffic in {cms*1e3:.1f} us = {160*1.048576/cms:.0f} GB/s", flush=True)
     for dtype in (torch.float64, torch.float32):
         for sigma in (0.0, 1.0):
             ms, gbs = time_step(a.n, dtype, sigma, a.steps)
