@@ -240,7 +240,7 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the public call, copies inside the timed region -----------------
     e2e_steps = max(3, args.e2e_steps)
-    host_acts = [acts[k % pool].cpu().numpy() for k in range(min(pool, e2e_steps))]
+    host_acts = [acts[k % pool].cpu().pin_memory() for k in range(min(pool, e2e_steps))]   # pinned host inputs
     for k in range(2):
         env.step_host(host_acts[k % len(host_acts)])
     barrier()
@@ -252,7 +252,7 @@ def run_ours(args):
     el = 8 if args.dtype == "f64" else 4
     e2e = {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2 * el,
            "d2h_bytes_per_step": n * (5 * el + el + 1), "steps": e2e_steps,
-           "api": "VecMREnv.step_host(numpy actions) -> numpy obs, rew, done"}
+           "api": "VecMREnv.step_host(pinned host actions) -> numpy obs, rew, done"}
 
     # ---- episode statistics: the path's only collective -----------------------------------------------
     env.reset_stats()

@@ -242,15 +242,20 @@ class VecMREnv:
         return b
 
     def step_host(self, actions):
-        """The reference-facing call with HOST buffers: numpy actions [N, 2] in, numpy
-        (obs [N,5], rew [N], done [N] bool) out.  Copies go through pinned staging buffers on the
-        current stream; the call returns after the device->host copies have completed."""
+        """The reference-facing call with HOST buffers: actions [N, 2] (numpy array, or a pinned torch
+        tensor which is used without a staging copy) in, numpy (obs [N,5], rew [N], done [N] bool) out.
+        Host<->device copies run on the current stream; the call returns after the device->host
+        copies have completed.  The returned arrays are views of pinned buffers reused by the next call."""
         n = self.num_envs
-        a_np = np.ascontiguousarray(np.asarray(actions, dtype=np.float64 if self.dtype == torch.float64 else np.float32))
-        if a_np.size != 2 * n:
-            raise ValueError(f"actions must be [{n}, 2]")
-        a_pin = self._pinned_buf("act", (n, 2), self.dtype)
-        a_pin.numpy()[...] = a_np.reshape(n, 2)
+        if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() \
+                and actions.dtype == self.dtype and actions.is_contiguous() and actions.numel() == 2 * n:
+            a_pin = actions.view(n, 2)
+        else:
+            a_np = np.asarray(actions.numpy() if torch.is_tensor(actions) else actions)
+            if a_np.size != 2 * n:
+                raise ValueError(f"actions must be [{n}, 2]")
+            a_pin = self._pinned_buf("act", (n, 2), self.dtype)
+            np.copyto(a_pin.numpy(), a_np.reshape(n, 2), casting="same_kind")
         a_dev = self._pinned.get("act_dev")
         if a_dev is None:
             a_dev = self._pinned["act_dev"] = torch.empty(n, 2, dtype=self.dtype, device=self.device)
@@ -263,7 +268,7 @@ class VecMREnv:
         r_pin.copy_(self._rew[:n], non_blocking=True)
         d_pin.copy_(self._done[:n], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return o_pin.numpy().T, r_pin.numpy(), d_pin.numpy().astype(bool), {}
+        return o_pin.numpy().T, r_pin.numpy(), d_pin.numpy().view(np.bool_), {}
 
     # ---- fused K-step rollout: utils.run_sim (utils.py:43-61) / the DDPG acting loop --------------
     def rollout(self, actions=None, k_steps=None, policy=None, record=False, record_state_prime=False,
@@ -333,11 +338,10 @@ class VecMREnv:
         self._stats.zero_()
 
     def allreduce_stats(self, group=None):
-        """Sum the episode-statistics vector over all ranks (torch.distributed, NCCL on GPUs)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self._stats, op=dist.ReduceOp.SUM, group=group)
-        return self.stats_dict()
+        """Sum the episode-statistics vector over all ranks (torch.distributed, NCCL on GPUs).
+        Returns the global statistics; the local accumulators are left untouched."""
+        from .dist import merge_stats
+        return merge_stats(self._stats, group)
 
     def stats_dict(self):
         v = self._stats.tolist()
@@ -384,9 +388,4 @@ class VecMREnv:
         return None
 
 
-def shard_range(num_envs_total, rank, world_size):
-    """Contiguous env-index shard of rank r: [r*N/G, (r+1)*N/G)."""
-    per = num_envs_total // world_size
-    rem = num_envs_total % world_size
-    start = rank * per + min(rank, rem)
-    return start, per + (1 if rank < rem else 0)
+from .dist import shard_range  # noqa: E402,F401  (re-exported)
