@@ -260,6 +260,25 @@ def run_ours(args):
     stats = env.allreduce_stats()
 
     extras = {}
+    if not args.no_extras and args.sigma != 0.0:
+        # the same single-step kernel with sigma = 0 (MR_simulator.py:18 default noise_var): no RNG work
+        env0 = VecMREnv(n, device=dev, dtype=tdt, noise="none", seed=2024, env_base=rank * n, auto_reset=True)
+        env0.want_state_prime = False
+        env0.reset(init=None, noise_var=0.0, a0=1.0)
+        for k in range(5):
+            env0.step(acts[k % pool])
+        barrier()
+        ev0.record()
+        for k in range(args.steps):
+            env0.step(acts[k % pool])
+        ev1.record()
+        torch.cuda.synchronize()
+        ms0 = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        ach0 = bytes_per_launch / (ms0 * 1e-3) / 1e9
+        extras["noise_free_sigma0"] = {"value": world * n / (ms0 * 1e-3), "unit": UNIT, "ms_per_step": ms0,
+                                       "roofline": {"bound": "hbm", "achieved": ach0, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                    "frac": ach0 / peaks["hbm_gbs"]}}
+        del env0
     if not args.no_extras:
         # fused K = 64 rollout on the same envs (state in registers; FP64-pipe bound)
         env.rollout(policy="random", k_steps=64)

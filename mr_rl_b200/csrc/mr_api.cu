@@ -23,8 +23,9 @@ int check_launch(const char* what) {
     return MR_OK;
 }
 
-static Params to_params(const mr_sim_params& s) {
+static Params to_params(const mr_sim_params& s, const mr_noise* nz) {
     Params p;
+    philox_make_keys(nz ? nz->seed : 0, p.keys);
     p.a0 = s.a0; p.sigma = s.noise_var;
     p.dt = s.time_span; p.rtol = s.rtol; p.atol = s.atol;
     p.min_dist = s.min_dist2goal; p.bound_xy = s.bound_xy; p.bound_d = s.bound_d;
@@ -53,7 +54,8 @@ static OutView<T> out_view(const mr_step_out* o, int64_t n) {
 }
 
 static NoiseView noise_view(const mr_noise* nz) {
-    NoiseView v{nullptr, 0, 0, 0, 0};
+    NoiseView v;
+    memset(&v, 0, sizeof(v));
     if (nz) { v.table = nz->table; v.table_len = nz->table_len; v.seed = nz->seed; v.offset = nz->offset; v.env_base = nz->env_base; }
     return v;
 }
@@ -168,7 +170,7 @@ int mr_env_reset(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_
     int rc = mr::check_common("mr_env_reset", st, n, dtype, p, nz);
     if (rc) return rc;
     if (n == 0) return MR_OK;
-    const mr::Params pp = mr::to_params(*p);
+    const mr::Params pp = mr::to_params(*p, nz);
     cudaStream_t s = (cudaStream_t)stream;
     return dtype == MR_F64 ? mr::do_reset<double>(*st, n, pp, nz, init_xy, mask, reset_cursor, out, s)
                            : mr::do_reset<float>(*st, n, pp, nz, init_xy, mask, reset_cursor, out, s);
@@ -181,7 +183,7 @@ int mr_env_step(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_p
     if (n == 0) return MR_OK;
     if (!actions) return mr::fail(MR_ERR_ARG, "mr_env_step: null actions");
     if (!tt || !tt->t || tt->len < 2) return mr::fail(MR_ERR_ARG, "mr_env_step: time table missing");
-    const mr::Params pp = mr::to_params(*p);
+    const mr::Params pp = mr::to_params(*p, nz);
     mr::TimeView tv{tt->t, tt->len};
     cudaStream_t s = (cudaStream_t)stream;
     return dtype == MR_F64 ? mr::do_step<double>(*st, n, pp, nz, tv, actions, out, s)
@@ -204,7 +206,7 @@ int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_si
         return mr::fail(MR_ERR_ARG, "mr_env_rollout: actions must be 16-byte aligned");
     if (p->auto_reset && nz == nullptr)
         return mr::fail(MR_ERR_ARG, "mr_env_rollout: auto_reset needs mr_noise (seed) for the init sampler");
-    const mr::Params pp = mr::to_params(*p);
+    const mr::Params pp = mr::to_params(*p, nz);
     mr::TimeView tv{tt->t, tt->len};
     cudaStream_t s = (cudaStream_t)stream;
     return dtype == MR_F64 ? mr::do_rollout<double>(*st, n, pp, nz, tv, *io, out, s)

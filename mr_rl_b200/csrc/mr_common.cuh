@@ -116,7 +116,7 @@ __device__ __forceinline__ typename NoiseOf<MODE>::type make_noise(const NoiseVi
         nz.col = nv.table + env; nz.stride = n; nz.cursor = cursor;
         nz.len = (int32_t)nv.table_len; nz.overflow = 0;
     } else if constexpr (MODE == MR_NOISE_PHILOX) {
-        nz.seek(nv.seed, nv.env_base + (uint64_t)env, step);
+        nz.seek(nv.env_base + (uint64_t)env, step);
     }
     return nz;
 }
@@ -128,7 +128,7 @@ template <int MODE, bool MISM>
 __device__ __forceinline__ void auto_reset_env(Env& e, const NoiseView& nv, int64_t n, int64_t i, int32_t& cur,
                                                uint64_t step, const Params& p, int& overflow) {
     double u[4];
-    philox_uniform4(nv.seed, nv.env_base + (uint64_t)i, step, kPurposeInit, u);
+    philox_uniform4(p, nv.env_base + (uint64_t)i, step, kPurposeInit, u);
     const double x0 = (double)(float)(p.init_lo[0] + (p.init_hi[0] - p.init_lo[0]) * u[0]);
     const double y0 = (double)(float)(p.init_lo[1] + (p.init_hi[1] - p.init_lo[1]) * u[1]);
     const int keep = e.status;

@@ -50,7 +50,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
                 f_t = (double)io.actions[2 * k]; al = (double)io.actions[2 * k + 1];
             } else if constexpr (SRC == MR_ACTIONS_PHILOX) {
                 double u[4];
-                philox_uniform4(nv.seed, nv.env_base + (uint64_t)i, nv.offset + (uint64_t)k, kPurposeAction, u);
+                philox_uniform4(p, nv.env_base + (uint64_t)i, nv.offset + (uint64_t)k, kPurposeAction, u);
                 f_t = p.act_hi[0] * u[0]; al = p.act_hi[1] * u[1];   // U[0,20) x U[0,2pi)
             } else {
                 float obs5[5] = {(float)e.x, (float)e.y, 0.f, 0.f, (float)o.d};

@@ -115,7 +115,7 @@ env_reset_kernel(StateView<T> st, const T* __restrict__ init_xy, const uint8_t* 
     if (init_xy) { x0 = (double)init_xy[2 * i]; y0 = (double)init_xy[2 * i + 1]; }
     else {
         double u[4];
-        philox_uniform4(nv.seed, nv.env_base + (uint64_t)i, nv.offset, kPurposeInit, u);
+        philox_uniform4(p, nv.env_base + (uint64_t)i, nv.offset, kPurposeInit, u);
         // gym Box.sample: uniform(low, high).astype(float32)
         x0 = (double)(float)(p.init_lo[0] + (p.init_hi[0] - p.init_lo[0]) * u[0]);
         y0 = (double)(float)(p.init_lo[1] + (p.init_hi[1] - p.init_lo[1]) * u[1]);
@@ -198,16 +198,20 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
     int64_t done = 0;
     // table-noise columns are addressed by (env, n), so that mode keeps one scalar launch
     if constexpr (MODE != MR_NOISE_TABLE) {
+        constexpr int kTile = TileOf<T>::value;
         if (vec_ok && n >= kTile && (force == 0 || force == 1)) {
             // Blackwell path: persistent CTAs, TMA bulk copies through shared memory
             const int64_t n_tiles = n / kTile;
             const size_t smem = sizeof(StepSmem<T>);
-            static bool attr_done = false;
-            if (!attr_done) {
+            static int ctas_per_sm = 0;                    // per template instantiation
+            if (!ctas_per_sm) {
                 cudaFuncSetAttribute(env_step_tma_kernel<T, MODE, MISM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_done = true;
+                int occ = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_step_tma_kernel<T, MODE, MISM>, kTile, smem);
+                ctas_per_sm = occ > 0 ? occ : 1;
             }
-            const int64_t max_ctas = (int64_t)sm_count() * (227 * 1024 / (int64_t)(smem + 1024));
+            // persistent grid: exactly the CTAs that are co-resident, so there is never a second wave
+            const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
             const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
             env_step_tma_kernel<T, MODE, MISM><<<grid, kTile, smem, s>>>(sv, act, ov, nv, tv, p, n_tiles, n);
             done = n_tiles * kTile;

@@ -14,13 +14,16 @@
 
 namespace mr {
 
-#ifndef MR_TILE
-#define MR_TILE 256
-#endif
 #ifndef MR_STAGES_IN
 #define MR_STAGES_IN 3
 #endif
-constexpr int kTile = MR_TILE;      // envs per tile == threads per CTA
+// envs per tile == threads per CTA.  Measured on B200 (2^20 envs): fp64 128 -> 30.9 us, 256 -> 32.2 us;
+// fp32 128 -> 27.6 us, 256 -> 25.6 us.
+#ifdef MR_TILE
+template <class T> struct TileOf { static constexpr int value = MR_TILE; };
+#else
+template <class T> struct TileOf { static constexpr int value = sizeof(T) == 8 ? 128 : 256; };
+#endif
 constexpr int kStagesIn = MR_STAGES_IN;
 constexpr int kStagesOut = 2;
 
@@ -56,14 +59,14 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <class T>
+template <class T, int kTile>
 struct alignas(128) TileIn {
     T x[kTile], y[kTile], fx[kTile], fy[kTile], h[kTile];
     T act[2 * kTile];
     int32_t counter[kTile];
 };
 
-template <class T>
+template <class T, int kTile>
 struct alignas(128) TileOut {
     T x[kTile], y[kTile], fx[kTile], fy[kTile], h[kTile];
     T d[kTile], rew[kTile], spx[kTile], spy[kTile];
@@ -71,18 +74,19 @@ struct alignas(128) TileOut {
     uint8_t done[kTile];
 };
 
-template <class T>
+template <class T, int kTile = TileOf<T>::value>
 struct StepSmem {
-    TileIn<T> in[kStagesIn];
-    TileOut<T> out[kStagesOut];
+    TileIn<T, kTile> in[kStagesIn];
+    TileOut<T, kTile> out[kStagesOut];
     alignas(128) T zero[kTile];
     alignas(8) uint64_t full[kStagesIn];
 };
 
 template <class T, int MODE, bool MISM>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(TileOf<T>::value)
 env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
                     Params p, int64_t n_tiles, int64_t n_total) {
+    constexpr int kTile = TileOf<T>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StepSmem<T>& sm = *reinterpret_cast<StepSmem<T>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -111,7 +115,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
     auto issue_loads = [&](int s, int64_t tile) {     // called by the elected lane of every warp
         const int64_t i0 = tile * kTile;
         uint64_t* bar = &sm.full[s];
-        TileIn<T>& b = sm.in[s];
+        TileIn<T, kTile>& b = sm.in[s];
         if (warp == 0) mbar_expect_tx(bar, kInBytes);
         if (warp == 0 % kWarps) bulk_load(b.x, st.x + i0, kRow, bar);
         if (warp == 1 % kWarps) bulk_load(b.y, st.y + i0, kRow, bar);
@@ -138,7 +142,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
 
         mbar_wait(&sm.full[s], parity);
         Env e;
-        const TileIn<T>& bi = sm.in[s];
+        const TileIn<T, kTile>& bi = sm.in[s];
         e.x = (double)bi.x[tid]; e.y = (double)bi.y[tid]; e.fx = (double)bi.fx[tid]; e.fy = (double)bi.fy[tid];
         const T h_raw = bi.h[tid];
         e.counter = bi.counter[tid]; e.status = 0; e.spx = e.spy = 0.0;
@@ -169,7 +173,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
             il_next = p.dt;
         }
 
-        TileOut<T>& bo = sm.out[so];
+        TileOut<T, kTile>& bo = sm.out[so];
         bo.x[tid] = (T)e.x; bo.y[tid] = (T)e.y; bo.fx[tid] = (T)e.fx; bo.fy[tid] = (T)e.fy;
         bo.h[tid] = encode_h<T>(e.h, il_next);
         bo.counter[tid] = e.counter;

@@ -18,6 +18,7 @@ extern "C" int host_core_rollout(const double* actions /*[T][2]*/, int T, double
     p.init_lo[0] = p.init_lo[1] = 100; p.init_hi[0] = p.init_hi[1] = 120; p.act_hi[0] = 20; p.act_hi[1] = 6.283185307179586;
     p.mism = mism; p.mism_reset = mism_at_reset; p.max_steps = 50; p.reward_mode = 0; p.auto_reset = 0;
     finalize_params(p);
+    philox_make_keys(0, p.keys);
     TableNoise nz;
     nz.col = z; nz.stride = 1; nz.cursor = 0; nz.len = zlen; nz.overflow = 0;
     Env e;

@@ -357,3 +357,35 @@ def test_nan_action_fails_fast_and_is_flagged():
     st = env.status.cpu().numpy()
     assert st[5] & 1 and st[np.arange(n) != 5].max() == 0
     assert np.isfinite(env.last_pos.cpu().numpy()[np.arange(n) != 5]).all()
+
+
+def test_generated_noise_has_the_reference_step_statistics():
+    """Throughput mode draws the sufficient statistics of an RK45 attempt (4 normals instead of 12).
+    The one-step displacement must have the reference's distribution: mean h*v, variance
+    h^2 sigma^2 (B0^2 + sum_{s=2..5} B_s^2), no correlation between consecutive steps — and must
+    agree with the parity (table) mode, which consumes one draw per reference draw."""
+    n, sigma, f, al = 1 << 18, 2.0, 6.0, 0.7
+    B = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84])
+    var_theory = (0.03 * sigma) ** 2 * (B ** 2).sum()
+    a = torch.tensor([[f, al]], dtype=torch.float64, device="cuda:0").expand(n, 2).contiguous()
+
+    def displacements(env):
+        env.reset(init=np.array([110.0, 105.0]), noise_var=sigma, a0=1.0)
+        pos = []
+        for _ in range(4):
+            env.step(a)
+            pos.append(env.last_pos.cpu().numpy().copy())
+        return pos[2] - pos[1], pos[3] - pos[2]
+
+    d1, d2 = displacements(make_env(n, noise="philox", seed=5))
+    rng = np.random.default_rng(0)
+    t1, _ = displacements(make_env(n, noise="table", noise_table=rng.standard_normal((80, n))))
+    mean_theory = 0.03 * f * np.array([np.cos(al), np.sin(al)])
+    se = np.sqrt(var_theory / n)
+    for d in (d1, t1):
+        assert np.all(np.abs(d.mean(0) - mean_theory) < 5 * se)
+        assert np.all(np.abs(d.var(0) / var_theory - 1.0) < 0.01)
+    assert abs(np.corrcoef(d1[:, 0], d2[:, 0])[0, 1]) < 0.01          # consecutive steps are independent
+    assert abs(np.corrcoef(d1[:, 0], d1[:, 1])[0, 1]) < 0.01          # x and y noise are independent
+    k = ((d1 - d1.mean(0)) / d1.std(0)) ** 4
+    assert np.all(np.abs(k.mean(0) - 3.0) < 0.1)                      # Gaussian kurtosis

@@ -1,0 +1,74 @@
+"""Dev tool: time the GP (config 4) and actor-in-loop (config 5) paths with CUDA events."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from mr_rl_b200 import DeviceGP, VecMREnv, init_actor, pack_actor
+from oracle import mr_oracle as mo
+
+
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def gp_bench(n_train=2000, n_q=262144):
+    rng = np.random.default_rng(0)
+    X = np.sort(rng.uniform(-np.pi, np.pi, n_train))
+    yx = 0.2 + 0.5 * np.cos(X + 0.3) + 0.09 * rng.standard_normal(n_train)
+    t0 = time.perf_counter()
+    m = mo.fit_fixed_gp(X, yx, 0.2, 0.008)
+    d = DeviceGP(m.X_train, m.alpha, m.L, m.length_scale, m.noise_level, device="cuda:0")
+    print(f"gp: host fit + upload {time.perf_counter()-t0:.2f} s (n_train={n_train}, n_pad={d.n_pad})")
+    q = torch.rand(n_q, device="cuda:0", dtype=torch.float64) * 2 * np.pi - np.pi
+    for want_std in (False, True):
+        d.predict(q, want_std)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        reps = 5 if not want_std else 2
+        e0.record()
+        for _ in range(reps):
+            d.predict(q, want_std)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        pairs = n_q * n_train
+        if want_std:
+            flops = n_q * float(d.n_pad) ** 2      # triangular: 2 * n^2 / 2 per query
+            print(f"gp mean+std: {ms:8.2f} ms per GP  ({n_q/ms/1e3:.1f} Mquery/s, variance contraction {flops/ms/1e9:.2f} TFLOP/s fp64)")
+        else:
+            print(f"gp mean    : {ms:8.3f} ms per GP  ({pairs/ms/1e6:.1f} Gpair/s)")
+    # spot parity
+    qs = q[:512].cpu().numpy().reshape(-1, 1)
+    mo_m, mo_s = mo.gp_predict(m, qs)
+    g_m, g_s = d.predict(q[:512], True)
+    print("gp parity: mean rel", float(np.max(np.abs(g_m.cpu().numpy() - mo_m) / np.maximum(np.abs(mo_m), 1e-12))),
+          "std rel", float(np.max(np.abs(g_s.cpu().numpy() - mo_s) / mo_s)))
+
+
+def actor_bench(n=1 << 20, K=64):
+    packed = pack_actor(init_actor(0), "cuda:0")
+    for sigma in (0.0, 1.0):
+        env = VecMREnv(n, device="cuda:0", noise="philox" if sigma else "none", seed=3, auto_reset=True)
+        env.reset(init=None, noise_var=sigma, a0=1.0)
+        env.rollout(policy=packed, k_steps=K)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        env.rollout(policy=packed, k_steps=K)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print(f"actor-in-loop rollout K={K} sigma={sigma}: {ms:8.2f} ms  {n*K/ms/1e6:8.2f} Genv-steps/s  "
+              f"({n*K*2*4544/ms/1e9:.1f} TFLOP/s fp32 in the MLP)")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "gp"):
+        gp_bench()
+    if what in ("all", "actor"):
+        actor_bench()
