@@ -149,7 +149,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ---- this repo's arm ---------------------------------------------------------------------------------
@@ -251,12 +251,12 @@ def run_ours(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     el = 8 if args.dtype == "f64" else 4
     e2e = {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2 * el,
-           "d2h_bytes_per_step": n * (5 * el + el + 1), "steps": e2e_steps,
+           "d2h_bytes_per_step": n * (3 * el + el + 1), "steps": e2e_steps,   # obs rows x, y, d + rew + done (goal rows are constant 0)
            "api": "VecMREnv.step_host(pinned host actions) -> numpy obs, rew, done"}
 
     # ---- episode statistics: the path's only collective -----------------------------------------------
     env.reset_stats()
-    env.rollout(policy="random", k_steps=8)
+    env.rollout(policy="random", k_steps=64)            # > one episode (51 steps) for every env
     stats = env.allreduce_stats()
 
     extras = {}
@@ -324,13 +324,23 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "episode_stats_allreduced": stats, **extras,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Only the JSON line may reach stdout: libraries (e.g. NCCL's version banner) write to fd 1 too, so
+    fd 1 is pointed at stderr for the run and the saved descriptor is used for the final line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 if __name__ == "__main__":
     a = parse()
+    _OUT = _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -1,6 +1,9 @@
 // Fused K-step rollout kernel.  Included by the per-(dtype, noise mode) instantiation units
 // with MR_T and MR_MODE defined.
+#include <cstdlib>
+
 #include "mr_actor.cuh"
+#include "mr_actor_tc.cuh"
 #include "mr_common.cuh"
 
 namespace mr {
@@ -9,63 +12,74 @@ namespace mr {
 // Fused rollout: K env steps per launch, state in registers, one env per thread.
 // FP64-pipe bound (no HBM traffic for state between steps).
 // =============================================================================================
+constexpr int kSrcActorTc = 100;   // internal: MR_ACTIONS_ACTOR evaluated on the tensor cores (mr_actor_tc.cuh)
+
 template <class T, int MODE, bool MISM, int SRC>
 __global__ void __launch_bounds__(128)
 env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView nv, TimeView tv, Params p, int64_t n) {
-    extern __shared__ __align__(16) float s_actor[];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ double s_stats[MR_STATS_LEN];
+    float* s_actor = reinterpret_cast<float*>(s_dyn);
     if constexpr (SRC == MR_ACTIONS_ACTOR) {
         for (int k = threadIdx.x; k < kActorParams; k += blockDim.x) s_actor[k] = io.actor[k];
     }
+    if constexpr (SRC == kSrcActorTc) actor_tc_setup(*reinterpret_cast<ActorTcSmem*>(s_dyn), io.actor);
     if (threadIdx.x < MR_STATS_LEN) s_stats[threadIdx.x] = 0.0;
     __syncthreads();
 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
+    const bool live = i < n;                       // every thread runs the loop (CTA-wide barriers in the actor path)
     double acc[MR_STATS_LEN];
 #pragma unroll
     for (int k = 0; k < MR_STATS_LEN; ++k) acc[k] = 0.0;
 
+    Env e;
+    e.x = 110.0; e.y = 110.0; e.fx = 0.0; e.fy = 0.0; e.h = p.dt; e.counter = 0;   // harmless state for padding lanes
+    e.status = 0; e.spx = e.spy = 0.0;
+    int32_t cur = 0;
     if (live) {
-        Env e;
         e.x = (double)st.x[i]; e.y = (double)st.y[i]; e.fx = (double)st.fx[i]; e.fy = (double)st.fy[i];
-        e.counter = st.counter[i]; e.status = 0; e.spx = e.spy = 0.0;
-        {
-            const double t_in = time_at(tv, e.counter, p.dt);
-            e.h = decode_h<T>(st.h[i], (t_in + p.dt) - t_in);
-        }
-        int32_t cur = 0;
+        e.counter = st.counter[i];
+        const double t_in = time_at(tv, e.counter, p.dt);
+        e.h = decode_h<T>(st.h[i], (t_in + p.dt) - t_in);
         if constexpr (MODE == MR_NOISE_TABLE) cur = st.cursor[i];
-        Observation o;
-        o.d = sqrt(e.x * e.x + e.y * e.y); o.rew = 0.0; o.done = false; o.why = 0;
-        bool overflow = false;
+    }
+    Observation o;
+    o.d = sqrt(e.x * e.x + e.y * e.y); o.rew = 0.0; o.done = false; o.why = 0;
+    bool overflow = false;
 
-        for (int k = 0; k < io.k_steps; ++k) {
-            double f_t, al;
-            if constexpr (SRC == MR_ACTIONS_TENSOR) {
+    for (int k = 0; k < io.k_steps; ++k) {
+        double f_t = 0.0, al = 0.0;
+        if constexpr (SRC == MR_ACTIONS_TENSOR) {
+            if (live) {
                 const T* a = io.actions + ((int64_t)k * n + i) * 2;
                 if constexpr (sizeof(T) == 8) { const double2 v = *reinterpret_cast<const double2*>(a); f_t = v.x; al = v.y; }
                 else { const float2 v = *reinterpret_cast<const float2*>(a); f_t = v.x; al = v.y; }
-            } else if constexpr (SRC == MR_ACTIONS_BROADCAST) {
-                f_t = (double)io.actions[2 * k]; al = (double)io.actions[2 * k + 1];
-            } else if constexpr (SRC == MR_ACTIONS_PHILOX) {
-                double u[4];
-                philox_uniform4(p, nv.env_base + (uint64_t)i, nv.offset + (uint64_t)k, kPurposeAction, u);
-                f_t = p.act_hi[0] * u[0]; al = p.act_hi[1] * u[1];   // U[0,20) x U[0,2pi)
-            } else {
-                float obs5[5] = {(float)e.x, (float)e.y, 0.f, 0.f, (float)o.d};
-                float a2[2];
-                actor_forward_smem(s_actor, obs5, (float)p.act_hi[0], (float)p.act_hi[1], a2);
-                f_t = (double)a2[0]; al = (double)a2[1];
             }
-            auto nz = make_noise<MODE>(nv, n, i, cur, nv.offset + (uint64_t)k);
-            const double t = time_at(tv, e.counter, p.dt);
-            const double tb = t + p.dt, tb2 = tb + p.dt;
-            e.counter += 1;
-            const ActionTerms a = action_terms<MISM>(f_t, al, p);
-            sim_step<MISM>(e, t, tb, tb2, a, p, nz);
-            o = observe(e, p);
-            if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; overflow |= nz.overflow != 0; }
+        } else if constexpr (SRC == MR_ACTIONS_BROADCAST) {
+            f_t = (double)io.actions[2 * k]; al = (double)io.actions[2 * k + 1];
+        } else if constexpr (SRC == MR_ACTIONS_PHILOX) {
+            double u[4];
+            philox_uniform4(p, nv.env_base + (uint64_t)i, nv.offset + (uint64_t)k, kPurposeAction, u);
+            f_t = p.act_hi[0] * u[0]; al = p.act_hi[1] * u[1];   // U[0,20) x U[0,2pi)
+        } else {
+            const float obs5[5] = {(float)e.x, (float)e.y, 0.f, 0.f, (float)o.d};
+            float a2[2];
+            if constexpr (SRC == kSrcActorTc)
+                actor_tc_forward(*reinterpret_cast<ActorTcSmem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], k, a2);
+            else
+                actor_forward_smem(s_actor, obs5, (float)p.act_hi[0], (float)p.act_hi[1], a2);
+            f_t = (double)a2[0]; al = (double)a2[1];
+        }
+        auto nz = make_noise<MODE>(nv, n, live ? i : 0, cur, nv.offset + (uint64_t)k);
+        const double t = time_at(tv, e.counter, p.dt);
+        const double tb = t + p.dt, tb2 = tb + p.dt;
+        e.counter += 1;
+        const ActionTerms a = action_terms<MISM>(f_t, al, p);
+        sim_step<MISM>(e, t, tb, tb2, a, p, nz);
+        o = observe(e, p);
+        if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; overflow |= nz.overflow != 0; }
+        if (live) {
             if (io.traj_xy) {
                 io.traj_xy[((int64_t)k * 2) * n + i] = (T)e.x;
                 io.traj_xy[((int64_t)k * 2 + 1) * n + i] = (T)e.y;
@@ -77,31 +91,35 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             if (io.traj_done) io.traj_done[(int64_t)k * n + i] = o.done ? 1 : 0;
             acc[MR_STAT_ENV_STEPS] += 1.0;
             acc[MR_STAT_SUM_REWARD] += o.rew;
-            if (o.done) {
+        }
+        if (o.done) {
+            if (live) {
                 acc[MR_STAT_EPISODES] += 1.0;
                 acc[MR_STAT_SUM_LENGTH] += (double)e.counter;
                 if (o.why == 1) acc[MR_STAT_GOAL] += 1.0;
                 else if (o.why == 2) acc[MR_STAT_OUT_OF_BOUNDS] += 1.0;
                 else acc[MR_STAT_TIMEOUT] += 1.0;
-                if (p.auto_reset) {
-                    int ov = 0;
-                    auto_reset_env<MODE, MISM>(e, nv, n, i, cur, nv.offset + (uint64_t)k, p, ov);
-                    overflow |= ov != 0;
-                }
+            }
+            if (p.auto_reset) {
+                int ov = 0;
+                auto_reset_env<MODE, MISM>(e, nv, n, live ? i : 0, cur, nv.offset + (uint64_t)k, p, ov);
+                overflow |= ov != 0;
             }
         }
+    }
+    if constexpr (SRC == kSrcActorTc) actor_tc_teardown(*reinterpret_cast<ActorTcSmem*>(s_dyn));
+
+    if (live) {
         if (overflow) e.status |= kNoiseOverflow;
         if (e.status) acc[MR_STAT_FAILED] += 1.0;
-
         const double t_out = time_at(tv, e.counter, p.dt);
         st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy;
         st.h[i] = encode_h<T>(e.h, (t_out + p.dt) - t_out);
         st.counter[i] = e.counter;
         if constexpr (MODE == MR_NOISE_TABLE) st.cursor[i] = cur;
         if (e.status) st.status[i] |= (uint8_t)e.status;
-        // outputs of the LAST step (terminal observation if that step ended an episode)
+        // outputs of the LAST step (after an auto reset: the first observation of the new episode)
         if (out.obs) {
-            // after an auto reset e.x/e.y are the fresh start; report them with their distance
             out.obs[i] = (T)e.x; out.obs[out.stride + i] = (T)e.y;
             out.obs[2 * out.stride + i] = (T)0; out.obs[3 * out.stride + i] = (T)0;
             out.obs[4 * out.stride + i] = (T)sqrt(e.x * e.x + e.y * e.y);
@@ -137,8 +155,22 @@ static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const O
             env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_BROADCAST><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
         case MR_ACTIONS_PHILOX:
             env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_PHILOX><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
-        case MR_ACTIONS_ACTOR:
-            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_ACTOR><<<blocks, threads, kActorParams * sizeof(float), s>>>(sv, rv, ov, nv, tv, p, n); break;
+        case MR_ACTIONS_ACTOR: {
+            // default: hidden layer on the tensor cores (tcgen05); MR_ACTOR_PATH=simt selects the CUDA-core MLP
+            static const bool simt = [] { const char* e = getenv("MR_ACTOR_PATH"); return e && e[0] == 's'; }();
+            if (simt) {
+                env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_ACTOR><<<blocks, threads, kActorParams * sizeof(float), s>>>(sv, rv, ov, nv, tv, p, n);
+            } else {
+                static bool attr = false;
+                if (!attr) {
+                    cudaFuncSetAttribute(env_rollout_kernel<T, MODE, MISM, kSrcActorTc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(ActorTcSmem));
+                    attr = true;
+                }
+                env_rollout_kernel<T, MODE, MISM, kSrcActorTc><<<blocks, kTcRows, sizeof(ActorTcSmem), s>>>(sv, rv, ov, nv, tv, p, n);
+            }
+            break;
+        }
         default: return fail(MR_ERR_ARG, "mr_env_rollout: unknown action source %d", rv.action_source);
     }
     return check_launch("mr_env_rollout");

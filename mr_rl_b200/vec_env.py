@@ -261,10 +261,14 @@ class VecMREnv:
             a_dev = self._pinned["act_dev"] = torch.empty(n, 2, dtype=self.dtype, device=self.device)
         a_dev.copy_(a_pin, non_blocking=True)
         self.step(a_dev)
+        fresh = "obs" not in self._pinned
         o_pin = self._pinned_buf("obs", (5, n), self.dtype)
         r_pin = self._pinned_buf("rew", (n,), self.dtype)
         d_pin = self._pinned_buf("done", (n,), torch.uint8)
-        o_pin.copy_(self._obs[:, :n], non_blocking=True)
+        if fresh:
+            o_pin.zero_()          # goal rows 2, 3 are always 0 (MR_env.py:57): written once, never re-copied
+        o_pin[:2].copy_(self._obs[:2, :n], non_blocking=True)
+        o_pin[4].copy_(self._obs[4, :n], non_blocking=True)
         r_pin.copy_(self._rew[:n], non_blocking=True)
         d_pin.copy_(self._done[:n], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
