@@ -15,6 +15,8 @@
  *                       RL/MR_ddpg.py:268-311   closed loop with ActorNetwork.predict (:124-149)
  *   mr_gp_predict    <- LearningModule.error / objective / predict -> sklearn GPR.predict
  *                       (Learning_module.py:10-24,186-224)
+ *   mr_gp_correct_heading <- LearningModule.predict's minimize_scalar(objective, 'Bounded')
+ *                       (Learning_module.py:215, utils.py:194-196)
  *   mr_actor_forward <- ActorNetwork.predict    (RL/MR_ddpg.py:124-149)
  *
  * Conventions
@@ -202,6 +204,14 @@ typedef struct mr_gp_model {
 int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* mean, double* std,
                   void* workspace, int64_t workspace_bytes, void* stream);
 int64_t mr_gp_workspace_bytes(const mr_gp_model* gp, int64_t n_q, int32_t want_std);
+
+/* LearningModule.predict's search (Learning_module.py:198-215, utils.find_alpha_corrected) for n desired
+ * velocities vd[n][2]: bounded scalar minimisation over alpha in [-pi, pi] (scipy _minimize_scalar_bounded:
+ * golden section + parabolic steps, xatol 1e-5, maxiter 500) of `objective` (Learning_module.py:10-24) with
+ * both GP means evaluated on the device inside the loop.  alpha_out[n]; nfev_out[n] may be NULL.  The
+ * posterior at the minimiser (Learning_module.py:221-222) is a following mr_gp_predict call. */
+int mr_gp_correct_heading(const mr_gp_model* gpx, const mr_gp_model* gpy, const double* vd, int64_t n, double a0,
+                          double freq, double drift_x, double drift_y, double* alpha_out, int32_t* nfev_out, void* stream);
 
 /* ---- DDPG actor forward (RL/MR_ddpg.py:124-149) --------------------------------------
  * Packed float32 parameters (input-major matrices W[in][out]):

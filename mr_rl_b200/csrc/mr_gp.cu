@@ -148,6 +148,120 @@ __global__ void gp_std_finish_kernel(const double* __restrict__ ssq, int64_t n_q
     std[i] = sqrt(v);
 }
 
+
+// ---- LearningModule.predict: batched bounded scalar minimisation with the GP means in the loop ----
+// One warp per desired velocity.  The control flow is scipy's _minimize_scalar_bounded (golden section
+// + parabolic interpolation, xatol = 1e-5, maxiter = 500) on bounds [-pi, pi], evaluated redundantly
+// by all lanes; each objective call (Learning_module.py:10-24) needs the two GP posterior means, which
+// the 32 lanes compute cooperatively (lane-strided training points, xor-shuffle reduction).
+struct HeadingProblem { double a0f, dx, dy; };
+
+__device__ __forceinline__ double gp_objective_warp(double alpha, double vdx, double vdy, const HeadingProblem& hp,
+                                                    const double* __restrict__ xsx, const double* __restrict__ ax,
+                                                    double lsx, const double* __restrict__ xsy,
+                                                    const double* __restrict__ ay, double lsy, int n_pad, int n_train,
+                                                    int lane) {
+    const double qx = alpha / lsx, qy = alpha / lsy;
+    double sx = 0.0, sy = 0.0;
+    for (int j = lane; j < n_pad; j += 32) {
+        const double d0 = qx - xsx[j], d1 = qy - xsy[j];
+        double kx = exp(-0.5 * (d0 * d0)), ky = exp(-0.5 * (d1 * d1));
+        if (j >= n_train) { kx = 0.0; ky = 0.0; }
+        sx = fma(kx, ax[j], sx);
+        sy = fma(ky, ay[j], sy);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, off);
+        sy += __shfl_xor_sync(0xffffffffu, sy, off);
+    }
+    const double ex = sx + hp.dx - vdx, ey = sy + hp.dy - vdy;     // mux + Dx - v_d[0], muy + Dy - v_d[1]
+    double s, c;
+    sincos(alpha, &s, &c);
+    return hp.a0f * hp.a0f + ex * ex + 2 * hp.a0f * c * ex + ey * ey + 2 * hp.a0f * s * ey;
+}
+
+__global__ void __launch_bounds__(256)
+gp_correct_heading_kernel(const double* __restrict__ vd, int64_t n, HeadingProblem hp, const double* __restrict__ xsx,
+                          const double* __restrict__ ax, double lsx, const double* __restrict__ xsy,
+                          const double* __restrict__ ay, double lsy, int n_pad, int n_train, double lo, double hi,
+                          double xatol, int maxfun, double* __restrict__ alpha_out, int32_t* __restrict__ nfev_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const double vdx = vd[2 * row], vdy = vd[2 * row + 1];
+    auto f = [&](double x) { return gp_objective_warp(x, vdx, vdy, hp, xsx, ax, lsx, xsy, ay, lsy, n_pad, n_train, lane); };
+
+    const double sqrt_eps = sqrt(2.2e-16);
+    const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
+    double a = lo, b = hi;
+    double fulc = a + golden_mean * (b - a);
+    double nfc = fulc, xf = fulc;
+    double rat = 0.0, e = 0.0;
+    double x = xf;
+    double fx = f(x);
+    int num = 1;
+    double ffulc = fx, fnfc = fx;
+    double xm = 0.5 * (a + b);
+    double tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+    double tol2 = 2.0 * tol1;
+    while (fabs(xf - xm) > (tol2 - 0.5 * (b - a))) {
+        bool golden = true;
+        if (fabs(e) > tol1) {                                   // try a parabolic fit
+            golden = false;
+            double r = (xf - nfc) * (fx - ffulc);
+            double q = (xf - fulc) * (fx - fnfc);
+            double p = (xf - fulc) * q - (xf - nfc) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) p = -p;
+            q = fabs(q);
+            r = e;
+            e = rat;
+            if ((fabs(p) < fabs(0.5 * q * r)) && (p > q * (a - xf)) && (p < q * (b - xf))) {
+                rat = (p + 0.0) / q;
+                x = xf + rat;
+                if (((x - a) < tol2) || ((b - x) < tol2)) {
+                    const double dm = xm - xf;
+                    const double si = (dm > 0.0 ? 1.0 : (dm < 0.0 ? -1.0 : 0.0)) + (dm == 0.0 ? 1.0 : 0.0);
+                    rat = tol1 * si;
+                }
+            } else {
+                golden = true;
+            }
+        }
+        if (golden) {                                           // golden-section step
+            e = (xf >= xm) ? a - xf : b - xf;
+            rat = golden_mean * e;
+        }
+        const double si = (rat > 0.0 ? 1.0 : (rat < 0.0 ? -1.0 : 0.0)) + (rat == 0.0 ? 1.0 : 0.0);
+        x = xf + si * fmax(fabs(rat), tol1);
+        const double fu = f(x);
+        ++num;
+        if (fu <= fx) {
+            if (x >= xf) a = xf; else b = xf;
+            fulc = nfc; ffulc = fnfc;
+            nfc = xf; fnfc = fx;
+            xf = x; fx = fu;
+        } else {
+            if (x < xf) a = x; else b = x;
+            if ((fu <= fnfc) || (nfc == xf)) {
+                fulc = nfc; ffulc = fnfc;
+                nfc = x; fnfc = fu;
+            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
+                fulc = x; ffulc = fu;
+            }
+        }
+        xm = 0.5 * (a + b);
+        tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+        tol2 = 2.0 * tol1;
+        if (num >= maxfun) break;
+    }
+    if (lane == 0) {
+        alpha_out[row] = xf;
+        if (nfev_out) nfev_out[row] = num;
+    }
+}
+
 constexpr int64_t kGpChunk = 16384;   // queries per pass of the variance pipeline (K_q chunk = chunk * n_pad * 8 B)
 
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -227,6 +341,27 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
         if (rc) return rc;
     }
     return MR_OK;
+}
+
+
+int mr_gp_correct_heading(const mr_gp_model* gpx, const mr_gp_model* gpy, const double* vd, int64_t n, double a0,
+                          double freq, double drift_x, double drift_y, double* alpha_out, int32_t* nfev_out, void* stream) {
+    using namespace mr;
+    if (!gpx || !gpy || !gpx->x_train_scaled || !gpy->x_train_scaled || !gpx->alpha || !gpy->alpha)
+        return fail(MR_ERR_ARG, "mr_gp_correct_heading: null model");
+    if (gpx->dim != 1 || gpy->dim != 1) return fail(MR_ERR_UNSUPPORTED, "mr_gp_correct_heading: heading GPs have dim 1");
+    if (gpx->n_pad != gpy->n_pad || gpx->n_train != gpy->n_train)
+        return fail(MR_ERR_ARG, "mr_gp_correct_heading: the two GPs must share their training inputs");
+    if (n < 0) return fail(MR_ERR_ARG, "mr_gp_correct_heading: bad n");
+    if (n == 0) return MR_OK;
+    if (!vd || !alpha_out) return fail(MR_ERR_ARG, "mr_gp_correct_heading: null vd/alpha_out");
+    HeadingProblem hp{a0 * freq, drift_x, drift_y};
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n * 32 + threads - 1) / threads);
+    gp_correct_heading_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        vd, n, hp, gpx->x_train_scaled, gpx->alpha, gpx->length_scale, gpy->x_train_scaled, gpy->alpha, gpy->length_scale,
+        gpx->n_pad, gpx->n_train, -3.141592653589793, 3.141592653589793, 1e-5, 500, alpha_out, nfev_out);
+    return check_launch("mr_gp_correct_heading");
 }
 
 int32_t mr_actor_param_count(void) { return mr::kActorParams; }

@@ -121,14 +121,27 @@ class LearningModule:
         return (a0f ** 2 + (mux + self.Dx - vd[0]) ** 2 + 2 * a0f * np.cos(alpha) * (mux + self.Dx - vd[0])
                 + (muy + self.Dy - vd[1]) ** 2 + 2 * a0f * np.sin(alpha) * (muy + self.Dy - vd[1]))
 
+    def predict_batch(self, vd, return_nfev=False):
+        """LearningModule.predict for vd [N, 2] on the device: the bounded minimisation of the objective
+        (scipy's algorithm, GP means in the loop) and the posterior at the minimiser.
+        Returns (alpha, muX, muY, sigX, sigY) device tensors."""
+        import ctypes as C
+
+        from . import _lib as L
+        vd = torch.as_tensor(vd, dtype=torch.float64, device=self.device).reshape(-1, 2).contiguous()
+        n = vd.shape[0]
+        alpha = torch.empty(n, dtype=torch.float64, device=vd.device)
+        nfev = torch.empty(n, dtype=torch.int32, device=vd.device)
+        stream = C.c_void_p(torch.cuda.current_stream(vd.device).cuda_stream)
+        rc = L.load().mr_gp_correct_heading(C.byref(self._dx._c), C.byref(self._dy._c), vd.data_ptr(), n, float(self.a0),
+                                            float(self.freq), float(self.Dx), float(self.Dy), alpha.data_ptr(),
+                                            nfev.data_ptr(), stream)
+        L.check(rc, "mr_gp_correct_heading")
+        mx, my, sx, sy = self.gp_batch(alpha, True)
+        return (alpha, mx, my, sx, sy, nfev) if return_nfev else (alpha, mx, my, sx, sy)
+
     def predict(self, vd):
-        """Learning_module.py:198-224: bounded scalar minimisation of the objective over alpha, then
-        the posterior at the minimiser.  The minimiser itself runs on the host (scipy), each objective
-        evaluation on the device."""
-        from scipy.optimize import minimize_scalar
-        result = minimize_scalar(lambda a: float(np.ravel(self._objective(a, vd))[0]), method="Bounded",
-                                 bounds=[-np.pi, np.pi])
-        X = np.array(result.x)
-        a = torch.tensor([float(result.x)], dtype=torch.float64, device=self.device)
-        out = torch.stack(self.gp_batch(a, True)).cpu().numpy()
-        return X, out[0], out[1], out[2], out[3]
+        """Learning_module.py:198-224: bounded scalar minimisation of the objective over alpha, then the
+        posterior at the minimiser -> (alpha, muX, muY, sigX, sigY).  Runs entirely on the device."""
+        out = torch.stack(self.predict_batch(np.asarray(vd, dtype=np.float64).reshape(1, 2))).cpu().numpy()
+        return np.array(out[0, 0]), out[1], out[2], out[3], out[4]

@@ -143,13 +143,15 @@ def gen_gp():
     alphas = qrng.uniform(-np.pi, np.pi, 64)
     obj = np.array([float(np.ravel(LM.objective(a, lm.a0, lm.freq, vd[i], lm.gprX, lm.gprY, lm.Dx, lm.Dy))[0])
                     for i, a in enumerate(alphas)])                         # Learning_module.py:10-24
+    # LearningModule.predict (Learning_module.py:198-224): the bounded minimisation itself, live
+    pred = np.array([np.concatenate([np.atleast_1d(np.asarray(o, dtype=float)).ravel() for o in lm.predict(v)]) for v in vd[:24]])
     q = np.linspace(-np.pi, np.pi, 257).reshape(-1, 1)
     mx, sx = lm.gprX.predict(q, return_std=True)
     my, sy = lm.gprY.predict(q, return_std=True)
     np.savez_compressed(
         os.path.join(GOLDEN_DIR, "gp.npz"), versions=versions(), X=X, yx=yx, yy=yy,
         lsx=0.2, lsy=0.25, noise=0.008, alpha_x=lm.gprX.alpha_, alpha_y=lm.gprY.alpha_,
-        hyper=np.array([lm.a0, lm.freq, lm.Dx, lm.Dy]), vd=vd, error=err, obj_alpha=alphas, objective=obj,
+        hyper=np.array([lm.a0, lm.freq, lm.Dx, lm.Dy]), vd=vd, error=err, predict=pred, obj_alpha=alphas, objective=obj,
         grid=q.ravel(), grid_mx=mx, grid_sx=sx, grid_my=my, grid_sy=sy)
     print("gp: error() rows", err.shape, "sigma range", err[:, 2].min(), err[:, 2].max())
 
