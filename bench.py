@@ -305,6 +305,53 @@ def run_ours(args):
             torch.cuda.synchronize()
             sms = ev0.elapsed_time(ev1) / 20
             extras["config1_4096_envs_k64"] = {"value": 4096 * 64 / (sms * 1e-3), "unit": UNIT, "ms_per_launch": sms}
+            # BASELINE configs[4]: DDPG actor (MR_ddpg architecture, random init) in the loop, hidden layer on tcgen05
+            from mr_rl_b200 import init_actor, pack_actor
+            packed = pack_actor(init_actor(0), dev)
+            env.rollout(policy=packed, k_steps=64)
+            torch.cuda.synchronize()
+            ev0.record()
+            env.rollout(policy=packed, k_steps=64)
+            ev1.record()
+            torch.cuda.synchronize()
+            ams = ev0.elapsed_time(ev1)
+            extras["config4_actor_in_loop_k64"] = {"value": n * 64 / (ams * 1e-3), "unit": UNIT, "ms_per_launch": ams,
+                                                   "envs": n, "actor": "5-64-BN-ReLU-64-BN-ReLU-2 tanh, fp32, 3xTF32 tcgen05 hidden layer"}
+            # BASELINE configs[3]: GP disturbance model, 2000 training points, 262144 queries (both GPs, mean + std)
+            try:
+                from mr_rl_b200 import DeviceGP
+                from oracle import mr_oracle as mo
+                rng = np.random.default_rng(0)
+                X = np.sort(rng.uniform(-np.pi, np.pi, 2000))
+                yx = 0.2 + 0.5 * np.cos(X + 0.3) + 0.09 * rng.standard_normal(2000)
+                yy = -0.1 + 0.4 * np.sin(X - 0.2) + 0.09 * rng.standard_normal(2000)
+                gps = []
+                for yv, ls in ((yx, 0.2), (yy, 0.25)):
+                    m = mo.fit_fixed_gp(X, yv, ls, 0.008)            # host fit (sklearn's job in the reference)
+                    gps.append(DeviceGP(m.X_train, m.alpha, m.L, m.length_scale, m.noise_level, device=dev))
+                q = env.last_pos[:262144, 1].contiguous() * 0 + torch.rand(262144, device=dev, dtype=torch.float64) * 6.28 - 3.14
+                for gp_ in gps:
+                    gp_.predict(q, True)
+                torch.cuda.synchronize()
+                ev0.record()
+                for gp_ in gps:
+                    gp_.predict(q, True)
+                ev1.record()
+                torch.cuda.synchronize()
+                gms = ev0.elapsed_time(ev1)
+                ev0.record()
+                for gp_ in gps:
+                    gp_.predict(q, False)
+                ev1.record()
+                torch.cuda.synchronize()
+                gmm = ev0.elapsed_time(ev1)
+                extras["config3_gp_262k_queries_2k_train"] = {
+                    "mean_std_ms_both_gps": gms, "mean_only_ms_both_gps": gmm, "queries_per_s_mean_std": 262144 / (gms * 1e-3),
+                    "variance_contraction_tflops_fp64": 2 * 262144 * 2048.0 ** 2 / (gms * 1e-3) / 1e12,
+                    "kernels": "gp_kq_mean_kernel (fp64 exp) + gp_var_kernel (fp64 DMMA m8n8k4, triangular)"}
+                del gps
+            except Exception as ex:                                  # never let a side number break the headline
+                extras["config3_gp_262k_queries_2k_train"] = {"error": str(ex)[:160]}
         barrier()
 
     if rank == 0:

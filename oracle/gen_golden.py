@@ -156,8 +156,40 @@ def gen_gp():
     print("gp: error() rows", err.shape, "sigma range", err[:, 2].min(), err[:, 2].max())
 
 
+def gen_learn():
+    """main.py flow at reduced size through the reference's own run_sim + LearningModule: idle run ->
+    estimateDisturbance, circle run -> learn().  Records the deterministic preprocessing outputs
+    (Dx, Dy, a0, X, Yx, Yy); the GPR hyper-parameter search itself is sklearn's and not pinned."""
+    mods = lr.load()
+    LM, utils = mods["Learning_module"], mods["utils"]
+    import contextlib, io
+    freq, a0_def, dt, sigma = 4.0, 1.5, 0.030, 0.5
+    idle = np.zeros((60, 3)); idle[:, 2] = np.arange(60) * dt
+    T = 240
+    circ = np.zeros((T, 3)); circ[:, 0] = freq; circ[:, 1] = np.linspace(-np.pi, np.pi, T); circ[:, 2] = np.arange(T) * dt
+    z1 = np.random.default_rng(31).standard_normal(60 * 1500)
+    z2 = np.random.default_rng(32).standard_normal(T * 1500)
+    with contextlib.redirect_stdout(io.StringIO()):
+        with lr.patched_noise(z1) as n1:
+            px_i, py_i, _, t_i, _ = utils.run_sim(idle, init_pos=np.array([0, 0]), noise_var=sigma, a0=a0_def, is_mismatched=True)
+            used1 = n1.cursor
+        with lr.patched_noise(z2) as n2:
+            px, py, al, tm, _ = utils.run_sim(circ, init_pos=np.array([0, 0]), noise_var=sigma, a0=a0_def, is_mismatched=True)
+            used2 = n2.cursor
+        lm = LM.LearningModule()
+        lm.gprX.n_restarts_optimizer = 0
+        lm.gprY.n_restarts_optimizer = 0
+        lm.estimateDisturbance(px_i, py_i, t_i)
+        a0 = lm.learn(px, py, al, tm.copy(), circ)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "learn.npz"), versions=versions(), idle=idle, circ=circ, z1=z1[:used1 + 8],
+                        z2=z2[:used2 + 8], px_idle=px_i, py_idle=py_i, t_idle=t_i, px=px, py=py, alpha=al, time=tm,
+                        Dx=lm.Dx, Dy=lm.Dy, a0=a0, X=lm.X, Yx=lm.Yx, Yy=lm.Yy, params=np.array([sigma, a0_def, freq]))
+    print("learn: a0", a0, "D", lm.Dx, lm.Dy, "n", len(lm.X), "draws", used1, used2)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     gen_single()
     gen_batch()
     gen_gp()
+    gen_learn()

@@ -1,0 +1,68 @@
+"""The main.py flow (idle run -> estimateDisturbance, circle run -> learn) through this repo's
+LearningModule: host preprocessing parity against the live reference (CPU), and the whole flow on the GPU."""
+import numpy as np
+import pytest
+
+from conftest import Golden, rel_err
+
+
+@pytest.fixture(scope="module")
+def golden_learn():
+    return Golden("learn.npz")
+
+
+def test_learn_preprocessing_matches_reference_on_cpu(golden_learn):
+    """estimateDisturbance / learn up to the GPR fit are pure host numpy: filtered velocities, drift, a0 and
+    the GP training targets must equal the reference's (Learning_module.py:46-59,63-120)."""
+    from mr_rl_b200.learning_module import LearningModule
+    g = golden_learn
+    lm = LearningModule.__new__(LearningModule)          # no device needed for the preprocessing
+    lm.Dx = lm.Dy = 0
+    lm.estimateDisturbance(g["px_idle"], g["py_idle"], g["t_idle"])
+    assert rel_err(lm.Dx, g["Dx"]) < 1e-12 and rel_err(lm.Dy, g["Dy"]) < 1e-12
+    N, px, py, vx, vy = lm._velocities(g["px"].astype(float), g["py"].astype(float), g["time"] - g["time"][0])
+    freq = g["circ"][0, 0]
+    speed = np.sqrt((vx - lm.Dx) ** 2 + (vy - lm.Dy) ** 2)[N:-N]
+    a0 = np.median(speed / freq)
+    assert rel_err(a0, g["a0"]) < 1e-12
+    al = g["alpha"][N:-N]
+    assert rel_err(vx[N:-N] - a0 * freq * np.cos(al), g["Yx"]) < 1e-10
+    assert rel_err(al.reshape(-1, 1), g["X"]) < 1e-15
+
+
+@pytest.mark.gpu
+def test_main_flow_on_the_device(golden_learn):
+    """run_sim (fused rollout, parity noise) -> learn (host sklearn fit) -> batched corrected headings."""
+    import torch
+
+    from mr_rl_b200 import LearningModule, run_sim
+    g = golden_learn
+    sigma, a0_def, freq = g["params"]
+    px_i, py_i, _, t_i, _ = run_sim(g["idle"], init_pos=np.array([0, 0]), noise_var=sigma, a0=a0_def, is_mismatched=True,
+                                    device="cuda:0", noise="table", noise_table=g["z1"][:, None])
+    px, py, al, tm, _ = run_sim(g["circ"], init_pos=np.array([0, 0]), noise_var=sigma, a0=a0_def, is_mismatched=True,
+                                device="cuda:0", noise="table", noise_table=g["z2"][:, None])
+    assert rel_err(px_i, g["px_idle"]) < 1e-9 and rel_err(py, g["py"]) < 1e-9      # trajectories = the reference's
+    lm = LearningModule(device="cuda:0")
+    lm.gprX.n_restarts_optimizer = 0
+    lm.gprY.n_restarts_optimizer = 0
+    lm.estimateDisturbance(px_i, py_i, t_i)
+    a0 = lm.learn(px, py, al, tm.copy(), g["circ"])
+    assert rel_err(a0, g["a0"]) < 1e-9 and rel_err(lm.Yx, g["Yx"]) < 1e-7
+    # device GP == the sklearn model it was uploaded from
+    q = np.linspace(-3, 3, 101)
+    m_ref, s_ref = lm.gprX.predict(q.reshape(-1, 1), return_std=True)
+    m, _, s, _ = lm.gp_batch(torch.as_tensor(q, device="cuda:0"), True)
+    assert np.allclose(m.cpu().numpy(), m_ref, rtol=1e-7, atol=1e-9) and np.allclose(s.cpu().numpy(), s_ref, rtol=1e-5, atol=1e-8)
+    # corrected headings for a batch of desired velocities (main.py:145-155)
+    ang = np.linspace(0, np.pi / 2, 64)
+    vd = a0 * freq * np.stack([np.cos(ang), np.sin(ang)], 1)
+    alpha, mx, my, sx, sy = lm.predict_batch(vd)
+    assert alpha.shape == (64,) and torch.isfinite(alpha).all() and float(sx.min()) > 0
+    vxp, vyp = lm.velocity_model(torch.full((64,), float(freq), device="cuda:0"), alpha)
+    # the corrected heading brings the predicted velocity closer to the desired one than the naive heading
+    vxn, vyn = lm.velocity_model(torch.full((64,), float(freq), device="cuda:0"), torch.as_tensor(ang, device="cuda:0"))
+    vd_t = torch.as_tensor(vd, device="cuda:0")
+    err_c = torch.hypot(vxp + lm.Dx - vd_t[:, 0], vyp + lm.Dy - vd_t[:, 1]).mean()
+    err_n = torch.hypot(vxn + lm.Dx - vd_t[:, 0], vyn + lm.Dy - vd_t[:, 1]).mean()
+    assert float(err_c) <= float(err_n) + 1e-9
