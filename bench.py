@@ -227,7 +227,7 @@ def run_ours(args):
     bytes_per_launch = BYTES_PER_ENV_STEP[args.dtype] * n
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "env_step_kernel",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "env_step_tma_kernel",
                 "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP[args.dtype], "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
     prof = os.path.join(ROOT, "profiles", "traffic_step_kernel.json")

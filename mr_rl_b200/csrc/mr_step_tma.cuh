@@ -82,8 +82,11 @@ struct StepSmem {
     alignas(8) uint64_t full[kStagesIn];
 };
 
+#ifndef MR_TMA_MINB
+#define MR_TMA_MINB 1
+#endif
 template <class T, int MODE, bool MISM>
-__global__ void __launch_bounds__(TileOf<T>::value)
+__global__ void __launch_bounds__(TileOf<T>::value, MR_TMA_MINB)
 env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
                     Params p, int64_t n_tiles, int64_t n_total) {
     constexpr int kTile = TileOf<T>::value;

@@ -389,3 +389,33 @@ def test_generated_noise_has_the_reference_step_statistics():
     assert abs(np.corrcoef(d1[:, 0], d1[:, 1])[0, 1]) < 0.01          # x and y noise are independent
     k = ((d1 - d1.mean(0)) / d1.std(0)) ** 4
     assert np.all(np.abs(k.mean(0) - 3.0) < 0.1)                      # Gaussian kurtosis
+
+
+@pytest.mark.parametrize("sigma,mism", [(1.0, False), (0.5, True), (0.0, False)])
+def test_config2_4096_envs_fused_k64_against_c_oracle(sigma, mism):
+    """BASELINE configs[1] (4096 envs, fused K = 64 steps per launch), parity mode: every env of the batch
+    against the plain-C oracle on the same per-env noise streams — done flags and draw counts exact,
+    positions 1e-9."""
+    from oracle import c_oracle
+    n, K, launches = 4096, 64, 2
+    T = K * launches
+    rng = np.random.default_rng(99)
+    init = rng.uniform(100, 120, (n, 2)).astype(np.float32).astype(np.float64)
+    acts = np.stack([rng.uniform(0, 20, (T, n)), rng.uniform(0, 2 * np.pi, (T, n))], -1)
+    L = 26 * T + 64
+    z = rng.standard_normal((n, L))
+    ref = c_oracle.rollout(init, acts, sigma, 1.3, mism=mism, mism_at_reset=False, z=z)
+    assert ref["bad"] == 0
+    env = make_env(n, noise="table", noise_table=np.ascontiguousarray(z.T))
+    env.reset(init=init, noise_var=sigma, a0=1.3, is_mismatched=mism)
+    a_dev = torch.as_tensor(acts, device="cuda:0")
+    xy, dn = [], []
+    for k0 in range(0, T, K):
+        res = env.rollout(actions=a_dev[k0:k0 + K], record=True, record_done=True)
+        xy.append(res["xy"].cpu().numpy()); dn.append(res["done_traj"].cpu().numpy())
+    xy = np.concatenate(xy).transpose(0, 2, 1)
+    assert np.array_equal(np.concatenate(dn), ref["done"])
+    assert np.array_equal(env._cursor[:n].cpu().numpy().astype(np.int64), ref["cursor"])
+    assert rel_err(xy, ref["pos"]) < FP64_TOL
+    assert rel_err(env._state[:, :n].t().cpu().numpy(), ref["final"]) < FP64_TOL
+    env.check_status()
