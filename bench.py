@@ -355,10 +355,13 @@ def run_ours(args):
         barrier()
 
     if rank == 0:
-        cpu_val, cores, sample, cpu_extra = cpu_port_throughput(args.cpu_seconds if world == 1 else 4.0, args.sigma)
-        cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                        "implementation": "oracle/scipy_env.py: reference env restated on scipy.integrate.RK45",
-                        **cpu_extra, "c_port": c_port_throughput(args.sigma)}
+        if world == 1:
+            cpu_val, cores, sample, cpu_extra = cpu_port_throughput(args.cpu_seconds, args.sigma)
+            cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                            "implementation": "oracle/scipy_env.py: reference env restated on scipy.integrate.RK45",
+                            **cpu_extra, "c_port": c_port_throughput(args.sigma)}
+        else:
+            cpu_baseline = {"skipped": "the CPU baseline is timed on rank 0 at N=1 only"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
