@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -216,7 +216,20 @@ def run_ours(args):
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = env.kernel_launches - launches0
+    # the timed region lasts a few ms — shorter than nvidia-smi's sampling period — so the same kernel
+    # keeps running (untimed) for ~0.4 s while the clock sampler collects its under-load samples
+    if rank == 0:
+        t_ext = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t_ext < 0.4:
+            for _ in range(50):
+                env.step(acts[k % pool]); k += 1
+            torch.cuda.synchronize()
+        t_wall1 = time.perf_counter()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed region + 0.4 s of the same kernel back to back (20 ms nvidia-smi period)"
+    barrier()
     env.check_status()
 
     value = world * n * args.steps / (ms * 1e-3)
