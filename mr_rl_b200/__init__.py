@@ -6,6 +6,7 @@ Public surface (mirrors the reference's names):
     run_sim                       utils.run_sim as one fused rollout launch
     LearningModule, DeviceGP      GP disturbance model with inference on the device
     init_actor / pack_actor / actor_forward   DDPG actor forward for the in-loop policy
+    experiment_dict / save_experiment          recorded rollouts in the reference's MRExperiment pickle layout
 
 All compute runs in hand-written sm_100a kernels behind the C ABI in include/mr_rl_b200.h;
 there is no CPU fallback (importing is cheap, the first compute call loads the library).
@@ -15,6 +16,7 @@ from .actor import actor_forward, init_actor, pack_actor  # noqa: F401
 from .gp import DeviceGP  # noqa: F401
 from .learning_module import LearningModule  # noqa: F401
 from .mr_env import MR_Env, Simulator  # noqa: F401
+from .recording import experiment_dict, load_experiment, save_experiment  # noqa: F401
 from .spaces import Box  # noqa: F401
 from .utils import run_sim  # noqa: F401
 from .vec_env import VecMREnv, shard_range  # noqa: F401

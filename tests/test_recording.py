@@ -1,0 +1,83 @@
+"""MRExperiment wire format (MR_data.py) written from rollout arrays; checked against the live reference's
+own logger when /root/reference is available (build container), structurally otherwise."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from mr_rl_b200.recording import experiment_dict, load_experiment, save_experiment
+from oracle import live_reference as lr
+from oracle import mr_oracle as mo
+
+
+def _oracle_run(T=40):
+    rng = np.random.default_rng(4)
+    acts = np.stack([rng.uniform(0, 20, T), rng.uniform(0, 2 * np.pi, T)], 1)
+    z = rng.standard_normal(40 * T)
+    r = mo.rollout(acts, [110.0, 105.0], 1.0, 1.0, False, z)
+    return acts, z, r
+
+
+def test_experiment_dict_structure_roundtrip(tmp_path):
+    acts, z, r = _oracle_run()
+    xy = r["pos"].T[None].transpose(2, 1, 0)                    # [K, 2, N=1]
+    exp = experiment_dict([110.0, 105.0], acts, xy, done=r["done"][:, None])
+    assert exp["iterations"] == 0 and exp["steps"][0] == len(acts)
+    assert exp["states"][0].shape == (41, 2) and exp["observations"][0].shape == (41, 5)
+    assert exp["actions"][0].shape == (41, 2) and exp["rewards"][0].shape == (41, 1)
+    assert np.all(exp["actions"][0][0] == 0) and exp["rewards"][0][0, 0] == 0 and np.all(exp["rewards"][0][1:] == 10)
+    assert np.allclose(exp["observations"][0][:, 4], np.hypot(*exp["states"][0].T))
+    p = tmp_path / "exp.pickle"
+    save_experiment(exp, p)
+    back = load_experiment(p)
+    assert set(back) == {"iterations", "states", "observations", "actions", "rewards", "steps", "info", "viewer",
+                         "scream", "obs_states_str", "time_step"}
+    assert np.array_equal(back["states"][0], exp["states"][0])
+
+
+@pytest.mark.skipif(not lr.available(), reason="needs the unmodified reference (build container)")
+def test_wire_format_equals_the_reference_logger():
+    """Run the live reference with its MRExperiment logger attached (MR_env.py:94-95,190-198) and compare the
+    dict it would pickle with the one built from the trajectory arrays."""
+    acts, z, r = _oracle_run()
+    mods = lr.load()
+    env = lr.new_env()
+    import importlib
+    MRExperiment = importlib.import_module("MR_data").MRExperiment
+    env.MR_data = MRExperiment()
+    env.name_experiment = "unused"
+    with lr.patched_noise(z), contextlib.redirect_stdout(io.StringIO()):
+        env.reset(init=np.array([110.0, 105.0]), noise_var=1.0, a0=1.0)
+        for a in acts:
+            env.step(a)
+    ref = env.MR_data.__dict__
+    xy = r["pos"].T[None].transpose(2, 1, 0)
+    mine = experiment_dict([110.0, 105.0], acts, xy)
+    assert set(mine) == set(ref)
+    n = ref["steps"][0]
+    assert n == len(acts)
+    for key in ("states", "observations", "actions", "rewards"):
+        a, b = np.asarray(ref[key][0], dtype=np.float64), mine[key][0][:n + 1]
+        assert a.shape == b.shape, key
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-12), key
+    assert mine["time_step"] == ref["time_step"] and mine["iterations"] == ref["iterations"]
+
+
+@pytest.mark.gpu
+def test_recorded_device_rollout_in_reference_format(tmp_path):
+    import torch
+
+    from mr_rl_b200 import VecMREnv
+    n, K = 5, 60
+    env = VecMREnv(n, device="cuda:0", noise="philox", seed=2)
+    env.reset(init=np.array([110.0, 105.0]), noise_var=1.0, a0=1.0)
+    rng = np.random.default_rng(0)
+    acts = torch.as_tensor(np.stack([rng.uniform(0, 20, (K, n)), rng.uniform(0, 6.28, (K, n))], -1), device="cuda:0")
+    res = env.rollout(actions=acts, record=True, record_done=True)
+    exp = experiment_dict([110.0, 105.0], acts, res["xy"], done=res["done_traj"], until_done=True)
+    assert exp["iterations"] == n - 1 and all(exp["steps"][e] == 51 for e in range(n))      # timeout at counter 51
+    assert np.allclose(exp["states"][3][-1], res["xy"][50, :, 3].cpu().numpy())
+    save_experiment(exp, tmp_path / "e")
+    assert load_experiment(tmp_path / "e")["observations"][4].shape == (52, 5)
