@@ -78,8 +78,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         const double t = time_at(tv, e.counter, p.dt);
         const double tb = t + p.dt, tb2 = tb + p.dt;
         e.counter += 1;
-        const ActionTerms a = action_terms<MISM>(f_t, al, p);
-        sim_step<MISM>(e, t, tb, tb2, a, p, nz);
+        sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
         o = observe(e, p);
         if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; overflow |= nz.overflow != 0; }
         if (live) {

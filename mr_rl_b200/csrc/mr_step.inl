@@ -57,8 +57,7 @@ env_step_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, 
         auto nz = make_noise<MODE>(nv, n, i0 + j, MODE == MR_NOISE_TABLE ? pcur.v[j] : 0,
                                    nv.offset);
         e.counter += 1;                                               // MR_env.py:80
-        const ActionTerms a = action_terms<MISM>(f_t, al, p);
-        sim_step<MISM>(e, t, tb, tb2, a, p, nz);
+        sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
         const Observation o = observe(e, p);
         int32_t cur = 0;
         if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; if (nz.overflow) e.status |= kNoiseOverflow; }

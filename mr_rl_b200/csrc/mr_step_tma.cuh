@@ -168,8 +168,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
         e.h = decode_h<T>(h_raw, tb - t);
         auto nz = make_noise<MODE>(nv, n_total, i0 + tid, 0, nv.offset);
         e.counter += 1;                                     // MR_env.py:80
-        const ActionTerms a = action_terms<MISM>(f_t, al, p);
-        sim_step<MISM>(e, t, tb, tb2, a, p, nz);
+        sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
         const Observation o = observe(e, p);
         double d_out = o.d, il_next = tb2 - tb;
         if (p.auto_reset && o.done) {                       // reported obs = first obs of the new episode

@@ -30,8 +30,8 @@ extern "C" int host_core_rollout(const double* actions /*[T][2]*/, int T, double
         const double tb = t + p.dt, tb2 = tb + p.dt;
         e.counter += 1;
         int att;
-        if (mism) { const ActionTerms a = action_terms<true>(actions[2 * k], actions[2 * k + 1], p); att = sim_step<true>(e, t, tb, tb2, a, p, nz); }
-        else { const ActionTerms a = action_terms<false>(actions[2 * k], actions[2 * k + 1], p); att = sim_step<false>(e, t, tb, tb2, a, p, nz); }
+        if (mism) att = sim_step<true>(e, t, tb, tb2, actions[2 * k], actions[2 * k + 1], p, nz);
+        else att = sim_step<false>(e, t, tb, tb2, actions[2 * k], actions[2 * k + 1], p, nz);
         const Observation o = observe(e, p);
         pos[2 * k] = e.x; pos[2 * k + 1] = e.y; obs_d[k] = o.d; done[k] = o.done; counter[k] = e.counter;
         cursor[k] = nz.cursor; attempts[k] = att; carry[3 * k] = e.fx; carry[3 * k + 1] = e.fy; carry[3 * k + 2] = e.h;
