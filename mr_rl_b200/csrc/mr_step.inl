@@ -212,7 +212,13 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
             // persistent grid: exactly the CTAs that are co-resident, so there is never a second wave
             const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
             const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
-            env_step_tma_kernel<T, MODE, MISM><<<grid, kTile, smem, s>>>(sv, act, ov, nv, tv, p, n_tiles, n);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTile); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous tail
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, env_step_tma_kernel<T, MODE, MISM>, sv, act, ov, nv, tv, p, n_tiles, n);
             done = n_tiles * kTile;
         } else if (vec_ok && n >= VEC && force != 3 && force != 1) {
             const int64_t n_vec = (n / VEC) * VEC;

@@ -82,11 +82,12 @@ struct StepSmem {
     alignas(8) uint64_t full[kStagesIn];
 };
 
-#ifndef MR_TMA_MINB
-#define MR_TMA_MINB 1
+// at least 16 warps per SM (<= 128 registers): the generated-noise variant would otherwise take 136
+#ifndef MR_TMA_WARPS
+#define MR_TMA_WARPS 16
 #endif
 template <class T, int MODE, bool MISM>
-__global__ void __launch_bounds__(TileOf<T>::value, MR_TMA_MINB)
+__global__ void __launch_bounds__(TileOf<T>::value, MR_TMA_WARPS * 32 / TileOf<T>::value)
 env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
                     Params p, int64_t n_tiles, int64_t n_total) {
     constexpr int kTile = TileOf<T>::value;
@@ -102,6 +103,10 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
     sm.zero[tid] = (T)0;   // kTile threads
     fence_async_smem();
     __syncthreads();
+    // Programmatic dependent launch: everything above (smem carve-up, mbarrier init) overlaps the tail of
+    // the previous launch in the stream; the state rows it wrote are only touched after this wait.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     constexpr uint32_t kRow = kTile * sizeof(T);
     constexpr uint32_t kInBytes = 5 * kRow + 2 * kRow + kTile * 4;
