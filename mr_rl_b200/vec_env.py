@@ -109,6 +109,11 @@ class VecMREnv:
         self.want_state_prime = True
         self._pinned = {}
         self.kernel_launches = 0
+        # per-step call overhead: argument references and result views are built once
+        self._call_step = self.lib.mr_env_step
+        self._b_state, self._b_params, self._b_tt = C.byref(self._c_state), C.byref(self.params), C.byref(self._c_tt)
+        self._b_out, self._b_out_lean = C.byref(self._c_out), C.byref(self._c_out_lean)
+        self._views = (self._obs[:, :n].t(), self._rew[:n], self._done[:n], {})
 
     # ---- properties mirroring the reference attributes ------------------------------------
     @property
@@ -217,22 +222,23 @@ class VecMREnv:
     def step(self, actions):
         """actions: [N, 2] (f_t, alpha_t) device tensor.  Returns (obs [N,5], rew [N], done [N] uint8, info).
         The returned tensors are views of buffers that the next step overwrites."""
-        n = self.num_envs
         if not torch.is_tensor(actions):
             return self.step_host(actions)
+        n = self.num_envs
         a = actions
-        if a.device != self.device or a.dtype != self.dtype or not a.is_contiguous():
+        if a.device != self.device or a.dtype is not self.dtype or not a.is_contiguous():
             a = a.to(device=self.device, dtype=self.dtype).contiguous()
         if a.numel() != 2 * n:
             raise ValueError(f"actions must be [{n}, 2]")
         nz = self._noise_for(self.params.noise_var)
-        out = self._c_out if self.want_state_prime else self._c_out_lean
-        rc = self.lib.mr_env_step(C.byref(self._c_state), n, self._dt, C.byref(self.params), C.byref(nz),
-                                  C.byref(self._c_tt), _ptr(a), C.byref(out), self._stream())
-        L.check(rc, "mr_env_step")
+        rc = self._call_step(self._b_state, n, self._dt, self._b_params, C.byref(nz), self._b_tt, a.data_ptr(),
+                             self._b_out if self.want_state_prime else self._b_out_lean,
+                             torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            L.check(rc, "mr_env_step")
         self.kernel_launches += 1
         self._step_index += 1
-        return self.obs, self._rew[:n], self._done[:n], {}
+        return self._views
 
     def _pinned_buf(self, key, shape, dtype):
         b = self._pinned.get(key)
