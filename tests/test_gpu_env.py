@@ -468,3 +468,53 @@ def test_fp32_fused_rollout_and_tma_step_agree_with_fp64(golden_batch):
     assert rel_err(p32s, p64s) < FP32_TOL and rel_err(p32r, p64s) < FP32_TOL
     assert np.array_equal(d64s, d64r) and np.array_equal(d32s, d64s) and np.array_equal(d32r, d64s)
     assert d64s[50].all() and not d64s[49].any()          # counter > 50 ends every episode at step index 50
+
+
+def test_divergent_multi_attempt_regime_at_scale():
+    """main.py's regime (start at the origin, mismatched model, sigma = 0.5): 1-30 RK attempts per env step,
+    different for every env -> the cold generic integrator under heavy warp divergence.  Compared with the
+    C oracle on the same noise streams for every env; must also finish quickly."""
+    from oracle import c_oracle
+    n, T = 2048, 24
+    rng = np.random.default_rng(5)
+    init = np.zeros((n, 2))
+    acts = np.zeros((T, n, 2)); acts[..., 0] = 4.0; acts[..., 1] = rng.uniform(-np.pi, np.pi, (T, n))
+    L = 900 * T
+    z = rng.standard_normal((n, L))
+    ref = c_oracle.rollout(init, acts, 0.5, 1.5, mism=True, mism_at_reset=False, z=z, want_attempts=True)
+    assert ref["bad"] == 0 and ref["attempts"].max() > 10
+    env = make_env(n, noise="table", noise_table=np.ascontiguousarray(z.T))
+    env.reset(init=init, noise_var=0.5, a0=1.5, is_mismatched=True)
+    a_dev = torch.as_tensor(acts, device="cuda:0")
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    pos = []
+    for k in range(T):
+        env.step(a_dev[k])
+        pos.append(env.last_pos.clone())
+    t1.record(); torch.cuda.synchronize()
+    assert t0.elapsed_time(t1) < 2000.0
+    pos = torch.stack(pos).cpu().numpy()
+    assert np.array_equal(env._cursor[:n].cpu().numpy().astype(np.int64), ref["cursor"])      # same draw counts
+    assert rel_err(pos, ref["pos"]) < 1e-8          # positions pass through 0: relative to max(|ref|, 1e-12)
+    env.check_status()
+
+
+def test_long_soak_generated_noise_auto_reset():
+    """2^18 envs x 600 steps with generated noise and auto reset, fp64 and fp32: no failure flags, every
+    episode ends by timeout at 51 steps, counters stay in range."""
+    for dt in (torch.float64, torch.float32):
+        n = 1 << 18
+        env = make_env(n, dtype=dt, noise="philox", seed=77, auto_reset=True)
+        env.reset(init=None, noise_var=1.0, a0=1.0)
+        a = (torch.rand(4, n, 2, device="cuda:0", dtype=torch.float64) * torch.tensor([20.0, 6.28], device="cuda:0", dtype=torch.float64)).to(dt)
+        dones = torch.zeros((), device="cuda:0", dtype=torch.int64)
+        for k in range(600):
+            _, _, d, _ = env.step(a[k % 4])
+            dones += d.sum()
+        env.check_status()
+        assert int(dones) == n * (600 // 51)
+        c = env.counter.cpu().numpy()
+        assert c.min() >= 0 and c.max() <= 50
+        p = env.last_pos.cpu().numpy()
+        assert np.isfinite(p).all() and np.abs(p).max() < 200
