@@ -66,9 +66,51 @@ def actor_bench(n=1 << 20, K=64):
               f"({n*K*2*4544/ms/1e9:.1f} TFLOP/s fp32 in the MLP)")
 
 
+def heading_bench(n=262144, n_train=2000):
+    """LearningModule.predict for a batch: device bounded minimiser + posterior at the minimiser."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    from mr_rl_b200 import LearningModule
+    rng = np.random.default_rng(0)
+    X = np.sort(rng.uniform(-np.pi, np.pi, n_train)).reshape(-1, 1)
+    yx = 0.2 + 0.5 * np.cos(X[:, 0] + 0.3) + 0.09 * rng.standard_normal(n_train)
+    yy = -0.1 + 0.4 * np.sin(X[:, 0] - 0.2) + 0.09 * rng.standard_normal(n_train)
+    gX = GaussianProcessRegressor(kernel=RBF(0.2) + WhiteKernel(0.008), optimizer=None).fit(X, yx)
+    gY = GaussianProcessRegressor(kernel=RBF(0.25) + WhiteKernel(0.008), optimizer=None).fit(X, yy)
+    lm = LearningModule(device="cuda:0")
+    lm.set_models(gX, gY, 1.5, 4.0, 0.2, -0.1)
+    ang = torch.rand(n, device="cuda:0", dtype=torch.float64) * 6.28 - 3.14
+    vd = 6.0 * torch.stack([torch.cos(ang), torch.sin(ang)], 1)
+    import ctypes as C
+    from mr_rl_b200 import _lib as L
+    alpha = torch.empty(n, dtype=torch.float64, device="cuda:0"); nfev = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    def run():
+        return L.load().mr_gp_correct_heading(C.byref(lm._dx._c), C.byref(lm._dy._c), vd.data_ptr(), n, 1.5, 4.0, 0.2, -0.1,
+                                              alpha.data_ptr(), nfev.data_ptr(), None)
+    run(); torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    evals = float(nfev.sum())
+    print(f"heading correction (bounded minimiser, 2 GPs in the loop): {ms:8.2f} ms for {n} velocities "
+          f"({n/ms/1e3:.2f} M/s, mean nfev {evals/n:.1f}, {evals*n_train*2/ms/1e6:.1f} G kernel evals/s)")
+    # CPU reference cost for scale: sklearn + scipy on one velocity
+    import time
+    from scipy.optimize import minimize_scalar
+    from oracle import mr_oracle as mo
+    gx, gy = mo.GPModel.from_sklearn(gX), mo.GPModel.from_sklearn(gY)
+    t0 = time.perf_counter()
+    for i in range(5):
+        v = vd[i].cpu().numpy()
+        minimize_scalar(lambda a: float(np.ravel(mo.lm_objective(a, 1.5, 4.0, v, gx, gy, 0.2, -0.1))[0]), method="Bounded", bounds=[-np.pi, np.pi])
+    print(f"  host (numpy port of the objective + scipy minimiser): {(time.perf_counter()-t0)/5*1e3:.2f} ms per velocity")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "gp"):
         gp_bench()
     if what in ("all", "actor"):
         actor_bench()
+    if what in ("all", "heading"):
+        heading_bench()
