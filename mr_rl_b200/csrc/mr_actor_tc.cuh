@@ -24,21 +24,19 @@ namespace mr {
 constexpr int kTcRows = 128;                   // envs per CTA = UMMA M
 constexpr int kTcLBO = 128;                    // bytes between the two 16-byte K chunks of one MMA
 constexpr int kTcSBO = 16 * 128;               // bytes between 8-row groups (16 K-chunks of 128 B each)
-constexpr int kTcParams = kActorParams - kActorHidden * kActorHidden;   // everything except W2
 
 struct alignas(128) ActorTcSmem {
     float a_hi[kTcRows * kActorHidden];        // 32 KB each
     float a_lo[kTcRows * kActorHidden];
     float b_hi[kActorHidden * kActorHidden];   // 16 KB each, B[n][k] = W2[k][n]
     float b_lo[kActorHidden * kActorHidden];
-    float w[kTcParams];                        // packed parameters without W2
-    float bn[4][kActorHidden];                 // folded BN: y = s * x + t  (s1, t1, s2, t2)
+    float w1f[3][kActorHidden];                // layer 1 with BN folded in, rows for obs x, y, d (the goal inputs
+    float b1f[kActorHidden];                   //   obs[2], obs[3] are identically 0 in this env: MR_env.py:57)
+    float4 ep[kActorHidden];                   // epilogue per hidden unit: (s2, t2, w3[j][0], w3[j][1])
+    float b3[2];
     alignas(8) uint64_t mbar;
     uint32_t tmem_base;
 };
-
-// index into ActorTcSmem::w of packed-parameter offset `off` (offsets beyond W2 shift down)
-__device__ __forceinline__ constexpr int tcw(int off) { return off < kOffW2 ? off : off - kActorHidden * kActorHidden; }
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,8 +71,6 @@ __device__ __forceinline__ void tc_split(float v, float& hi, float& lo) {
 // once per CTA: parameters, W2 hi/lo in UMMA layout, TMEM allocation, mbarrier
 __device__ __forceinline__ void actor_tc_setup(ActorTcSmem& sm, const float* __restrict__ actor) {
     const int tid = threadIdx.x;
-    for (int k = tid; k < kActorParams; k += kTcRows)
-        if (k < kOffW2 || k >= kOffB2) sm.w[tcw(k)] = actor[k];
     for (int idx = tid; idx < kActorHidden * kActorHidden; idx += kTcRows) {
         const int k = idx / kActorHidden, nn = idx % kActorHidden;      // W2[k][nn] (input-major)
         float hi, lo;
@@ -84,13 +80,19 @@ __device__ __forceinline__ void actor_tc_setup(ActorTcSmem& sm, const float* __r
         sm.b_lo[off] = lo;
     }
     if (tid < kActorHidden) {
-        // tflearn inference BN  gamma * (x - mean) / sqrt(var + eps) + beta  folded to s * x + t; the layer-2
-        // bias joins t2 because the tensor core produces the bias-free product
+        // tflearn inference BN  gamma * (x - mean) / sqrt(var + eps) + beta  folded to s * x + t.  Layer 1:
+        // s1 multiplies the weights and bias (h = relu(b1f + sum_i obs_i * w1f_i)); layer 2: the bias joins t2
+        // because the tensor core produces the bias-free product.
         const float s1 = actor[kOffG1 + tid] / sqrtf(actor[kOffV1 + tid] + kBnEps);
         const float s2 = actor[kOffG2 + tid] / sqrtf(actor[kOffV2 + tid] + kBnEps);
-        sm.bn[0][tid] = s1; sm.bn[1][tid] = actor[kOffBe1 + tid] - s1 * actor[kOffM1 + tid];
-        sm.bn[2][tid] = s2; sm.bn[3][tid] = actor[kOffBe2 + tid] + s2 * (actor[kOffB2 + tid] - actor[kOffM2 + tid]);
+        sm.w1f[0][tid] = s1 * actor[kOffW1 + 0 * kActorHidden + tid];
+        sm.w1f[1][tid] = s1 * actor[kOffW1 + 1 * kActorHidden + tid];
+        sm.w1f[2][tid] = s1 * actor[kOffW1 + 4 * kActorHidden + tid];
+        sm.b1f[tid] = s1 * (actor[kOffB1 + tid] - actor[kOffM1 + tid]) + actor[kOffBe1 + tid];
+        sm.ep[tid] = make_float4(s2, actor[kOffBe2 + tid] + s2 * (actor[kOffB2 + tid] - actor[kOffM2 + tid]),
+                                 actor[kOffW3 + tid * kActorOut], actor[kOffW3 + tid * kActorOut + 1]);
     }
+    if (tid < 2) sm.b3[tid] = actor[kOffB3 + tid];
     if (tid < 32) {                                                    // one warp owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sm.tmem_base)), "r"(64));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -116,29 +118,24 @@ __device__ __forceinline__ void actor_tc_teardown(ActorTcSmem& sm) {
 __device__ __forceinline__ void actor_tc_forward(ActorTcSmem& sm, const float obs[5], float hi0, float hi1, int step,
                                                  float act[2]) {
     const int tid = threadIdx.x;
-    const float* w = sm.w;
-    // ---- layer 1 + BN + ReLU, 4 hidden units (= one 16-byte K chunk) at a time -----------------
+    // ---- layer 1 (+ folded BN) + ReLU, 4 hidden units (= one 16-byte K chunk) at a time -------------
     char* a_hi = reinterpret_cast<char*>(sm.a_hi);
     char* a_lo = reinterpret_cast<char*>(sm.a_lo);
     const int row_off = (tid >> 3) * kTcSBO + (tid & 7) * 16;
+    const float ox = obs[0], oy = obs[1], od = obs[4];        // obs[2] = obs[3] = 0: the goal is the origin
 #pragma unroll 4
     for (int c = 0; c < kActorHidden / 4; ++c) {
-        float4 acc = *reinterpret_cast<const float4*>(w + kOffB1 + 4 * c);
-#pragma unroll
-        for (int i = 0; i < kActorIn; ++i) {
-            const float4 ww = *reinterpret_cast<const float4*>(w + kOffW1 + i * kActorHidden + 4 * c);
-            acc.x = fmaf(obs[i], ww.x, acc.x); acc.y = fmaf(obs[i], ww.y, acc.y);
-            acc.z = fmaf(obs[i], ww.z, acc.z); acc.w = fmaf(obs[i], ww.w, acc.w);
-        }
-        float h[4] = {acc.x, acc.y, acc.z, acc.w};
+        float4 acc = *reinterpret_cast<const float4*>(&sm.b1f[4 * c]);
+        const float4 wx = *reinterpret_cast<const float4*>(&sm.w1f[0][4 * c]);
+        const float4 wy = *reinterpret_cast<const float4*>(&sm.w1f[1][4 * c]);
+        const float4 wd = *reinterpret_cast<const float4*>(&sm.w1f[2][4 * c]);
+        acc.x = fmaf(od, wd.x, fmaf(oy, wy.x, fmaf(ox, wx.x, acc.x)));
+        acc.y = fmaf(od, wd.y, fmaf(oy, wy.y, fmaf(ox, wx.y, acc.y)));
+        acc.z = fmaf(od, wd.z, fmaf(oy, wy.z, fmaf(ox, wx.z, acc.z)));
+        acc.w = fmaf(od, wd.w, fmaf(oy, wy.w, fmaf(ox, wx.w, acc.w)));
         float4 vh, vl;
-        float* ph = &vh.x; float* pl = &vl.x;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float y = fmaf(sm.bn[0][4 * c + j], h[j], sm.bn[1][4 * c + j]);
-            y = y > 0.f ? y : 0.f;
-            tc_split(y, ph[j], pl[j]);
-        }
+        tc_split(fmaxf(acc.x, 0.f), vh.x, vl.x); tc_split(fmaxf(acc.y, 0.f), vh.y, vl.y);
+        tc_split(fmaxf(acc.z, 0.f), vh.z, vl.z); tc_split(fmaxf(acc.w, 0.f), vh.w, vl.w);
         *reinterpret_cast<float4*>(a_hi + row_off + c * kTcLBO) = vh;
         *reinterpret_cast<float4*>(a_lo + row_off + c * kTcLBO) = vl;
     }
@@ -191,13 +188,12 @@ __device__ __forceinline__ void actor_tc_forward(ActorTcSmem& sm, const float ob
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 
     // ---- BN + ReLU, output layer, tanh, action bound ------------------------------------------------
-    float o0 = w[tcw(kOffB3)], o1 = w[tcw(kOffB3 + 1)];
+    float o0 = sm.b3[0], o1 = sm.b3[1];
 #pragma unroll
     for (int j = 0; j < kActorHidden; ++j) {
-        float y = fmaf(sm.bn[2][j], __uint_as_float(r[j]), sm.bn[3][j]);
-        y = y > 0.f ? y : 0.f;
-        const float2 ww = *reinterpret_cast<const float2*>(w + tcw(kOffW3) + j * kActorOut);
-        o0 = fmaf(y, ww.x, o0); o1 = fmaf(y, ww.y, o1);
+        const float4 c = sm.ep[j];                                         // one broadcast 16-byte read per hidden unit
+        const float y = fmaxf(fmaf(c.x, __uint_as_float(r[j]), c.y), 0.f);
+        o0 = fmaf(y, c.z, o0); o1 = fmaf(y, c.w, o1);
     }
     act[0] = tanhf(o0) * hi0;
     act[1] = tanhf(o1) * hi1;
