@@ -13,6 +13,15 @@ namespace mr {
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
 
+// Per-device launch configuration cache (one process may drive several GPUs): kernel attributes are
+// per device, so "done once" flags are indexed by the current device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 // ---- device-side views ---------------------------------------------------------------------
 template <class T>
 struct StateView {

@@ -163,11 +163,12 @@ static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const O
             if (simt) {
                 env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_ACTOR><<<blocks, threads, kActorParams * sizeof(float), s>>>(sv, rv, ov, nv, tv, p, n);
             } else {
-                static bool attr = false;
-                if (!attr) {
+                static bool attr[kMaxDevices] = {};
+                const int dev = current_device();
+                if (!attr[dev]) {
                     cudaFuncSetAttribute(env_rollout_kernel<T, MODE, MISM, kSrcActorTc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(ActorTcSmem));
-                    attr = true;
+                    attr[dev] = true;
                 }
                 env_rollout_kernel<T, MODE, MISM, kSrcActorTc><<<blocks, kTcRows, sizeof(ActorTcSmem), s>>>(sv, rv, ov, nv, tv, p, n);
             }

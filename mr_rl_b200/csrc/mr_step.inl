@@ -168,15 +168,13 @@ static OutView<T> offset_out(OutView<T> v, int64_t o) {
     return v;
 }
 
-static int sm_count() {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        if (cached <= 0) cached = 148;
+static int sm_count(int dev) {
+    static int cached[kMaxDevices] = {};
+    if (!cached[dev]) {
+        cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (cached[dev] <= 0) cached[dev] = 148;
     }
-    return cached;
+    return cached[dev];
 }
 
 // MR_STEP_PATH=tma|vec|scalar overrides the kernel choice (tuning / A-B measurements)
@@ -202,15 +200,16 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
             // Blackwell path: persistent CTAs, TMA bulk copies through shared memory
             const int64_t n_tiles = n / kTile;
             const size_t smem = sizeof(StepSmem<T>);
-            static int ctas_per_sm = 0;                    // per template instantiation
-            if (!ctas_per_sm) {
+            static int ctas_per_sm[kMaxDevices] = {};      // per template instantiation and device
+            const int dev = current_device();
+            if (!ctas_per_sm[dev]) {
                 cudaFuncSetAttribute(env_step_tma_kernel<T, MODE, MISM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 int occ = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_step_tma_kernel<T, MODE, MISM>, kTile, smem);
-                ctas_per_sm = occ > 0 ? occ : 1;
+                ctas_per_sm[dev] = occ > 0 ? occ : 1;
             }
             // persistent grid: exactly the CTAs that are co-resident, so there is never a second wave
-            const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
+            const int64_t max_ctas = (int64_t)sm_count(dev) * ctas_per_sm[dev];
             const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTile); cfg.dynamicSmemBytes = smem; cfg.stream = s;

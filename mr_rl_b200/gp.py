@@ -21,6 +21,8 @@ class DeviceGP:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.MRLibraryError("DeviceGP needs a CUDA device: there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         X = np.asarray(X_train, dtype=np.float64)
         X = X.reshape(len(X), -1)
         n, d = X.shape
@@ -59,6 +61,9 @@ class DeviceGP:
 
     def predict(self, q, return_std=False):
         """q: [n_q] or [n_q, dim] float64 (device tensor or array).  Returns mean[, std] device tensors."""
+        if self.device.index is not None and torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):          # kernels launch on the runtime's current device
+                return self.predict(q, return_std)
         qt = torch.as_tensor(q) if not torch.is_tensor(q) else q
         qt = qt.to(device=self.device, dtype=torch.float64).reshape(-1, self.dim).contiguous()
         n_q = qt.shape[0]

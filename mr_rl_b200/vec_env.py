@@ -110,6 +110,7 @@ class VecMREnv:
         self._pinned = {}
         self.kernel_launches = 0
         # per-step call overhead: argument references and result views are built once
+        self._dev_index = self.device.index
         self._call_step = self.lib.mr_env_step
         self._b_state, self._b_params, self._b_tt = C.byref(self._c_state), C.byref(self.params), C.byref(self._c_tt)
         self._b_out, self._b_out_lean = C.byref(self._c_out), C.byref(self._c_out_lean)
@@ -188,6 +189,9 @@ class VecMREnv:
     def reset(self, init=None, noise_var=1, a0=1, is_mismatched=False, mask=None, reset_cursor=True):
         """Reset all envs (or those with ``mask[i] != 0``).  ``init``: None (sample init_space on
         device), a (2,) position for every env, or an [N, 2] tensor.  Returns obs [N, 5]."""
+        if torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self.device):
+                return self.reset(init, noise_var, a0, is_mismatched, mask, reset_cursor)
         n = self.num_envs
         p = self.params
         if mask is not None and (float(noise_var) != p.noise_var or float(a0) != p.a0
@@ -231,6 +235,9 @@ class VecMREnv:
         if a.numel() != 2 * n:
             raise ValueError(f"actions must be [{n}, 2]")
         nz = self._noise_for(self.params.noise_var)
+        if torch.cuda.current_device() != self._dev_index:      # kernels launch on the runtime's current device
+            with torch.cuda.device(self.device):
+                return self.step(a)
         rc = self._call_step(self._b_state, n, self._dt, self._b_params, C.byref(nz), self._b_tt, a.data_ptr(),
                              self._b_out if self.want_state_prime else self._b_out_lean,
                              torch.cuda.current_stream(self.device).cuda_stream)
@@ -352,6 +359,9 @@ class VecMREnv:
                   a packed float32 actor tensor (see actor.pack_actor) -> DDPG actor in the loop.
         Returns dict(obs, rew, done[, xy [K,2,N], state_prime [K,2,N], done_traj [K,N]]).
         """
+        if torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self.device):
+                return self.rollout(actions, k_steps, policy, record, record_state_prime, record_done, accumulate_stats)
         n = self.num_envs
         io = L.RolloutIO()
         keep = []
