@@ -160,7 +160,7 @@ __device__ __forceinline__ void actor_tc_forward(ActorTcSmem& sm, const float ob
     {   // wait for the MMAs of this call (bounded spin: a descriptor mistake must trap, not hang the GPU)
         const uint32_t bar = tc_smem_u32(&sm.mbar), parity = (uint32_t)step & 1u;
         uint32_t ok = 0;
-        for (int spin = 0; spin < (1 << 24) && !ok; ++spin)
+        for (int spin = 0; spin < (1 << 28) && !ok; ++spin)
             asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (!ok) __trap();
