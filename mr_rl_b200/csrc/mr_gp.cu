@@ -16,6 +16,7 @@
 
 #include "mr_actor.cuh"
 #include "mr_common.cuh"
+#include "mr_step_tma.cuh"   // mbarrier / cp.async.bulk helpers
 
 namespace mr {
 
@@ -44,6 +45,123 @@ gp_kq_mean_kernel(const double* __restrict__ q, int64_t n_q, const double* __res
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) mean[row] = acc;
+}
+
+
+
+// exp(x) for x <= 0 with a 64-entry table of 2^(j/64) in shared memory and a degree-5 polynomial:
+// x = (64 m + j) ln2/64 + r, |r| <= ln2/128, exp(x) = 2^m * T[j] * (1 + r + ... + r^5/120) (truncation
+// 3.5e-17).  ~14 fp64 instructions instead of the ~25 of the library exp; ~2 ulp.  Results below
+// 2^-1021 flush to 0 (such kernel values cannot influence a sum whose other terms are O(1e-300) larger).
+__device__ __forceinline__ void exp_table_init(double* T) {
+    if (threadIdx.x < 64) T[threadIdx.x] = exp2((double)threadIdx.x / 64.0);
+}
+__device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict__ T) {
+    const double t = x * 92.33248261689366;                      // 64 / ln 2
+    const int n = __double2int_rn(t);
+    const double nd = (double)n;
+    double r = fma(-nd, 0x1.62e42fefa0000p-7, x);                // ln2/64, high 36 bits (n * hi is exact)
+    r = fma(-nd, 0x1.cf78000000000p-46, r);                      // ... and the remainder
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int m = n >> 6;                                        // floor division: j = n & 63 in [0, 63]
+    const double v = T[n & 63] * p;                              // in [1, 2.04)
+    if (m < -1021) return 0.0;
+    return __longlong_as_double(__double_as_longlong(v) + ((long long)m << 52));
+}
+
+// ---- kernel 1 (staged): training points and alpha live in shared memory ---------------------
+// Persistent CTAs: the (pre-scaled) training inputs and alpha_ are fetched ONCE per CTA with two TMA
+// bulk copies (cp.async.bulk + mbarrier), then every warp walks over query rows, QPW rows at a time,
+// lanes striding the training points (conflict-free LDS.64), and reduces with xor shuffles.
+template <int DIM, bool WRITE_KQ, int QPW>
+__global__ void __launch_bounds__(256)
+gp_kq_mean_smem_kernel(const double* __restrict__ q, int64_t n_q, const double* __restrict__ xtr,
+                       const double* __restrict__ alpha, int n_pad, double ls, double* __restrict__ kq,
+                       double* __restrict__ mean) {
+    extern __shared__ __align__(128) unsigned char gp_smem[];
+    double* s_x = reinterpret_cast<double*>(gp_smem);                 // [n_pad][DIM]
+    double* s_a = s_x + (size_t)n_pad * DIM;                          // [n_pad]
+    double* s_tab = s_a + n_pad;                                      // [64] 2^(j/64)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + 64);
+    exp_table_init(s_tab);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bx = (uint32_t)n_pad * DIM * 8u, ba = (uint32_t)n_pad * 8u;
+        mbar_expect_tx(bar, bx + ba);
+        bulk_load(s_x, xtr, bx, bar);
+        bulk_load(s_a, alpha, ba, bar);
+    }
+    mbar_wait(bar, 0);
+
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
+    const int warp_global = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    for (int64_t row0 = (int64_t)warp_global * QPW; row0 < n_q; row0 += (int64_t)warps_total * QPW) {
+        double q0[QPW], q1[QPW], acc[QPW];
+#pragma unroll
+        for (int r = 0; r < QPW; ++r) {
+            const int64_t row = row0 + r < n_q ? row0 + r : n_q - 1;  // clamp: tail rows recompute the last row
+            q0[r] = q[row * DIM] / ls;                                // sklearn: cdist(X / l, Y / l, "sqeuclidean")
+            q1[r] = DIM == 2 ? q[row * DIM + 1] / ls : 0.0;
+            acc[r] = 0.0;
+        }
+        for (int j = lane; j < n_pad; j += 32) {
+            const double a = s_a[j];
+            double x0, x1 = 0.0;
+            if (DIM == 1) x0 = s_x[j]; else { x0 = s_x[2 * j]; x1 = s_x[2 * j + 1]; }
+#pragma unroll
+            for (int r = 0; r < QPW; ++r) {
+                const double d0 = q0[r] - x0;
+                double d2 = d0 * d0;
+                if (DIM == 2) { const double d1 = q1[r] - x1; d2 = fma(d1, d1, d2); }
+                const double k = exp_neg_tab(-0.5 * d2, s_tab);       // padding columns meet alpha = 0 / zero linv columns
+                if (WRITE_KQ && row0 + r < n_q) kq[(row0 + r) * (int64_t)n_pad + j] = k;
+                acc[r] = fma(k, a, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < QPW; ++r) {
+            double v = acc[r];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0 && row0 + r < n_q) mean[row0 + r] = v;
+        }
+    }
+}
+
+// launch helper: staged kernel when the model fits in shared memory, else the global-memory kernel
+template <int DIM, bool WRITE_KQ>
+static void launch_kq_mean(const double* q, int64_t n_q, const mr_gp_model* gp, double* kq, double* mean, cudaStream_t s) {
+    const size_t smem = (size_t)gp->n_pad * (DIM + 1) * 8 + 64 * 8 + 16;
+    const bool aligned = (((uintptr_t)gp->x_train_scaled | (uintptr_t)gp->alpha) & 15u) == 0;   // TMA bulk copies
+    if (smem <= 200 * 1024 && aligned) {
+        constexpr int QPW = 4;
+        static int sms[kMaxDevices] = {};
+        const int dev = current_device();
+        if (!sms[dev]) { cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev); if (sms[dev] <= 0) sms[dev] = 148; }
+        cudaFuncSetAttribute(gp_kq_mean_smem_kernel<DIM, WRITE_KQ, QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        int64_t want = (n_q + 8 * QPW - 1) / (8 * QPW);             // CTAs needed if every warp took one pass
+        int64_t grid = (int64_t)sms[dev] * per_sm;
+        if (grid > want) grid = want;
+        if (grid < 1) grid = 1;
+        gp_kq_mean_smem_kernel<DIM, WRITE_KQ, QPW><<<(unsigned)grid, 256, smem, s>>>(q, n_q, gp->x_train_scaled, gp->alpha,
+                                                                                     gp->n_pad, gp->length_scale, kq, mean);
+    } else {
+        const unsigned blocks = (unsigned)((n_q * 32 + 255) / 256);
+        gp_kq_mean_kernel<DIM, WRITE_KQ><<<blocks, 256, 0, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train,
+                                                                gp->length_scale, kq, mean);
+    }
 }
 
 // ---- kernel 2: triangular contraction + square-sum ---------------------------------------
@@ -160,12 +278,12 @@ __device__ __forceinline__ double gp_objective_warp(double alpha, double vdx, do
                                                     const double* __restrict__ xsx, const double* __restrict__ ax,
                                                     double lsx, const double* __restrict__ xsy,
                                                     const double* __restrict__ ay, double lsy, int n_pad, int n_train,
-                                                    int lane) {
+                                                    int lane, const double* __restrict__ tab) {
     const double qx = alpha / lsx, qy = alpha / lsy;
     double sx = 0.0, sy = 0.0;
     for (int j = lane; j < n_pad; j += 32) {
         const double d0 = qx - xsx[j], d1 = qy - xsy[j];
-        double kx = exp(-0.5 * (d0 * d0)), ky = exp(-0.5 * (d1 * d1));
+        double kx = exp_neg_tab(-0.5 * (d0 * d0), tab), ky = exp_neg_tab(-0.5 * (d1 * d1), tab);
         if (j >= n_train) { kx = 0.0; ky = 0.0; }
         sx = fma(kx, ax[j], sx);
         sy = fma(ky, ay[j], sy);
@@ -186,11 +304,14 @@ gp_correct_heading_kernel(const double* __restrict__ vd, int64_t n, HeadingProbl
                           const double* __restrict__ ax, double lsx, const double* __restrict__ xsy,
                           const double* __restrict__ ay, double lsy, int n_pad, int n_train, double lo, double hi,
                           double xatol, int maxfun, double* __restrict__ alpha_out, int32_t* __restrict__ nfev_out) {
+    __shared__ double s_tab[64];
+    exp_table_init(s_tab);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
     const double vdx = vd[2 * row], vdy = vd[2 * row + 1];
-    auto f = [&](double x) { return gp_objective_warp(x, vdx, vdy, hp, xsx, ax, lsx, xsy, ay, lsy, n_pad, n_train, lane); };
+    auto f = [&](double x) { return gp_objective_warp(x, vdx, vdy, hp, xsx, ax, lsx, xsy, ay, lsy, n_pad, n_train, lane, s_tab); };
 
     const double sqrt_eps = sqrt(2.2e-16);
     const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
@@ -307,12 +428,9 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
         return fail(MR_ERR_ARG, "mr_gp_predict: n_pad must be a multiple of %d and >= n_train", MR_GP_PAD);
     if (!(gp->length_scale > 0)) return fail(MR_ERR_ARG, "mr_gp_predict: bad length_scale");
     cudaStream_t s = (cudaStream_t)stream;
-    const double inv_ls = gp->length_scale;   // kernels divide by the length scale like sklearn
-    const int threads = 256;
     if (!std) {
-        const unsigned blocks = (unsigned)((n_q * 32 + threads - 1) / threads);
-        if (gp->dim == 1) gp_kq_mean_kernel<1, false><<<blocks, threads, 0, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, nullptr, mean);
-        else gp_kq_mean_kernel<2, false><<<blocks, threads, 0, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, nullptr, mean);
+        if (gp->dim == 1) launch_kq_mean<1, false>(q, n_q, gp, nullptr, mean, s);
+        else launch_kq_mean<2, false>(q, n_q, gp, nullptr, mean, s);
         return check_launch("mr_gp_predict(mean)");
     }
     if (!gp->linv) return fail(MR_ERR_ARG, "mr_gp_predict: std requested but model has no linv");
@@ -329,10 +447,9 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
     for (int64_t q0 = 0; q0 < n_q; q0 += kGpChunk) {
         const int64_t nq = (n_q - q0) < kGpChunk ? (n_q - q0) : kGpChunk;
         const int64_t nq_pad = round_up(nq, GP_BM);
-        const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
         if (nq_pad > nq) cudaMemsetAsync(kq + nq * gp->n_pad, 0, (size_t)(nq_pad - nq) * gp->n_pad * 8, s);
-        if (gp->dim == 1) gp_kq_mean_kernel<1, true><<<blocks, threads, 0, s>>>(q + q0, nq, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, kq, mean + q0);
-        else gp_kq_mean_kernel<2, true><<<blocks, threads, 0, s>>>(q + q0 * 2, nq, gp->x_train_scaled, gp->alpha, gp->n_pad, gp->n_train, inv_ls, kq, mean + q0);
+        if (gp->dim == 1) launch_kq_mean<1, true>(q + q0, nq, gp, kq, mean + q0, s);
+        else launch_kq_mean<2, true>(q + q0 * 2, nq, gp, kq, mean + q0, s);
         cudaMemsetAsync(ssq, 0, (size_t)nq_pad * 8, s);
         dim3 grid((unsigned)(nq_pad / GP_BM), (unsigned)(gp->n_pad / GP_BN));
         gp_var_kernel<<<grid, 256, smem, s>>>(kq, gp->linv, gp->n_pad, nq_pad, ssq);
