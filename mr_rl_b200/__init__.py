@@ -16,7 +16,7 @@ from .actor import actor_forward, init_actor, pack_actor  # noqa: F401
 from .gp import DeviceGP  # noqa: F401
 from .learning_module import LearningModule  # noqa: F401
 from .mr_env import MR_Env, Simulator  # noqa: F401
-from .recording import experiment_dict, load_experiment, save_experiment  # noqa: F401
+from .recording import MRExperiment, experiment_dict, load_experiment, save_experiment  # noqa: F401
 from .spaces import Box  # noqa: F401
 from .utils import run_sim  # noqa: F401
 from .vec_env import VecMREnv, shard_range  # noqa: F401

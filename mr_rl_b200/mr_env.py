@@ -117,7 +117,10 @@ class MR_Env:
         self.last_pos = [obs[0], obs[1]]
         self.last_action = np.array([f_t, alpha_t])
         if self.MR_data is not None:
-            self.MR_data.new_transition(sim.last_state, obs, self.last_action, rew)
+            self.MR_data.new_transition(sim.last_state, obs, self.last_action, rew)     # MR_env.py:94-95
+            if done and (not self.observation_space.contains(obs) or self.counter > self.max_timesteps) \
+                    and self.MR_data.iterations > 0:
+                self.MR_data.save_experiment(self.name_experiment)                      # MR_env.py:145-147
         return obs, rew, done, dict()
 
     def convert_state(self, state, goal_loc):
@@ -186,7 +189,9 @@ class MR_Env:
 
     def set_save_experice(self, name="experiment_ssn_ddpg_10iter"):
         assert type(name) == type(""), "name must be a string"
-        raise NotImplementedError("MRExperiment logging (MR_data.py) is out of scope of the hot path")
+        from .recording import MRExperiment
+        self.MR_data = MRExperiment()
+        self.name_experiment = name
 
     def set_test_performace(self):
         self.test_performance = True

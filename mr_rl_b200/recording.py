@@ -56,3 +56,46 @@ def save_experiment(exp, path):
 def load_experiment(path):
     with open(path, "rb") as f:
         return pickle.load(f)
+
+
+class MRExperiment:
+    """Host-side transition logger with the reference's interface and pickle layout (MR_data.py:9-85):
+    ``new_iter`` at reset, ``new_transition`` per step, ``save_experiment`` / ``load_from_experiment``.
+    The plotting helpers of the reference class are not reproduced."""
+
+    def __init__(self, info=None):
+        self.iterations = -1
+        self.states, self.observations, self.actions, self.rewards, self.steps = {}, {}, {}, {}, {}
+        self.info = info
+        self.viewer = None
+        self.scream = None
+        self.obs_states_str = {}
+        self.time_step = 10
+
+    def new_iter(self, s0, obs0, a0, r0):
+        self.iterations += 1
+        it = self.iterations
+        self.steps[it] = 0
+        self.states[it], self.observations[it], self.actions[it], self.rewards[it] = s0, obs0, a0, r0
+
+    def new_transition(self, s, obs, a, r):
+        it = self.iterations
+        self.steps[it] += 1
+        self.states[it] = np.vstack([self.states[it], s])
+        self.observations[it] = np.vstack([self.observations[it], obs])
+        self.actions[it] = np.vstack([self.actions[it], a])
+        self.rewards[it] = np.vstack([self.rewards[it], r])
+
+    def save_experiment(self, descr="_experiment", directory="_experiments"):
+        import datetime
+        import os
+        import time as t
+        st = datetime.datetime.fromtimestamp(t.time()).strftime("%Y-%m-%d-%H")
+        os.makedirs(directory, exist_ok=True)
+        path = os.path.join(directory, st + descr)
+        save_experiment(self.__dict__, path)
+        return path
+
+    def load_from_experiment(self, name, directory="_experiments"):
+        import os
+        self.__dict__.update(load_experiment(os.path.join(directory, name)))

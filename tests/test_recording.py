@@ -81,3 +81,32 @@ def test_recorded_device_rollout_in_reference_format(tmp_path):
     assert np.allclose(exp["states"][3][-1], res["xy"][50, :, 3].cpu().numpy())
     save_experiment(exp, tmp_path / "e")
     assert load_experiment(tmp_path / "e")["observations"][4].shape == (52, 5)
+
+
+def test_logger_class_matches_array_builder():
+    """MRExperiment (host logger with the reference's method names) fed step by step == experiment_dict."""
+    from mr_rl_b200.recording import MRExperiment
+    acts, z, r = _oracle_run(12)
+    lg = MRExperiment()
+    s0 = np.array([110.0, 105.0])
+    lg.new_iter(s0, np.array([110.0, 105.0, 0, 0, np.hypot(110.0, 105.0)]), np.zeros(2), np.array([0]))
+    for k in range(12):
+        lg.new_transition(r["pos"][k], r["obs"][k], acts[k], 10)
+    xy = r["pos"].T[None].transpose(2, 1, 0)
+    ref = experiment_dict(s0, acts, xy)
+    for key in ("states", "observations", "actions", "rewards"):
+        assert np.allclose(np.asarray(lg.__dict__[key][0], dtype=float), ref[key][0])
+    assert lg.steps[0] == 12 and set(lg.__dict__) == set(ref)
+
+
+@pytest.mark.gpu
+def test_mr_env_facade_logging_hook(tmp_path, monkeypatch):
+    from mr_rl_b200 import MR_Env
+    monkeypatch.chdir(tmp_path)
+    env = MR_Env(device="cuda:0", noise="philox", seed=1)
+    env.set_save_experice("unit")
+    env.reset(init=np.array([110.0, 105.0]))
+    for _ in range(5):
+        env.step(np.array([10.0, 0.5]))
+    d = env.MR_data
+    assert d.iterations == 0 and d.steps[0] == 5 and d.observations[0].shape == (6, 5) and d.actions[0].shape == (6, 2)
