@@ -2,7 +2,6 @@
 own logger when /root/reference is available (build container), structurally otherwise."""
 import contextlib
 import io
-import os
 
 import numpy as np
 import pytest

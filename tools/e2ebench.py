@@ -1,6 +1,6 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from mr_rl_b200 import VecMREnv
 n = 1 << 20
 for maxc in (1, 2, 4, 8):
