@@ -18,6 +18,8 @@
  *   mr_gp_correct_heading <- LearningModule.predict's minimize_scalar(objective, 'Bounded')
  *                       (Learning_module.py:215, utils.py:194-196)
  *   mr_actor_forward <- ActorNetwork.predict    (RL/MR_ddpg.py:124-149)
+ *   mr_gp_fit        <- GaussianProcessRegressor.fit at given hyper-parameters: K, cholesky, alpha_, L^-1,
+ *                       log marginal likelihood  (Learning_module.py:122-123; the optimiser stays on the host)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in _host; the library never
@@ -212,6 +214,18 @@ int64_t mr_gp_workspace_bytes(const mr_gp_model* gp, int64_t n_q, int32_t want_s
  * posterior at the minimiser (Learning_module.py:221-222) is a following mr_gp_predict call. */
 int mr_gp_correct_heading(const mr_gp_model* gpx, const mr_gp_model* gpy, const double* vd, int64_t n, double a0,
                           double freq, double drift_x, double drift_y, double* alpha_out, int32_t* nfev_out, void* stream);
+
+/* GaussianProcessRegressor.fit for kernel RBF(length_scale) + WhiteKernel(noise_level) at FIXED hyper-parameters
+ * (Learning_module.py:30-33,122-123): K = rbf(X/l) + (noise_level + jitter) I  (jitter = sklearn's alpha, 1e-10),
+ * L = chol(K), alpha = K^-1 y, linv = L^-1, lml = -0.5 y.alpha - sum log L_ii - n/2 log 2pi.
+ * x_train [n_train][dim], y [n_train].  Outputs are laid out as mr_gp_model wants them: x_scaled_out
+ * [n_pad][dim], alpha_out [n_pad], linv_out [n_pad][n_pad] (padding zero); lml_out (1 double) and info_out
+ * (1 int32: 0, or 1 + the first non-positive pivot like LAPACK potrf) may be NULL.  n_pad must be a multiple of
+ * MR_GP_PAD; workspace must hold mr_gp_fit_workspace_bytes(n_pad) bytes, 16-byte aligned. */
+int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n_pad, int32_t dim, double length_scale,
+              double noise_level, double jitter, double* x_scaled_out, double* alpha_out, double* linv_out,
+              double* lml_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mr_gp_fit_workspace_bytes(int32_t n_pad);
 
 /* ---- DDPG actor forward (RL/MR_ddpg.py:124-149) --------------------------------------
  * Packed float32 parameters (input-major matrices W[in][out]):

@@ -67,7 +67,7 @@ GP_PAD = 128
 
 
 EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time_table_host", "mr_env_reset",
-           "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_actor_param_count",
+           "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_gp_fit", "mr_gp_fit_workspace_bytes", "mr_actor_param_count",
            "mr_actor_forward")
 
 _lib = None
@@ -105,6 +105,11 @@ def load():
     lib.mr_gp_correct_heading.argtypes = [P(GPModel), P(GPModel), C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                           C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mr_gp_correct_heading.restype = C.c_int
+    lib.mr_gp_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mr_gp_fit.restype = C.c_int
+    lib.mr_gp_fit_workspace_bytes.argtypes = [C.c_int32]
+    lib.mr_gp_fit_workspace_bytes.restype = C.c_int64
     lib.mr_gp_workspace_bytes.argtypes = [P(GPModel), C.c_int64, C.c_int32]
     lib.mr_gp_workspace_bytes.restype = C.c_int64
     lib.mr_actor_param_count.restype = C.c_int32

@@ -16,6 +16,7 @@
 
 #include "mr_actor.cuh"
 #include "mr_common.cuh"
+#include "mr_dmma.cuh"
 #include "mr_step_tma.cuh"   // mbarrier / cp.async.bulk helpers
 
 namespace mr {
@@ -164,86 +165,25 @@ static void launch_kq_mean(const double* q, int64_t n_q, const mr_gp_model* gp, 
     }
 }
 
-// ---- kernel 2: triangular contraction + square-sum ---------------------------------------
-constexpr int GP_BM = 128, GP_BN = 128, GP_BK = 16, GP_LD = GP_BK + 4;   // +4 doubles: conflict-free fragments
-constexpr int GP_STAGE = (GP_BM + GP_BN) * GP_LD;                         // doubles per pipeline stage
-constexpr int GP_STAGES = 3;
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
+// ---- kernel 2: triangular contraction + square-sum (mainloop: mr_dmma.cuh) --------------------
 __global__ void __launch_bounds__(256)
 gp_var_kernel(const double* __restrict__ kq, const double* __restrict__ linv, int n_pad, int64_t n_q_pad,
               double* __restrict__ ssq) {
     extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int warp_m = warp >> 2, warp_n = warp & 3;            // 2 x 4 warps: each 64 (M) x 32 (N)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_m = warp >> 2;
     const int g = lane >> 2, t4 = lane & 3;
     const int bn = (int)gridDim.y - 1 - (int)blockIdx.y;        // heaviest column blocks first
     const int64_t m0 = (int64_t)blockIdx.x * GP_BM;
     const int r0 = bn * GP_BN;
     const int k_tiles = (r0 + GP_BN) / GP_BK;                   // c <= r: columns beyond the diagonal block are zero
 
-    const double* a_src = kq + m0 * n_pad;                      // A[m][c]
-    const double* b_src = linv + (int64_t)r0 * n_pad;           // B[r][c]
-
-    auto load_stage = [&](int stage, int kt) {
-        double* As = smem + stage * GP_STAGE;
-        double* Bs = As + GP_BM * GP_LD;
-        const int c0 = kt * GP_BK;
-        // 128 rows x 16 doubles = 1024 16-byte chunks per operand; 256 threads x 4
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int chunk = tid + it * 256;
-            const int r = chunk >> 3, cc = (chunk & 7) * 2;
-            cp_async16(As + r * GP_LD + cc, a_src + (int64_t)r * n_pad + c0 + cc);
-            cp_async16(Bs + r * GP_LD + cc, b_src + (int64_t)r * n_pad + c0 + cc);
-        }
-    };
-
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-#pragma unroll
-    for (int s = 0; s < GP_STAGES - 1; ++s) {
-        if (s < k_tiles) load_stage(s, s);
-        cp_async_commit();
-    }
-    for (int kt = 0; kt < k_tiles; ++kt) {
-        cp_async_wait<GP_STAGES - 2>();
-        __syncthreads();
-        const int nxt = kt + GP_STAGES - 1;
-        if (nxt < k_tiles) load_stage(nxt % GP_STAGES, nxt);
-        cp_async_commit();
-        const double* As = smem + (kt % GP_STAGES) * GP_STAGE + (warp_m * 64) * GP_LD;
-        const double* Bs = smem + (kt % GP_STAGES) * GP_STAGE + GP_BM * GP_LD + (warp_n * 32) * GP_LD;
-#pragma unroll
-        for (int k4 = 0; k4 < GP_BK / 4; ++k4) {
-            double a[8], b[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = As[(i * 8 + g) * GP_LD + k4 * 4 + t4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[(j * 8 + g) * GP_LD + k4 * 4 + t4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-    }
-    cp_async_wait<0>();
+    dmma_tile_tn(kq + m0 * n_pad, n_pad, linv + (int64_t)r0 * n_pad, n_pad, k_tiles, acc, smem);   // A[m][c], B[r][c]
 
     // epilogue: sum of squares over this CTA's 128 columns, per query row
 #pragma unroll
@@ -442,7 +382,7 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
     const int64_t chunk_cap = round_up(n_q < kGpChunk ? n_q : kGpChunk, GP_BM);
     double* kq = (double*)workspace;
     double* ssq = kq + chunk_cap * gp->n_pad;
-    const size_t smem = (size_t)GP_STAGES * GP_STAGE * sizeof(double);
+    const size_t smem = kDmmaSmemBytes;
     cudaFuncSetAttribute(gp_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int64_t q0 = 0; q0 < n_q; q0 += kGpChunk) {
         const int64_t nq = (n_q - q0) < kGpChunk ? (n_q - q0) : kGpChunk;

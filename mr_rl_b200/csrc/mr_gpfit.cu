@@ -1,0 +1,258 @@
+// GP "fit" on the device for given hyper-parameters (what GaussianProcessRegressor.fit computes after
+// / without its optimiser, sklearn _gpr.py: K = kernel_(X) + alpha*I, L_ = cholesky(K), alpha_ = K^-1 y,
+// and log_marginal_likelihood(theta)) — Learning_module.py:122-123, SURVEY §8 a14 / §8f rank 2.
+//
+//   K      = exp(-0.5 |x_i - x_j|^2 / l^2) + (noise + jitter) I             gp_build_k_kernel
+//   L      = chol(K)         right-looking, 128 x 128 blocks:
+//              diagonal block  -> chol_diag_kernel (one CTA, shared memory; also M_kk = L_kk^-1)
+//              panel           -> L_ik = A_ik M_kk^T                         block GEMM on the FP64 tensor pipe
+//              trailing update -> A_ij -= L_ik L_jk^T                        block GEMM (DMMA, mr_dmma.cuh)
+//   W      = L^-1            block forward substitution, W and W^T kept so every product is in TN form
+//   alpha  = W^T (W y),  LML = -0.5 y.alpha - sum log L_ii - n/2 log 2 pi
+// Padding rows/cols (n_train..n_pad) carry an identity block so the factorisation is well defined; they
+// are zeroed in W at the end, as mr_gp_predict expects.
+#include <cuda_runtime.h>
+
+#include "mr_common.cuh"
+#include "mr_dmma.cuh"
+
+namespace mr {
+
+constexpr int NB = 128;                 // block size = DMMA tile
+constexpr int DIAG_LD = NB + 1;         // padded shared-memory rows: thread t walks row t without bank conflicts
+
+template <int DIM>
+__global__ void gp_build_k_kernel(const double* __restrict__ x, int n_train, int n_pad, double ls, double noise, double jitter,
+                                  double* __restrict__ xs_out, double* __restrict__ K) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_pad * n_pad) return;
+    const int i = (int)(idx / n_pad), j = (int)(idx % n_pad);
+    double v;
+    if (i < n_train && j < n_train) {
+        double d2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) { const double d = x[i * DIM + c] / ls - x[j * DIM + c] / ls; d2 += d * d; }
+        v = exp(-0.5 * d2);
+        if (i == j) v = (1.0 + noise) + jitter;                       // np.fill_diagonal(K, 1) then + noise_level + alpha
+    } else {
+        v = (i == j) ? 1.0 : 0.0;
+    }
+    K[idx] = v;
+    if (j == 0) {
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) xs_out[i * DIM + c] = i < n_train ? x[i * DIM + c] / ls : 0.0;
+    }
+}
+
+// Cholesky of the diagonal block A[k0:k0+128, k0:k0+128] (lower, in place) and its inverse M (lower).
+__global__ void __launch_bounds__(NB)
+chol_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ M /*[128][128]*/, int* __restrict__ info) {
+    extern __shared__ __align__(16) double sL[];               // [128][129]
+    const int t = threadIdx.x;
+    double* Ablk = A + (int64_t)k0 * ld + k0;
+    for (int c = 0; c < NB; ++c) sL[t * DIAG_LD + c] = c <= t ? Ablk[(int64_t)t * ld + c] : 0.0;
+    __syncthreads();
+    // left-looking, one column per step: every thread t >= j finishes its element of column j
+    for (int j = 0; j < NB; ++j) {
+        double s = sL[t * DIAG_LD + j];
+        if (t >= j) {
+            for (int c = 0; c < j; ++c) s = fma(-sL[t * DIAG_LD + c], sL[j * DIAG_LD + c], s);
+        }
+        __syncthreads();
+        if (t == j) {
+            if (!(s > 0.0)) { atomicExch(info, k0 + j + 1); s = 1.0; }   // not positive definite (LAPACK info > 0)
+            sL[j * DIAG_LD + j] = sqrt(s);
+        }
+        __syncthreads();
+        if (t > j) sL[t * DIAG_LD + j] = s / sL[j * DIAG_LD + j];
+        __syncthreads();
+    }
+    for (int c = 0; c < NB; ++c) Ablk[(int64_t)t * ld + c] = sL[t * DIAG_LD + c];   // upper part of the block := 0
+    // inverse: thread j solves L m = e_j for column j of M by forward substitution
+    // (column j lives in M[:, j]: coalesced across the CTA, and a thread only re-reads its own stores)
+    const int j = t;
+    for (int i = 0; i < NB; ++i) {
+        double s = (i == j) ? 1.0 : 0.0;
+        for (int c = j; c < i; ++c) s = fma(-sL[i * DIAG_LD + c], M[c * NB + j], s);
+        M[i * NB + j] = i < j ? 0.0 : s / sL[i * DIAG_LD + i];
+    }
+}
+
+// One 128 x 128 block product in TN form with a selectable epilogue.
+//   mode 0: C  = acc          mode 1: C -= acc          mode 2: C = -acc and CT (transposed) = -acc
+struct BlockGemmJob { const double* a; const double* b; double* c; double* ct; int k_tiles; };
+
+__device__ __forceinline__ void block_gemm_epilogue(const double (&acc)[8][4][2], double* C, int64_t ldc, double* CT,
+                                                    int64_t ldct, int mode) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_m = warp >> 2, warp_n = warp & 3, g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = warp_m * 64 + i * 8 + g, c = warp_n * 32 + j * 8 + t4 * 2 + e;
+                const double v = acc[i][j][e];
+                if (mode == 0) C[(int64_t)r * ldc + c] = v;
+                else if (mode == 1) C[(int64_t)r * ldc + c] -= v;
+                else { C[(int64_t)r * ldc + c] = -v; CT[(int64_t)c * ldct + r] = -v; }
+            }
+}
+
+// panel: L_ik = A_ik M_kk^T for i = k+1 .. nb-1 (blockIdx.x = i - k - 1), in place over A_ik
+__global__ void __launch_bounds__(256)
+chol_panel_kernel(double* __restrict__ A, int ld, int k, const double* __restrict__ M, double* __restrict__ tmp) {
+    extern __shared__ __align__(16) double smem[];
+    const int i = k + 1 + blockIdx.x;
+    double acc[8][4][2] = {};
+    double* Aik = A + (int64_t)i * NB * ld + (int64_t)k * NB;
+    dmma_tile_tn(Aik, ld, M, NB, NB / GP_BK, acc, smem);        // C[m][n] = sum_c A_ik[m][c] M[n][c]
+    // in place: every thread's loads of A_ik finished inside the mainloop (its last __syncthreads)
+    block_gemm_epilogue(acc, Aik, ld, nullptr, 0, 0);
+    (void)tmp;
+}
+
+// trailing update: A_ij -= L_ik L_jk^T for k < j <= i < nb; blockIdx.x enumerates the (i, j) pairs
+__global__ void __launch_bounds__(256)
+chol_update_kernel(double* __restrict__ A, int ld, int k, int nb) {
+    extern __shared__ __align__(16) double smem[];
+    int rem = blockIdx.x, i = k + 1;
+    while (rem >= i - k) { rem -= i - k; ++i; }                 // row i has (i - k) blocks j = k+1 .. i
+    const int j = k + 1 + rem;
+    double acc[8][4][2] = {};
+    dmma_tile_tn(A + (int64_t)i * NB * ld + (int64_t)k * NB, ld, A + (int64_t)j * NB * ld + (int64_t)k * NB, ld,
+                 NB / GP_BK, acc, smem);
+    block_gemm_epilogue(acc, A + (int64_t)i * NB * ld + (int64_t)j * NB, ld, nullptr, 0, 1);
+}
+
+// inverse, step 1 for block row i: ST_ij = S_ij^T with S_ij = sum_{c=j}^{i-1} L_ic W_cj   (j = blockIdx.x < i)
+//   ST[n][m] = sum_c WT_jc[n][c'] L_ic[m][c']  -> A = WT rows of block j, B = L rows of block i, K = (i - j) * 128
+__global__ void __launch_bounds__(256)
+inv_s_kernel(const double* __restrict__ Lm, const double* __restrict__ WT, int ld, int i, double* __restrict__ ST) {
+    extern __shared__ __align__(16) double smem[];
+    const int j = blockIdx.x;
+    double acc[8][4][2] = {};
+    dmma_tile_tn(WT + (int64_t)j * NB * ld + (int64_t)j * NB, ld, Lm + (int64_t)i * NB * ld + (int64_t)j * NB, ld,
+                 (i - j) * NB / GP_BK, acc, smem);
+    block_gemm_epilogue(acc, ST + (int64_t)j * NB * NB, NB, nullptr, 0, 0);
+}
+
+// inverse, step 2: W_ij = -M_ii S_ij  ->  W_ij[m][n] = -sum_c M_ii[m][c] ST_ij[n][c];  WT_ji = W_ij^T
+__global__ void __launch_bounds__(256)
+inv_w_kernel(const double* __restrict__ Mii, const double* __restrict__ ST, double* __restrict__ W, double* __restrict__ WT,
+             int ld, int i) {
+    extern __shared__ __align__(16) double smem[];
+    const int j = blockIdx.x;
+    double acc[8][4][2] = {};
+    dmma_tile_tn(Mii, NB, ST + (int64_t)j * NB * NB, NB, NB / GP_BK, acc, smem);
+    block_gemm_epilogue(acc, W + (int64_t)i * NB * ld + (int64_t)j * NB, ld, WT + (int64_t)j * NB * ld + (int64_t)i * NB, ld, 2);
+}
+
+// W_ii = M_ii, WT_ii = M_ii^T for all diagonal blocks; everything above the block diagonal of W (below for WT) = 0
+__global__ void inv_init_kernel(const double* __restrict__ Mall, double* __restrict__ W, double* __restrict__ WT, int ld, int nb) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)ld * ld) return;
+    const int r = (int)(idx / ld), c = (int)(idx % ld);
+    const int br = r / NB, bc = c / NB;
+    double w = 0.0, wt = 0.0;
+    if (br == bc) { w = Mall[(int64_t)br * NB * NB + (r % NB) * NB + (c % NB)]; wt = Mall[(int64_t)br * NB * NB + (c % NB) * NB + (r % NB)]; }
+    if (br <= bc) W[idx] = w;          // strictly-lower blocks of W are written by inv_w_kernel
+    if (br >= bc) WT[idx] = wt;        // strictly-upper blocks of WT likewise
+    (void)nb;
+}
+
+// y = T x for a row-major matrix (one warp per row); used for W y and W^T (W y) via WT
+__global__ void matvec_kernel(const double* __restrict__ T, int ld, int n, const double* __restrict__ x, double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n) return;
+    double s = 0.0;
+    for (int c = lane; c < n; c += 32) s = fma(T[(int64_t)row * ld + c], x[c], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) y[row] = s;
+}
+
+// lml = -0.5 y.alpha - sum_{i<n} log L_ii - n/2 log(2 pi); also zero W on the padding diagonal
+__global__ void gp_finish_kernel(const double* __restrict__ Lm, int ld, int n_train, int n_pad, const double* __restrict__ y,
+                                 const double* __restrict__ alpha, double* __restrict__ W, double* __restrict__ lml) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_train; i += blockDim.x) s += -0.5 * y[i] * alpha[i] - log(Lm[(int64_t)i * ld + i]);
+    for (int i = n_train + threadIdx.x; i < n_pad; i += blockDim.x) W[(int64_t)i * ld + i] = 0.0;
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off]; __syncthreads(); }
+    if (threadIdx.x == 0 && lml) *lml = red[0] - 0.5 * n_train * 1.8378770664093453;   // log(2 pi)
+}
+
+}  // namespace mr
+
+extern "C" {
+
+int64_t mr_gp_fit_workspace_bytes(int32_t n_pad) {
+    const int64_t n = n_pad, nb = n_pad / mr::NB;
+    // K/L, WT, per-block inverses M, ST scratch (nb blocks), y padded, tmp vector, info
+    return (2 * n * n + nb * mr::NB * mr::NB * 2 + 2 * n) * 8 + 64;
+}
+
+int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n_pad, int32_t dim, double length_scale,
+              double noise_level, double jitter, double* x_scaled_out, double* alpha_out, double* linv_out,
+              double* lml_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace mr;
+    if (!x_train || !y || !x_scaled_out || !alpha_out || !linv_out) return fail(MR_ERR_ARG, "mr_gp_fit: null argument");
+    if (n_train <= 0 || n_pad < n_train || n_pad % NB != 0) return fail(MR_ERR_ARG, "mr_gp_fit: n_pad must be a multiple of %d >= n_train", NB);
+    if (dim != 1 && dim != 2) return fail(MR_ERR_UNSUPPORTED, "mr_gp_fit: dim must be 1 or 2");
+    if (!(length_scale > 0)) return fail(MR_ERR_ARG, "mr_gp_fit: bad length_scale");
+    if (!workspace || workspace_bytes < mr_gp_fit_workspace_bytes(n_pad)) return fail(MR_ERR_ARG, "mr_gp_fit: workspace too small");
+    if (((uintptr_t)workspace | (uintptr_t)linv_out) & 15u) return fail(MR_ERR_ARG, "mr_gp_fit: buffers must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ld = n_pad, nb = n_pad / NB;
+    double* K = (double*)workspace;                       // becomes L
+    double* WT = K + (int64_t)ld * ld;
+    double* Mall = WT + (int64_t)ld * ld;                 // [nb][128][128]
+    double* ST = Mall + (int64_t)nb * NB * NB;            // [nb][128][128]
+    double* ypad = ST + (int64_t)nb * NB * NB;            // [n_pad]
+    double* tmp = ypad + n_pad;                           // [n_pad]
+    int* info = (int*)(tmp + n_pad);
+    double* W = linv_out;
+
+    cudaMemsetAsync(info, 0, sizeof(int), s);
+    cudaMemsetAsync(ypad, 0, (size_t)n_pad * 8, s);
+    cudaMemcpyAsync(ypad, y, (size_t)n_train * 8, cudaMemcpyDeviceToDevice, s);
+    const int64_t nn = (int64_t)ld * ld;
+    if (dim == 1) gp_build_k_kernel<1><<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(x_train, n_train, n_pad, length_scale, noise_level, jitter, x_scaled_out, K);
+    else gp_build_k_kernel<2><<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(x_train, n_train, n_pad, length_scale, noise_level, jitter, x_scaled_out, K);
+
+    const size_t diag_smem = (size_t)NB * DIAG_LD * 8;
+    cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem);
+    cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+    cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+    cudaFuncSetAttribute(inv_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+    cudaFuncSetAttribute(inv_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+
+    for (int k = 0; k < nb; ++k) {
+        chol_diag_kernel<<<1, NB, diag_smem, s>>>(K, ld, k * NB, Mall + (int64_t)k * NB * NB, info);
+        const int r = nb - k - 1;
+        if (r > 0) {
+            chol_panel_kernel<<<r, 256, kDmmaSmemBytes, s>>>(K, ld, k, Mall + (int64_t)k * NB * NB, tmp);
+            chol_update_kernel<<<r * (r + 1) / 2, 256, kDmmaSmemBytes, s>>>(K, ld, k, nb);
+        }
+    }
+    // the strictly-upper blocks of K still hold kernel values: they are never read again (all products
+    // touch blocks on or below the diagonal), and W / WT are initialised explicitly
+    inv_init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(Mall, W, WT, ld, nb);
+    for (int i = 1; i < nb; ++i) {
+        inv_s_kernel<<<i, 256, kDmmaSmemBytes, s>>>(K, WT, ld, i, ST);
+        inv_w_kernel<<<i, 256, kDmmaSmemBytes, s>>>(Mall + (int64_t)i * NB * NB, ST, W, WT, ld, i);
+    }
+    const unsigned mv_blocks = (unsigned)(((int64_t)n_pad * 32 + 255) / 256);
+    matvec_kernel<<<mv_blocks, 256, 0, s>>>(W, ld, n_pad, ypad, tmp);            // tmp = W y = L^-1 y
+    matvec_kernel<<<mv_blocks, 256, 0, s>>>(WT, ld, n_pad, tmp, alpha_out);      // alpha = W^T tmp = K^-1 y
+    gp_finish_kernel<<<1, 256, 0, s>>>(K, ld, n_train, n_pad, ypad, alpha_out, W, lml_out);
+    if (info_out) cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, s);
+    return check_launch("mr_gp_fit");
+}
+
+}  // extern "C"

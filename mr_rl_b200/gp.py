@@ -59,6 +59,52 @@ class DeviceGP:
             raise ValueError("normalize_y=True models are not supported (the reference uses the default False)")
         return cls(gpr.X_train_, gpr.alpha_, gpr.L_ if with_std else None, k.k1.length_scale, k.k2.noise_level, device)
 
+    @classmethod
+    def fit(cls, X, y, length_scale, noise_level, jitter=1e-10, device="cuda"):
+        """GaussianProcessRegressor.fit at FIXED hyper-parameters, on the device (csrc/mr_gpfit.cu): what sklearn
+        computes once theta is known (K, cholesky, alpha_, L^-1 and the log marginal likelihood;
+        Learning_module.py:122-123).  ``jitter`` is sklearn's ``alpha`` (default 1e-10).  The optimiser over theta
+        can stay on the host and call this as its objective: ``gp.log_marginal_likelihood_value_``."""
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.MRLibraryError("DeviceGP needs a CUDA device: there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        Xt = torch.as_tensor(X).to(device=self.device, dtype=torch.float64)
+        Xt = Xt.reshape(Xt.shape[0], -1).contiguous()
+        yt = torch.as_tensor(y).to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        n, d = Xt.shape
+        if d not in (1, 2):
+            raise ValueError("GP input dimension must be 1 (Learning_module) or 2 (Learning_module_2d)")
+        if yt.numel() != n:
+            raise ValueError("X and y disagree on the number of samples")
+        self.n_train, self.dim = n, d
+        self.n_pad = (n + L.GP_PAD - 1) // L.GP_PAD * L.GP_PAD
+        self.length_scale, self.noise_level = float(length_scale), float(noise_level)
+        with torch.cuda.device(self.device):
+            self._xs = torch.empty((self.n_pad, d), dtype=torch.float64, device=self.device)
+            self._alpha = torch.empty(self.n_pad, dtype=torch.float64, device=self.device)
+            self._linv = torch.empty((self.n_pad, self.n_pad), dtype=torch.float64, device=self.device)
+            scal = torch.zeros(2, dtype=torch.float64, device=self.device)       # [lml, info (int32 in the low bytes)]
+            ws_bytes = int(self.lib.mr_gp_fit_workspace_bytes(self.n_pad))
+            ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            rc = self.lib.mr_gp_fit(Xt.data_ptr(), yt.data_ptr(), n, self.n_pad, d, self.length_scale, self.noise_level,
+                                    float(jitter), self._xs.data_ptr(), self._alpha.data_ptr(), self._linv.data_ptr(),
+                                    scal.data_ptr(), scal.data_ptr() + 8, ws.data_ptr(), ws_bytes, stream)
+            L.check(rc, "mr_gp_fit")
+            info = int(scal[1:].view(torch.int32)[0].item())
+            if info != 0:
+                raise np.linalg.LinAlgError(f"{info}-th leading minor of the kernel matrix is not positive definite")
+            self.log_marginal_likelihood_value_ = float(scal[0].item())
+        self._c = L.GPModel(self._xs.data_ptr(), self._alpha.data_ptr(), self._linv.data_ptr(),
+                            n, self.n_pad, d, 0, self.length_scale, self.noise_level)
+        self._ws = None
+        self.kernel_launches = 0
+        return self
+
     def predict(self, q, return_std=False):
         """q: [n_q] or [n_q, dim] float64 (device tensor or array).  Returns mean[, std] device tensors."""
         if self.device.index is not None and torch.cuda.current_device() != self.device.index:
