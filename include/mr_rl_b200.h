@@ -219,12 +219,13 @@ int mr_gp_correct_heading(const mr_gp_model* gpx, const mr_gp_model* gpy, const 
  * (Learning_module.py:30-33,122-123): K = rbf(X/l) + (noise_level + jitter) I  (jitter = sklearn's alpha, 1e-10),
  * L = chol(K), alpha = K^-1 y, linv = L^-1, lml = -0.5 y.alpha - sum log L_ii - n/2 log 2pi.
  * x_train [n_train][dim], y [n_train].  Outputs are laid out as mr_gp_model wants them: x_scaled_out
- * [n_pad][dim], alpha_out [n_pad], linv_out [n_pad][n_pad] (padding zero); lml_out (1 double) and info_out
- * (1 int32: 0, or 1 + the first non-positive pivot like LAPACK potrf) may be NULL.  n_pad must be a multiple of
+ * [n_pad][dim], alpha_out [n_pad], linv_out [n_pad][n_pad] (padding zero); lml_out (1 double), grad_out
+ * (2 doubles: d lml / d log length_scale, d lml / d log noise_level — what sklearn's optimiser consumes) and
+ * info_out (1 int32: 0, or 1 + the first non-positive pivot like LAPACK potrf) may be NULL.  n_pad must be a multiple of
  * MR_GP_PAD; workspace must hold mr_gp_fit_workspace_bytes(n_pad) bytes, 16-byte aligned. */
 int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n_pad, int32_t dim, double length_scale,
               double noise_level, double jitter, double* x_scaled_out, double* alpha_out, double* linv_out,
-              double* lml_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream);
+              double* lml_out, double* grad_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t mr_gp_fit_workspace_bytes(int32_t n_pad);
 
 /* ---- DDPG actor forward (RL/MR_ddpg.py:124-149) --------------------------------------

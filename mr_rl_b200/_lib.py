@@ -106,7 +106,8 @@ def load():
                                           C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mr_gp_correct_heading.restype = C.c_int
     lib.mr_gp_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
-                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                              C.c_void_p]
     lib.mr_gp_fit.restype = C.c_int
     lib.mr_gp_fit_workspace_bytes.argtypes = [C.c_int32]
     lib.mr_gp_fit_workspace_bytes.restype = C.c_int64

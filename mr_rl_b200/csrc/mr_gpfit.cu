@@ -162,6 +162,61 @@ __global__ void inv_init_kernel(const double* __restrict__ Mall, double* __restr
     (void)nb;
 }
 
+// Gradient of the log marginal likelihood w.r.t. theta = (log l, log noise) (sklearn _gpr.py log_marginal_likelihood,
+// eval_gradient: 0.5 * sum_ij (alpha_i alpha_j - Kinv_ij) dK_ij/dtheta) with K^-1 = W^T W never materialised: each CTA
+// forms one 128 x 128 block of K^-1 on the tensor pipe (lower block triangle only, off-diagonal blocks count
+// twice) and contracts it in registers with dK/dlog l = K_rbf * d2 (recomputed from the scaled inputs) and
+// dK/dlog noise = noise * I.  Per-CTA partial sums, added in a fixed order by gp_finish_kernel (deterministic).
+template <int DIM>
+__global__ void __launch_bounds__(256)
+gp_lml_grad_kernel(const double* __restrict__ WT, int ld, int nb, int n_train, const double* __restrict__ xs,
+                   const double* __restrict__ alpha, double* __restrict__ partial /*[grid][2]*/) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double s_red[8][2];
+    int rem = blockIdx.x, bi = 0;
+    while (rem > bi) { rem -= bi + 1; ++bi; }                   // block row bi has bi + 1 blocks bj = 0 .. bi
+    const int bj = rem;
+    double acc[8][4][2] = {};
+    dmma_tile_tn(WT + (int64_t)bi * NB * ld + (int64_t)bi * NB, ld, WT + (int64_t)bj * NB * ld + (int64_t)bi * NB, ld,
+                 (nb - bi) * NB / GP_BK, acc, smem);            // W[c][i] = 0 for c < i: the sum starts at block bi
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_m = warp >> 2, warp_n = warp & 3, g = lane >> 2, t4 = lane & 3;
+    const double wgt = bi == bj ? 1.0 : 2.0;
+    double gl = 0.0, gn = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = bi * NB + warp_m * 64 + i * 8 + g;
+        if (r >= n_train) continue;
+        const double ar = alpha[r];
+        double xr[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) xr[c] = xs[r * DIM + c];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cidx = bj * NB + warp_n * 32 + j * 8 + t4 * 2 + e;
+                if (cidx >= n_train) continue;
+                double d2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) { const double d = xr[c] - xs[cidx * DIM + c]; d2 += d * d; }
+                const double t = ar * alpha[cidx] - acc[i][j][e];
+                gl += t * exp(-0.5 * d2) * d2;
+                if (r == cidx) gn += t;
+            }
+    }
+    gl *= wgt;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { gl += __shfl_xor_sync(0xffffffffu, gl, off); gn += __shfl_xor_sync(0xffffffffu, gn, off); }
+    if (lane == 0) { s_red[warp][0] = gl; s_red[warp][1] = gn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += s_red[w][0]; b += s_red[w][1]; }
+        partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b;
+    }
+}
+
 // y = T x for a row-major matrix (one warp per row); used for W y and W^T (W y) via WT
 __global__ void matvec_kernel(const double* __restrict__ T, int ld, int n, const double* __restrict__ x, double* __restrict__ y) {
     const int lane = threadIdx.x & 31;
@@ -176,8 +231,20 @@ __global__ void matvec_kernel(const double* __restrict__ T, int ld, int n, const
 
 // lml = -0.5 y.alpha - sum_{i<n} log L_ii - n/2 log(2 pi); also zero W on the padding diagonal
 __global__ void gp_finish_kernel(const double* __restrict__ Lm, int ld, int n_train, int n_pad, const double* __restrict__ y,
-                                 const double* __restrict__ alpha, double* __restrict__ W, double* __restrict__ lml) {
+                                 const double* __restrict__ alpha, double* __restrict__ W, double* __restrict__ lml,
+                                 const double* __restrict__ partial, int n_partial, double noise, double* __restrict__ grad) {
     __shared__ double red[256];
+    if (grad) {                                                  // fixed summation order: strided, then a tree
+        for (int comp = 0; comp < 2; ++comp) {
+            double g = 0.0;
+            for (int i = threadIdx.x; i < n_partial; i += blockDim.x) g += partial[2 * i + comp];
+            red[threadIdx.x] = g;
+            __syncthreads();
+            for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off]; __syncthreads(); }
+            if (threadIdx.x == 0) grad[comp] = comp == 0 ? 0.5 * red[0] : 0.5 * noise * red[0];
+            __syncthreads();
+        }
+    }
     double s = 0.0;
     for (int i = threadIdx.x; i < n_train; i += blockDim.x) s += -0.5 * y[i] * alpha[i] - log(Lm[(int64_t)i * ld + i]);
     for (int i = n_train + threadIdx.x; i < n_pad; i += blockDim.x) W[(int64_t)i * ld + i] = 0.0;
@@ -194,12 +261,13 @@ extern "C" {
 int64_t mr_gp_fit_workspace_bytes(int32_t n_pad) {
     const int64_t n = n_pad, nb = n_pad / mr::NB;
     // K/L, WT, per-block inverses M, ST scratch (nb blocks), y padded, tmp vector, info
-    return (2 * n * n + nb * mr::NB * mr::NB * 2 + 2 * n) * 8 + 64;
+    // + per-CTA gradient partials
+    return (2 * n * n + nb * mr::NB * mr::NB * 2 + 2 * n + nb * (nb + 1)) * 8 + 64;
 }
 
 int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n_pad, int32_t dim, double length_scale,
               double noise_level, double jitter, double* x_scaled_out, double* alpha_out, double* linv_out,
-              double* lml_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream) {
+              double* lml_out, double* grad_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream) {
     using namespace mr;
     if (!x_train || !y || !x_scaled_out || !alpha_out || !linv_out) return fail(MR_ERR_ARG, "mr_gp_fit: null argument");
     if (n_train <= 0 || n_pad < n_train || n_pad % NB != 0) return fail(MR_ERR_ARG, "mr_gp_fit: n_pad must be a multiple of %d >= n_train", NB);
@@ -215,7 +283,8 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     double* ST = Mall + (int64_t)nb * NB * NB;            // [nb][128][128]
     double* ypad = ST + (int64_t)nb * NB * NB;            // [n_pad]
     double* tmp = ypad + n_pad;                           // [n_pad]
-    int* info = (int*)(tmp + n_pad);
+    double* partial = tmp + n_pad;                        // [nb (nb + 1) / 2][2]
+    int* info = (int*)(partial + (int64_t)nb * (nb + 1));
     double* W = linv_out;
 
     cudaMemsetAsync(info, 0, sizeof(int), s);
@@ -250,7 +319,17 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     const unsigned mv_blocks = (unsigned)(((int64_t)n_pad * 32 + 255) / 256);
     matvec_kernel<<<mv_blocks, 256, 0, s>>>(W, ld, n_pad, ypad, tmp);            // tmp = W y = L^-1 y
     matvec_kernel<<<mv_blocks, 256, 0, s>>>(WT, ld, n_pad, tmp, alpha_out);      // alpha = W^T tmp = K^-1 y
-    gp_finish_kernel<<<1, 256, 0, s>>>(K, ld, n_train, n_pad, ypad, alpha_out, W, lml_out);
+    const int n_partial = nb * (nb + 1) / 2;
+    if (grad_out) {                                       // needs WT with its identity padding, alpha, scaled inputs
+        if (dim == 1) {
+            cudaFuncSetAttribute(gp_lml_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+            gp_lml_grad_kernel<1><<<n_partial, 256, kDmmaSmemBytes, s>>>(WT, ld, nb, n_train, x_scaled_out, alpha_out, partial);
+        } else {
+            cudaFuncSetAttribute(gp_lml_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+            gp_lml_grad_kernel<2><<<n_partial, 256, kDmmaSmemBytes, s>>>(WT, ld, nb, n_train, x_scaled_out, alpha_out, partial);
+        }
+    }
+    gp_finish_kernel<<<1, 256, 0, s>>>(K, ld, n_train, n_pad, ypad, alpha_out, W, lml_out, partial, n_partial, noise_level, grad_out);
     if (info_out) cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, s);
     return check_launch("mr_gp_fit");
 }

@@ -60,11 +60,12 @@ class DeviceGP:
         return cls(gpr.X_train_, gpr.alpha_, gpr.L_ if with_std else None, k.k1.length_scale, k.k2.noise_level, device)
 
     @classmethod
-    def fit(cls, X, y, length_scale, noise_level, jitter=1e-10, device="cuda"):
+    def fit(cls, X, y, length_scale, noise_level, jitter=1e-10, device="cuda", eval_gradient=False):
         """GaussianProcessRegressor.fit at FIXED hyper-parameters, on the device (csrc/mr_gpfit.cu): what sklearn
         computes once theta is known (K, cholesky, alpha_, L^-1 and the log marginal likelihood;
         Learning_module.py:122-123).  ``jitter`` is sklearn's ``alpha`` (default 1e-10).  The optimiser over theta
-        can stay on the host and call this as its objective: ``gp.log_marginal_likelihood_value_``."""
+        can stay on the host and call this as its objective (``eval_gradient=True``): ``log_marginal_likelihood_value_``
+        and ``log_marginal_likelihood_gradient_`` (w.r.t. log length_scale, log noise_level) — see gpr.DeviceGPR."""
         self = cls.__new__(cls)
         self.lib = L.load()
         self.device = torch.device(device)
@@ -87,18 +88,21 @@ class DeviceGP:
             self._xs = torch.empty((self.n_pad, d), dtype=torch.float64, device=self.device)
             self._alpha = torch.empty(self.n_pad, dtype=torch.float64, device=self.device)
             self._linv = torch.empty((self.n_pad, self.n_pad), dtype=torch.float64, device=self.device)
-            scal = torch.zeros(2, dtype=torch.float64, device=self.device)       # [lml, info (int32 in the low bytes)]
+            scal = torch.zeros(4, dtype=torch.float64, device=self.device)       # [lml, dlml/dlog l, dlml/dlog noise, info]
             ws_bytes = int(self.lib.mr_gp_fit_workspace_bytes(self.n_pad))
             ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)
             stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             rc = self.lib.mr_gp_fit(Xt.data_ptr(), yt.data_ptr(), n, self.n_pad, d, self.length_scale, self.noise_level,
                                     float(jitter), self._xs.data_ptr(), self._alpha.data_ptr(), self._linv.data_ptr(),
-                                    scal.data_ptr(), scal.data_ptr() + 8, ws.data_ptr(), ws_bytes, stream)
+                                    scal.data_ptr(), scal.data_ptr() + 8 if eval_gradient else None, scal.data_ptr() + 24,
+                                    ws.data_ptr(), ws_bytes, stream)
             L.check(rc, "mr_gp_fit")
-            info = int(scal[1:].view(torch.int32)[0].item())
+            host = scal.cpu()                                                    # one 32-byte read back
+            info = int(host[3:].view(torch.int32)[0])
             if info != 0:
                 raise np.linalg.LinAlgError(f"{info}-th leading minor of the kernel matrix is not positive definite")
-            self.log_marginal_likelihood_value_ = float(scal[0].item())
+            self.log_marginal_likelihood_value_ = float(host[0])
+            self.log_marginal_likelihood_gradient_ = host[1:3].numpy().copy() if eval_gradient else None
         self._c = L.GPModel(self._xs.data_ptr(), self._alpha.data_ptr(), self._linv.data_ptr(),
                             n, self.n_pad, d, 0, self.length_scale, self.noise_level)
         self._ws = None

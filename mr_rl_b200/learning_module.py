@@ -2,8 +2,9 @@
 
 Same attribute / method surface as the reference (gprX, gprY, X, Yx, Yy, a0, freq, Dx, Dy;
 estimateDisturbance, learn, error, predict) plus batched entry points for the vectorised
-control loop.  Fitting (sklearn GPR with 5 optimiser restarts) stays on the host exactly as in
-the reference; the fitted model is uploaded once and every inference call runs on the GPU.
+control loop.  ``fit="device"`` (default) runs the GPR fit on the GPU too (gpr.DeviceGPR: sklearn's L-BFGS-B
+search with 5 restarts, each objective evaluation a device Cholesky); ``fit="host"`` fits with sklearn exactly
+as the reference does and uploads the fitted model once.  Every inference call runs on the GPU either way.
 """
 from __future__ import annotations
 
@@ -16,12 +17,20 @@ from .gp import DeviceGP
 
 
 class LearningModule:
-    def __init__(self, device="cuda"):
-        from sklearn.gaussian_process import GaussianProcessRegressor
-        from sklearn.gaussian_process.kernels import RBF, WhiteKernel
-        kernel = RBF(length_scale=1.0, length_scale_bounds=(1e-2, 10.0)) + WhiteKernel()     # Learning_module.py:30
-        self.gprX = GaussianProcessRegressor(kernel=kernel, n_restarts_optimizer=5)
-        self.gprY = GaussianProcessRegressor(kernel=kernel, n_restarts_optimizer=5)
+    def __init__(self, device="cuda", fit="device"):
+        if fit == "device":
+            from .gpr import DeviceGPR
+            # Learning_module.py:30-33: RBF(1.0, (1e-2, 10)) + WhiteKernel() (noise 1.0, bounds (1e-5, 1e5)), 5 restarts
+            self.gprX = DeviceGPR(n_restarts_optimizer=5, device=device)
+            self.gprY = DeviceGPR(n_restarts_optimizer=5, device=device)
+        elif fit == "host":
+            from sklearn.gaussian_process import GaussianProcessRegressor
+            from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+            kernel = RBF(length_scale=1.0, length_scale_bounds=(1e-2, 10.0)) + WhiteKernel()     # Learning_module.py:30
+            self.gprX = GaussianProcessRegressor(kernel=kernel, n_restarts_optimizer=5)
+            self.gprY = GaussianProcessRegressor(kernel=kernel, n_restarts_optimizer=5)
+        else:
+            raise ValueError("fit must be 'device' or 'host'")
         self.device = device
         self.X, self.Yx, self.Yy = [], [], []
         self.a0 = 0
@@ -74,12 +83,13 @@ class LearningModule:
         return a0
 
     def upload(self):
-        """Copy the fitted sklearn models into HBM."""
-        self._dx = DeviceGP.from_sklearn(self.gprX, self.device)
-        self._dy = DeviceGP.from_sklearn(self.gprY, self.device)
+        """Fitted models into HBM (sklearn fits are copied; device fits already live there)."""
+        as_device = lambda g: g.device_model() if hasattr(g, "device_model") else DeviceGP.from_sklearn(g, self.device)
+        self._dx = as_device(self.gprX)
+        self._dy = as_device(self.gprY)
 
     def set_models(self, gprX, gprY, a0, freq, Dx=0.0, Dy=0.0):
-        """Install already-fitted sklearn GPRs (e.g. fixed kernels, optimizer=None)."""
+        """Install already-fitted GPRs (sklearn or DeviceGPR; e.g. fixed kernels, optimizer=None)."""
         self.gprX, self.gprY, self.a0, self.freq, self.Dx, self.Dy = gprX, gprY, a0, freq, Dx, Dy
         self.X = gprX.X_train_
         self.upload()

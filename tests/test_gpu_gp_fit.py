@@ -24,7 +24,7 @@ def test_device_fit_matches_sklearn_fixed_theta(n, dim, ls, noise):
     X = rng.uniform(-np.pi, np.pi, size=(n, dim))
     y = np.sin(X).sum(axis=1) + 0.1 * rng.standard_normal(n)
     ref = sk_fit(X, y, ls, noise)
-    gp = DeviceGP.fit(X, y, ls, noise)
+    gp = DeviceGP.fit(X, y, ls, noise, eval_gradient=True)
     n_pad = gp.n_pad
     alpha = gp._alpha.cpu().numpy()
     W = gp._linv.cpu().numpy()
@@ -38,6 +38,8 @@ def test_device_fit_matches_sklearn_fixed_theta(n, dim, ls, noise):
     assert np.all(np.triu(W, 1) == 0.0)
     lml = ref.log_marginal_likelihood(ref.kernel_.theta)
     assert abs(gp.log_marginal_likelihood_value_ - lml) <= 1e-9 * max(1.0, abs(lml))
+    _, grad = ref.log_marginal_likelihood(ref.kernel_.theta, eval_gradient=True)
+    assert np.allclose(gp.log_marginal_likelihood_gradient_, grad, rtol=1e-7, atol=1e-7 * np.abs(grad).max())
     assert np.allclose(gp._xs.cpu().numpy()[:n], X / ls, rtol=1e-15, atol=0)
     # and the fitted model predicts like sklearn's
     q = rng.uniform(-np.pi, np.pi, size=(513, dim))
@@ -59,11 +61,38 @@ def test_device_fit_reports_non_positive_definite():
 def test_device_fit_argument_errors():
     from mr_rl_b200 import _lib as L
     lib = L.load()
-    rc = lib.mr_gp_fit(None, None, 10, 128, 1, 1.0, 0.1, 1e-10, None, None, None, None, None, None, 0, None)
+    rc = lib.mr_gp_fit(None, None, 10, 128, 1, 1.0, 0.1, 1e-10, None, None, None, None, None, None, None, 0, None)
     assert rc != 0 and b"null" in lib.mr_last_error()
     d = torch.zeros(128 * 130, dtype=torch.float64, device="cuda")
     p = d.data_ptr()
-    rc = lib.mr_gp_fit(p, p, 10, 100, 1, 1.0, 0.1, 1e-10, p, p, p, None, None, p, 1 << 30, None)
+    rc = lib.mr_gp_fit(p, p, 10, 100, 1, 1.0, 0.1, 1e-10, p, p, p, None, None, None, p, 1 << 30, None)
     assert rc != 0 and b"multiple" in lib.mr_last_error()
-    rc = lib.mr_gp_fit(p, p, 10, 128, 1, 1.0, 0.1, 1e-10, p, p, p, None, None, p, 16, None)
+    rc = lib.mr_gp_fit(p, p, 10, 128, 1, 1.0, 0.1, 1e-10, p, p, p, None, None, None, p, 16, None)
     assert rc != 0 and b"workspace" in lib.mr_last_error()
+
+
+@pytest.mark.parametrize("restarts", [0, 3])
+def test_device_gpr_hyperparameter_search_matches_sklearn(restarts):
+    """gpr.DeviceGPR.fit = sklearn's search (L-BFGS-B from the initial theta + restarts drawn from the estimator's
+    RandomState), each objective evaluation on the device: same optimum, same predictions, same r^2
+    (Learning_module.py:28-33,122-126)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    from mr_rl_b200.gpr import DeviceGPR
+    rng = np.random.default_rng(7)
+    n = 400
+    X = np.sort(rng.uniform(-np.pi, np.pi, size=(n, 1)), axis=0)
+    y = 0.8 * np.sin(2 * X[:, 0]) + 0.3 * np.cos(X[:, 0]) + 0.15 * rng.standard_normal(n)
+    ref = GaussianProcessRegressor(kernel=RBF(1.0, (1e-2, 10.0)) + WhiteKernel(), n_restarts_optimizer=restarts,
+                                   random_state=11).fit(X, y)
+    dev = DeviceGPR(n_restarts_optimizer=restarts, random_state=11).fit(X, y)
+    assert np.allclose(dev.kernel_.theta, ref.kernel_.theta, rtol=1e-4, atol=1e-4)
+    assert abs(dev.log_marginal_likelihood_value_ - ref.log_marginal_likelihood_value_) < 1e-7 * abs(ref.log_marginal_likelihood_value_)
+    q = np.linspace(-3, 3, 257).reshape(-1, 1)
+    m, s = dev.predict(q, return_std=True)
+    mr, sr = ref.predict(q, return_std=True)
+    assert np.allclose(m, mr, rtol=1e-4, atol=1e-5) and np.allclose(s, sr, rtol=1e-4, atol=1e-6)
+    assert abs(dev.score(X, y) - ref.score(X, y)) < 1e-6
+    lml, grad = dev.log_marginal_likelihood(ref.kernel_.theta, eval_gradient=True)
+    lml_r, grad_r = ref.log_marginal_likelihood(ref.kernel_.theta, eval_gradient=True)
+    assert abs(lml - lml_r) < 1e-9 * abs(lml_r) and np.allclose(grad, grad_r, rtol=1e-6, atol=1e-6)

@@ -38,6 +38,28 @@ def main():
             row["lml_sklearn"] = float(ref.log_marginal_likelihood(ref.kernel_.theta))
         out.append(row)
         print(json.dumps(row), flush=True)
+    # the reference's fit (Learning_module.py:28-33,122): ~2k samples, 5 restarts
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    from mr_rl_b200.gpr import DeviceGPR
+    n = 1970
+    rng = np.random.default_rng(1)
+    X = np.sort(rng.uniform(-np.pi, np.pi, size=(n, 1)), axis=0)
+    y = 0.8 * np.sin(2 * X[:, 0]) + 0.3 * np.cos(X[:, 0]) + 0.15 * rng.standard_normal(n)
+    DeviceGPR(n_restarts_optimizer=0, random_state=3).fit(X[:256], y[:256])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev = DeviceGPR(n_restarts_optimizer=5, random_state=3).fit(X, y)
+    torch.cuda.synchronize()
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = GaussianProcessRegressor(kernel=RBF(1.0, (1e-2, 10.0)) + WhiteKernel(), n_restarts_optimizer=5, random_state=3).fit(X, y)
+    t_ref = time.perf_counter() - t0
+    row = {"search_n_train": n, "restarts": 5, "device_s": t_dev, "device_objective_evals": dev.n_objective_evals,
+           "sklearn_s": t_ref, "theta_device": dev.kernel_.theta.tolist(), "theta_sklearn": ref.kernel_.theta.tolist(),
+           "lml_device": dev.log_marginal_likelihood_value_, "lml_sklearn": float(ref.log_marginal_likelihood_value_)}
+    out.append(row)
+    print(json.dumps(row), flush=True)
     json.dump(out, open("gpurun_out/gpfit.json", "w"), indent=1)
 
 
