@@ -44,42 +44,106 @@ __global__ void gp_build_k_kernel(const double* __restrict__ x, int n_train, int
     }
 }
 
-// Cholesky of the diagonal block A[k0:k0+128, k0:k0+128] (lower, in place) and its inverse M (lower).
-__global__ void __launch_bounds__(NB)
+// Cholesky of the diagonal block A[k0:k0+128, k0:k0+128] (lower, in place) and its inverse M (lower), one CTA.
+// 256 threads hold the block as 8 x 8 register tiles (thread (ty, tx) owns rows ty + 16 a, columns tx + 16 b).
+// Step j of the right-looking factorisation needs column j of the trailing matrix; step j of the Gauss-Jordan
+// inversion of L needs row j of the partial inverse.  Both run in ONE loop on ONE register tile: once column c
+// is factored its entries are parked (unscaled) in shared memory and the registers start accumulating M[:, c].
+// Scaling by 1/sqrt(pivot) is deferred to the end (column c of L and row r of M are frozen after their step), so
+// a step is: publish 128 values -> one barrier -> X[r][c] -= (v[r] / pivot) * v[c].
+constexpr int DIAG_THREADS = 256;
+constexpr size_t kDiagSmemBytes = ((size_t)NB * DIAG_LD + 2 * NB + 2 * NB) * sizeof(double);
+
+__global__ void __launch_bounds__(DIAG_THREADS)
 chol_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ M /*[128][128]*/, int* __restrict__ info) {
-    extern __shared__ __align__(16) double sL[];               // [128][129]
-    const int t = threadIdx.x;
+    extern __shared__ __align__(16) double sm[];
+    double* sL = sm;                              // [128][129] unscaled columns of L, pivots on the diagonal
+    double* sV = sL + NB * DIAG_LD;               // [2][128]   per-step exchange: row j of M (c < j), pivot, column j (r > j)
+    double* sD = sV + 2 * NB;                     // [128] sqrt(pivot)
+    double* sR = sD + NB;                         // [128] 1 / sqrt(pivot)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double* Ablk = A + (int64_t)k0 * ld + k0;
-    for (int c = 0; c < NB; ++c) sL[t * DIAG_LD + c] = c <= t ? Ablk[(int64_t)t * ld + c] : 0.0;
+    double X[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            X[a][b] = c <= r ? Ablk[(int64_t)r * ld + c] : 0.0;     // tiles above the diagonal (b > a) are never used
+        }
+    // the tile index of column / row j is CTA-uniform, so only one of the eight bodies below runs per step
+    auto publish = [&](int j) {                   // exchange values for step j; column j leaves the trailing matrix
+        double* v = sV + (j & 1) * NB;
+        const int jt = j >> 4, jl = j & 15;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b != jt) continue;
+            if (tx == jl) {
+#pragma unroll
+                for (int a = b; a < 8; ++a) {
+                    const int r = ty + 16 * a;
+                    if (r >= j) { v[r] = X[a][b]; sL[r * DIAG_LD + j] = X[a][b]; X[a][b] = r == j ? 1.0 : 0.0; }
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            if (a != jt) continue;
+            if (ty == jl) {
+#pragma unroll
+                for (int b = 0; b <= a; ++b) {
+                    const int c = tx + 16 * b;
+                    if (c < j) v[c] = X[a][b];
+                }
+            }
+        }
+    };
+    const bool in_lower = tx <= ty;               // inside a diagonal tile: column <= row
+    publish(0);
     __syncthreads();
-    // left-looking, one column per step: every thread t >= j finishes its element of column j
     for (int j = 0; j < NB; ++j) {
-        double s = sL[t * DIAG_LD + j];
-        if (t >= j) {
-            for (int c = 0; c < j; ++c) s = fma(-sL[t * DIAG_LD + c], sL[j * DIAG_LD + c], s);
+        const double* v = sV + (j & 1) * NB;
+        const double inv_p = 1.0 / v[j];
+        double vc[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { const int c = tx + 16 * b; vc[b] = c == j ? 1.0 : v[c]; }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            if (16 * a + 15 <= j) continue;       // CTA-uniform: these rows are finished
+            const int r = ty + 16 * a;
+            const double lr = r > j ? -(v[r] * inv_p) : 0.0;      // rows <= j: a multiply by zero, no branch
+#pragma unroll
+            for (int b = 0; b < a; ++b) X[a][b] = fma(lr, vc[b], X[a][b]);
+            X[a][a] = fma(lr, in_lower ? vc[a] : 0.0, X[a][a]);
         }
-        __syncthreads();
-        if (t == j) {
-            if (!(s > 0.0)) { atomicExch(info, k0 + j + 1); s = 1.0; }   // not positive definite (LAPACK info > 0)
-            sL[j * DIAG_LD + j] = sqrt(s);
-        }
-        __syncthreads();
-        if (t > j) sL[t * DIAG_LD + j] = s / sL[j * DIAG_LD + j];
+        if (j + 1 < NB) publish(j + 1);
         __syncthreads();
     }
-    for (int c = 0; c < NB; ++c) Ablk[(int64_t)t * ld + c] = sL[t * DIAG_LD + c];   // upper part of the block := 0
-    // inverse: thread j solves L m = e_j for column j of M by forward substitution
-    // (column j lives in M[:, j]: coalesced across the CTA, and a thread only re-reads its own stores)
-    const int j = t;
-    for (int i = 0; i < NB; ++i) {
-        double s = (i == j) ? 1.0 : 0.0;
-        for (int c = j; c < i; ++c) s = fma(-sL[i * DIAG_LD + c], M[c * NB + j], s);
-        M[i * NB + j] = i < j ? 0.0 : s / sL[i * DIAG_LD + i];
+    if (threadIdx.x < NB) {
+        const double p = sL[threadIdx.x * DIAG_LD + threadIdx.x];
+        const double d = sqrt(p);
+        sD[threadIdx.x] = d; sR[threadIdx.x] = 1.0 / d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i)
+            if (!(sL[i * DIAG_LD + i] > 0.0)) { atomicCAS(info, 0, k0 + i + 1); break; }   // LAPACK potrf's info > 0
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            M[r * NB + c] = c <= r ? X[a][b] * sR[r] : 0.0;
+        }
+    for (int idx = threadIdx.x; idx < NB * NB; idx += DIAG_THREADS) {
+        const int r = idx / NB, c = idx % NB;
+        Ablk[(int64_t)r * ld + c] = c < r ? sL[r * DIAG_LD + c] * sR[c] : (c == r ? sD[c] : 0.0);   // upper part := 0
     }
 }
 
 // One 128 x 128 block product in TN form with a selectable epilogue.
-//   mode 0: C  = acc          mode 1: C -= acc          mode 2: C = -acc and CT (transposed) = -acc
+//   mode 0: C  = acc     mode 1: C -= acc     mode 3: C += acc     mode 2: C = -acc and CT (transposed) = -acc
 struct BlockGemmJob { const double* a; const double* b; double* c; double* ct; int k_tiles; };
 
 __device__ __forceinline__ void block_gemm_epilogue(const double (&acc)[8][4][2], double* C, int64_t ldc, double* CT,
@@ -96,6 +160,7 @@ __device__ __forceinline__ void block_gemm_epilogue(const double (&acc)[8][4][2]
                 const double v = acc[i][j][e];
                 if (mode == 0) C[(int64_t)r * ldc + c] = v;
                 else if (mode == 1) C[(int64_t)r * ldc + c] -= v;
+                else if (mode == 3) C[(int64_t)r * ldc + c] += v;
                 else { C[(int64_t)r * ldc + c] = -v; CT[(int64_t)c * ldct + r] = -v; }
             }
 }
@@ -126,40 +191,42 @@ chol_update_kernel(double* __restrict__ A, int ld, int k, int nb) {
     block_gemm_epilogue(acc, A + (int64_t)i * NB * ld + (int64_t)j * NB, ld, nullptr, 0, 1);
 }
 
-// inverse, step 1 for block row i: ST_ij = S_ij^T with S_ij = sum_{c=j}^{i-1} L_ic W_cj   (j = blockIdx.x < i)
-//   ST[n][m] = sum_c WT_jc[n][c'] L_ic[m][c']  -> A = WT rows of block j, B = L rows of block i, K = (i - j) * 128
+// Inverse W = L^-1 by block rows, right-looking so that every step is a wide grid of independent 128^3 products:
+// once block row c of W is known, S_ij += L_ic W_cj is pushed into every later row i (j <= c).  S_ij^T accumulates
+// in the slot of WT_ji (block (j, i) of W^T, zero until row i is finished), which is exactly the TN operand the
+// finishing product W_ij = -M_ii S_ij wants.
+//   ST_ij[n][m] += sum_k WT_jc[n][k] L_ic[m][k]     grid = (nb - c - 1) * (c + 1) blocks (i, j)
 __global__ void __launch_bounds__(256)
-inv_s_kernel(const double* __restrict__ Lm, const double* __restrict__ WT, int ld, int i, double* __restrict__ ST) {
+inv_acc_kernel(const double* __restrict__ Lm, double* __restrict__ WT, int ld, int c) {
+    extern __shared__ __align__(16) double smem[];
+    const int i = c + 1 + blockIdx.x / (c + 1), j = blockIdx.x % (c + 1);
+    double acc[8][4][2] = {};
+    dmma_tile_tn(WT + (int64_t)j * NB * ld + (int64_t)c * NB, ld, Lm + (int64_t)i * NB * ld + (int64_t)c * NB, ld,
+                 NB / GP_BK, acc, smem);
+    block_gemm_epilogue(acc, WT + (int64_t)j * NB * ld + (int64_t)i * NB, ld, nullptr, 0, 3);
+}
+
+//   W_ij[m][n] = -sum_k M_ii[m][k] ST_ij[n][k];  WT_ji = W_ij^T overwrites ST_ij (its loads finished in the mainloop)
+__global__ void __launch_bounds__(256)
+inv_w_kernel(const double* __restrict__ Mii, double* __restrict__ W, double* __restrict__ WT, int ld, int i) {
     extern __shared__ __align__(16) double smem[];
     const int j = blockIdx.x;
     double acc[8][4][2] = {};
-    dmma_tile_tn(WT + (int64_t)j * NB * ld + (int64_t)j * NB, ld, Lm + (int64_t)i * NB * ld + (int64_t)j * NB, ld,
-                 (i - j) * NB / GP_BK, acc, smem);
-    block_gemm_epilogue(acc, ST + (int64_t)j * NB * NB, NB, nullptr, 0, 0);
+    double* STij = WT + (int64_t)j * NB * ld + (int64_t)i * NB;
+    dmma_tile_tn(Mii, NB, STij, ld, NB / GP_BK, acc, smem);
+    block_gemm_epilogue(acc, W + (int64_t)i * NB * ld + (int64_t)j * NB, ld, STij, ld, 2);
 }
 
-// inverse, step 2: W_ij = -M_ii S_ij  ->  W_ij[m][n] = -sum_c M_ii[m][c] ST_ij[n][c];  WT_ji = W_ij^T
-__global__ void __launch_bounds__(256)
-inv_w_kernel(const double* __restrict__ Mii, const double* __restrict__ ST, double* __restrict__ W, double* __restrict__ WT,
-             int ld, int i) {
-    extern __shared__ __align__(16) double smem[];
-    const int j = blockIdx.x;
-    double acc[8][4][2] = {};
-    dmma_tile_tn(Mii, NB, ST + (int64_t)j * NB * NB, NB, NB / GP_BK, acc, smem);
-    block_gemm_epilogue(acc, W + (int64_t)i * NB * ld + (int64_t)j * NB, ld, WT + (int64_t)j * NB * ld + (int64_t)i * NB, ld, 2);
-}
-
-// W_ii = M_ii, WT_ii = M_ii^T for all diagonal blocks; everything above the block diagonal of W (below for WT) = 0
-__global__ void inv_init_kernel(const double* __restrict__ Mall, double* __restrict__ W, double* __restrict__ WT, int ld, int nb) {
+// W_ii = M_ii, WT_ii = M_ii^T for all diagonal blocks, zero elsewhere
+__global__ void inv_init_kernel(const double* __restrict__ Mall, double* __restrict__ W, double* __restrict__ WT, int ld) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)ld * ld) return;
     const int r = (int)(idx / ld), c = (int)(idx % ld);
     const int br = r / NB, bc = c / NB;
     double w = 0.0, wt = 0.0;
     if (br == bc) { w = Mall[(int64_t)br * NB * NB + (r % NB) * NB + (c % NB)]; wt = Mall[(int64_t)br * NB * NB + (c % NB) * NB + (r % NB)]; }
-    if (br <= bc) W[idx] = w;          // strictly-lower blocks of W are written by inv_w_kernel
-    if (br >= bc) WT[idx] = wt;        // strictly-upper blocks of WT likewise
-    (void)nb;
+    W[idx] = w;
+    WT[idx] = wt;
 }
 
 // Gradient of the log marginal likelihood w.r.t. theta = (log l, log noise) (sklearn _gpr.py log_marginal_likelihood,
@@ -260,9 +327,8 @@ extern "C" {
 
 int64_t mr_gp_fit_workspace_bytes(int32_t n_pad) {
     const int64_t n = n_pad, nb = n_pad / mr::NB;
-    // K/L, WT, per-block inverses M, ST scratch (nb blocks), y padded, tmp vector, info
-    // + per-CTA gradient partials
-    return (2 * n * n + nb * mr::NB * mr::NB * 2 + 2 * n + nb * (nb + 1)) * 8 + 64;
+    // K/L, WT, per-block inverses M, y padded, tmp vector, per-CTA gradient partials, info
+    return (2 * n * n + nb * mr::NB * mr::NB + 2 * n + nb * (nb + 1)) * 8 + 64;
 }
 
 int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n_pad, int32_t dim, double length_scale,
@@ -280,8 +346,7 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     double* K = (double*)workspace;                       // becomes L
     double* WT = K + (int64_t)ld * ld;
     double* Mall = WT + (int64_t)ld * ld;                 // [nb][128][128]
-    double* ST = Mall + (int64_t)nb * NB * NB;            // [nb][128][128]
-    double* ypad = ST + (int64_t)nb * NB * NB;            // [n_pad]
+    double* ypad = Mall + (int64_t)nb * NB * NB;          // [n_pad]
     double* tmp = ypad + n_pad;                           // [n_pad]
     double* partial = tmp + n_pad;                        // [nb (nb + 1) / 2][2]
     int* info = (int*)(partial + (int64_t)nb * (nb + 1));
@@ -294,15 +359,15 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     if (dim == 1) gp_build_k_kernel<1><<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(x_train, n_train, n_pad, length_scale, noise_level, jitter, x_scaled_out, K);
     else gp_build_k_kernel<2><<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(x_train, n_train, n_pad, length_scale, noise_level, jitter, x_scaled_out, K);
 
-    const size_t diag_smem = (size_t)NB * DIAG_LD * 8;
+    const size_t diag_smem = kDiagSmemBytes;
     cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem);
     cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
     cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
-    cudaFuncSetAttribute(inv_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+    cudaFuncSetAttribute(inv_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
     cudaFuncSetAttribute(inv_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
 
     for (int k = 0; k < nb; ++k) {
-        chol_diag_kernel<<<1, NB, diag_smem, s>>>(K, ld, k * NB, Mall + (int64_t)k * NB * NB, info);
+        chol_diag_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(K, ld, k * NB, Mall + (int64_t)k * NB * NB, info);
         const int r = nb - k - 1;
         if (r > 0) {
             chol_panel_kernel<<<r, 256, kDmmaSmemBytes, s>>>(K, ld, k, Mall + (int64_t)k * NB * NB, tmp);
@@ -311,10 +376,10 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     }
     // the strictly-upper blocks of K still hold kernel values: they are never read again (all products
     // touch blocks on or below the diagonal), and W / WT are initialised explicitly
-    inv_init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(Mall, W, WT, ld, nb);
-    for (int i = 1; i < nb; ++i) {
-        inv_s_kernel<<<i, 256, kDmmaSmemBytes, s>>>(K, WT, ld, i, ST);
-        inv_w_kernel<<<i, 256, kDmmaSmemBytes, s>>>(Mall + (int64_t)i * NB * NB, ST, W, WT, ld, i);
+    inv_init_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(Mall, W, WT, ld);
+    for (int c = 0; c < nb; ++c) {
+        if (c > 0) inv_w_kernel<<<c, 256, kDmmaSmemBytes, s>>>(Mall + (int64_t)c * NB * NB, W, WT, ld, c);
+        if (c + 1 < nb) inv_acc_kernel<<<(nb - c - 1) * (c + 1), 256, kDmmaSmemBytes, s>>>(K, WT, ld, c);
     }
     const unsigned mv_blocks = (unsigned)(((int64_t)n_pad * 32 + 255) / 256);
     matvec_kernel<<<mv_blocks, 256, 0, s>>>(W, ld, n_pad, ypad, tmp);            // tmp = W y = L^-1 y
