@@ -18,6 +18,7 @@
  *   mr_gp_correct_heading <- LearningModule.predict's minimize_scalar(objective, 'Bounded')
  *                       (Learning_module.py:215, utils.py:194-196)
  *   mr_actor_forward <- ActorNetwork.predict    (RL/MR_ddpg.py:124-149)
+ *   mr_ddpg_update, mr_replay_add, mr_ou_noise_add <- the learner of RL/MR_ddpg.py (:16-78, :163-231, :285-305)
  *   mr_gp_fit        <- GaussianProcessRegressor.fit at given hyper-parameters: K, cholesky, alpha_, L^-1,
  *                       log marginal likelihood  (Learning_module.py:122-123; the optimiser stays on the host)
  *
@@ -236,6 +237,63 @@ int32_t mr_actor_param_count(void);
 /* obs is [5][obs_row_stride] (storage dtype), actions out is [n][2] (storage dtype). */
 int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
                      const double action_high[2], void* actions, void* stream);
+
+/* ---- DDPG learner (RL/MR_ddpg.py:16-78,80-231,285-305) ---------------------------
+ * Packed float32 critic parameters (input-major matrices), mr_critic_param_count() floats:
+ *   wc1[5][64] bc1[64] gamma[64] beta[64] mean[64] var[64]  t1[64][32] t1b[32] (unused, as in the reference)
+ *   t2[2][32] t2b[32]  wo[32] bo[1]
+ * The learner state is eight parameter-sized device arrays plus two gradient scratch arrays; the replay ring is
+ * five row-major float32 arrays of `capacity` rows.  The caller owns head / count / Adam's step number. */
+typedef struct mr_ddpg_state {
+    float* actor;          /* [mr_actor_param_count()]  online actor  (ActorNetwork.network_params)        */
+    float* actor_target;   /*                            target actor  (:93-103)                             */
+    float* critic;         /* [mr_critic_param_count()] online critic (CriticNetwork.network_params)       */
+    float* critic_target;
+    float* adam_actor_m;   /* Adam first / second moments, same layouts                                      */
+    float* adam_actor_v;
+    float* adam_critic_m;
+    float* adam_critic_v;
+    float* grad_actor;     /* scratch, same layouts                                                          */
+    float* grad_critic;
+} mr_ddpg_state;
+
+typedef struct mr_replay {
+    float* s;              /* [capacity][5]  state                    (ReplayBuffer.add, :27-35)            */
+    float* a;              /* [capacity][2]  action                                                          */
+    float* r;              /* [capacity]     reward                                                          */
+    float* d;              /* [capacity]     terminal flag as 0 / 1                                          */
+    float* s2;             /* [capacity][5]  next state                                                      */
+    int64_t capacity;
+} mr_replay;
+
+typedef struct mr_ddpg_hyper {
+    double gamma, tau, lr_actor, lr_critic;     /* 0.99, 0.001, 0.001, 0.01   (RL/MR_ddpg.py:337-341)        */
+    double action_bound[2];                      /* env.action_space.high                                     */
+    double adam_beta1, adam_beta2, adam_eps;     /* TF1 AdamOptimizer defaults 0.9, 0.999, 1e-8               */
+} mr_ddpg_hyper;
+
+int32_t mr_critic_param_count(void);
+
+/* ReplayBuffer.add for the n transitions of one vectorised env step: transition i goes to ring slot
+ * (head + i) % capacity.  obs / obs_next are SoA rows [5][row_stride], actions [n][2], rew [n] (storage dtype),
+ * done [n] bytes.  The caller advances head by n (mod capacity) and count to min(count + n, capacity). */
+int mr_replay_add(const mr_replay* rb, int64_t head, const void* obs, int64_t obs_row_stride, const void* actions,
+                  const void* rew, const uint8_t* done, const void* obs_next, int64_t obs_next_row_stride, int64_t n,
+                  int32_t dtype, void* stream);
+
+/* OUNoise.__call__ (:67-71) for n envs: ou_state [n][2] float64 is advanced by one step with Philox normals keyed by
+ * (seed; env_base + i, counter) and added to actions [n][2] in place; envs with reset_mask[i] != 0 (may be NULL)
+ * restart from 0 first (OUNoise.reset). */
+int mr_ou_noise_add(double* ou_state, void* actions, const uint8_t* reset_mask, int64_t n, int32_t dtype, double theta, double mu,
+                    double sigma, double dt, uint64_t seed, uint64_t counter, uint64_t env_base, void* stream);
+
+/* One pass of the reference's update block (:285-305) in ONE launch: minibatch (rows `indices[batch]`, or if NULL a
+ * uniform sample without replacement from the first `count` ring rows, Philox keyed by (seed; update_index)),
+ * y = r + gamma Q'(s2, mu'(s2)) (1 - done), critic MSE step (Adam), dQ/da at mu(s) under the updated critic, actor
+ * step (Adam on d scaled_out/d theta . (-dQ/da) / batch), soft target updates.  update_index = 1, 2, ... is Adam's
+ * step count.  info_out (2 floats, may be NULL): critic loss and mean Q before the update. */
+int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
+                   uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, float* info_out, void* stream);
 
 #ifdef __cplusplus
 }

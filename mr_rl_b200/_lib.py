@@ -63,11 +63,27 @@ class GPModel(C.Structure):
                 ("length_scale", C.c_double), ("noise_level", C.c_double)]
 
 
+class DDPGState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("actor", "actor_target", "critic", "critic_target", "adam_actor_m", "adam_actor_v",
+                                          "adam_critic_m", "adam_critic_v", "grad_actor", "grad_critic")]
+
+
+class Replay(C.Structure):
+    _fields_ = [("s", C.c_void_p), ("a", C.c_void_p), ("r", C.c_void_p), ("d", C.c_void_p), ("s2", C.c_void_p),
+                ("capacity", C.c_int64)]
+
+
+class DDPGHyper(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("tau", C.c_double), ("lr_actor", C.c_double), ("lr_critic", C.c_double),
+                ("action_bound", C.c_double * 2), ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double)]
+
+
 GP_PAD = 128
 
 
 EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time_table_host", "mr_env_reset",
            "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_gp_fit", "mr_gp_fit_workspace_bytes", "mr_actor_param_count",
+           "mr_critic_param_count", "mr_replay_add", "mr_ou_noise_add", "mr_ddpg_update",
            "mr_actor_forward")
 
 _lib = None
@@ -109,6 +125,16 @@ def load():
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_void_p]
     lib.mr_gp_fit.restype = C.c_int
+    lib.mr_critic_param_count.restype = C.c_int32
+    lib.mr_replay_add.argtypes = [P(Replay), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.mr_replay_add.restype = C.c_int
+    lib.mr_ou_noise_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.mr_ou_noise_add.restype = C.c_int
+    lib.mr_ddpg_update.argtypes = [P(DDPGState), P(Replay), C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64,
+                                   P(DDPGHyper), C.c_void_p, C.c_void_p]
+    lib.mr_ddpg_update.restype = C.c_int
     lib.mr_gp_fit_workspace_bytes.argtypes = [C.c_int32]
     lib.mr_gp_fit_workspace_bytes.restype = C.c_int64
     lib.mr_gp_workspace_bytes.argtypes = [P(GPModel), C.c_int64, C.c_int32]

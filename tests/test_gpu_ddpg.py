@@ -1,0 +1,167 @@
+"""DDPG learner on the device (csrc/mr_ddpg.cu, mr_rl_b200/ddpg.py) against the torch restatement of the reference's
+TensorFlow graph (oracle/ddpg_oracle.py — parity unpinned: no TensorFlow here).  fp32 on both sides; the tolerances
+below are fp32 summation-order noise after a few Adam steps."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BOUND = (20.0, 2 * math.pi)
+
+
+def make_pair(seed=0, **kw):
+    from mr_rl_b200.actor import init_actor
+    from mr_rl_b200.ddpg import DDPGLearner, init_critic
+    from oracle.ddpg_oracle import DDPGOracle
+    a, c, at, ct = init_actor(seed), init_critic(seed + 1), init_actor(seed + 2), init_critic(seed + 3)
+    dev = DDPGLearner(a, c, BOUND, actor_target_init=at, critic_target_init=ct, device="cuda:0", **kw)
+    ref = DDPGOracle(a, c, at, ct, BOUND, **kw)
+    return dev, ref
+
+
+def fill_replay(n, seed=0):
+    from mr_rl_b200.ddpg import ReplayBuffer
+    g = torch.Generator().manual_seed(seed)
+    rb = ReplayBuffer(n, 0, device="cuda:0")
+    xy = (torch.rand(n, 2, generator=g) * 2 - 1) * 80
+    s = torch.cat([xy, torch.zeros(n, 2), xy.norm(dim=1, keepdim=True)], 1)
+    a = torch.rand(n, 2, generator=g) * torch.tensor(BOUND)
+    xy2 = xy + torch.randn(n, 2, generator=g)
+    s2 = torch.cat([xy2, torch.zeros(n, 2), xy2.norm(dim=1, keepdim=True)], 1)
+    r = torch.where(torch.rand(n, generator=g) < 0.2, torch.tensor(-50.0), torch.tensor(10.0))
+    d = (torch.rand(n, generator=g) < 0.15).float()
+    for dst, src in ((rb.s, s), (rb.a, a), (rb.r, r), (rb.d, d), (rb.s2, s2)):
+        dst.copy_(src)
+    rb.count = n
+    return rb, (s, a, r, d, s2)
+
+
+def assert_params_close(dev, ref, atol=3e-6, rtol=2e-4):
+    for name, got, want in (("actor", dev.actor_params(), ref.actor), ("actor_t", dev.actor_params(True), ref.actor_t),
+                            ("critic", dev.critic_params(), ref.critic), ("critic_t", dev.critic_params(True), ref.critic_t)):
+        for k, w in want.items():
+            g = got[k]
+            assert torch.allclose(g, w.reshape(g.shape).float(), atol=atol, rtol=rtol), \
+                f"{name}.{k}: max abs diff {float((g - w.reshape(g.shape)).abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("batch", [64, 50, 256])
+def test_update_matches_torch_restatement(batch):
+    dev, ref = make_pair(0)
+    rb, (s, a, r, d, s2) = fill_replay(1000, seed=batch)
+    g = torch.Generator().manual_seed(5)
+    for it in range(6):
+        idx = torch.randperm(1000, generator=g)[:batch]
+        info = dev.update(rb, indices=idx.cuda()).cpu()
+        loss, qm = ref.update(s[idx], a[idx], r[idx], d[idx], s2[idx])
+        assert abs(float(info[0]) - loss) <= 1e-4 * abs(loss) + 1e-5, (it, float(info[0]), loss)
+        assert abs(float(info[1]) - qm) <= 1e-4 * abs(qm) + 1e-5
+    assert_params_close(dev, ref)
+    # the unused t1 bias never moves, the moving statistics stay frozen
+    assert torch.all(dev.critic_params()["t1b"] == 0) and torch.all(dev.critic_params()["vc"] == 1)
+    assert torch.all(dev.actor_params()["m1"] == 0) and torch.all(dev.actor_params()["v2"] == 1)
+
+
+def test_targets_start_from_the_soft_update_of_independent_inits():
+    dev, ref = make_pair(3)
+    assert_params_close(dev, ref, atol=1e-7, rtol=1e-6)
+    assert not torch.allclose(dev.actor_params()["w2"], dev.actor_params(True)["w2"])
+
+
+def test_internal_sampling_without_replacement_and_determinism():
+    from mr_rl_b200.ddpg import DDPGLearner
+    # count == batch: a sample without replacement is the whole buffer -> equals the explicit full batch
+    rb, _ = fill_replay(128, seed=1)
+    a, _ = make_pair(1)
+    b, _ = make_pair(1)
+    ia = a.update(rb, 128).clone()
+    ib = b.update(rb, indices=torch.arange(128)).clone()
+    assert torch.allclose(ia, ib, rtol=1e-5, atol=1e-6)
+    for k, v in a.critic_params().items():
+        assert torch.allclose(v, b.critic_params()[k], atol=2e-6, rtol=1e-4), k
+    # same seed and update index -> same minibatch; the next update draws another one
+    rb, _ = fill_replay(5000, seed=2)
+    c, _ = make_pair(2)
+    e, _ = make_pair(2)
+    i1, i2 = c.update(rb, 64).clone(), e.update(rb, 64).clone()
+    assert torch.equal(i1, i2) and torch.equal(c.critic, e.critic)
+    i3 = c.update(rb, 64).clone()
+    assert not torch.equal(i1, i3)
+
+
+def test_update_argument_errors():
+    from mr_rl_b200 import _lib as L
+    dev, _ = make_pair(0)
+    rb, _ = fill_replay(100)
+    rb.count = 10
+    with pytest.raises(L.MRLibraryError, match="min_batch|count"):
+        dev.update(rb, 64)
+    assert dev.updates == 0
+    rb.count = 100
+    with pytest.raises(L.MRLibraryError, match="batch"):
+        dev.update(rb, 0)
+
+
+def test_replay_ring_add_wraps_like_the_deque():
+    from mr_rl_b200.ddpg import ReplayBuffer
+    rb = ReplayBuffer(8, device="cuda:0")
+    stride = 256
+    for step in range(3):                                   # 3 x 3 transitions into 8 slots: the oldest one is dropped
+        obs = torch.zeros(5, stride, dtype=torch.float64, device="cuda:0")
+        obs2 = torch.zeros(5, stride, dtype=torch.float64, device="cuda:0")
+        for k in range(5):
+            obs[k, :3] = torch.arange(3, device="cuda:0") + 10 * step + 100 * k
+            obs2[k, :3] = obs[k, :3] + 0.5
+        act = (torch.arange(6, dtype=torch.float64, device="cuda:0").reshape(3, 2) + step)
+        rew = torch.full((3,), float(step), dtype=torch.float64, device="cuda:0")
+        done = torch.tensor([0, 1, 0], dtype=torch.uint8, device="cuda:0")
+        rb.add(obs, act, rew, done, obs2, 3)
+    assert rb.size() == 8 and rb.head == 1
+    s = rb.s.cpu()
+    # slot 0 was overwritten by the last transition of step 2; slots 1, 2 still hold step 0's transitions 1, 2
+    assert s[0].tolist() == [22.0, 122.0, 222.0, 322.0, 422.0]
+    assert s[1].tolist() == [1.0, 101.0, 201.0, 301.0, 401.0]
+    assert s[6].tolist() == [20.0, 120.0, 220.0, 320.0, 420.0]
+    assert rb.s2.cpu()[7, 0] == 21.5 and rb.r.cpu()[7] == 2.0 and rb.d.cpu().tolist()[6:8] == [0.0, 1.0]
+    assert rb.a.cpu()[0].tolist() == [6.0, 7.0]
+
+
+def test_ou_noise_follows_the_reference_recurrence():
+    from mr_rl_b200.ddpg import OUNoise
+    n = 200_000
+    ou = OUNoise(n, sigma=0.3, theta=0.15, dt=1e-2, seed=4, device="cuda:0")
+    act = torch.zeros(n, 2, dtype=torch.float64, device="cuda:0")
+    ou.add_to(act)
+    x1 = ou.x_prev.clone()
+    assert torch.equal(act, x1)                                              # x0 = 0: the first sample is sigma sqrt(dt) z
+    z = x1 / (0.3 * math.sqrt(1e-2))
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1) < 0.01
+    assert abs(float((z[:, 0] * z[:, 1]).mean())) < 0.01
+    base = torch.ones(n, 2, dtype=torch.float32, device="cuda:0")
+    ou.add_to(base)
+    incr = (ou.x_prev - (x1 + 0.15 * (0.0 - x1) * 1e-2)) / (0.3 * math.sqrt(1e-2))   # the second normal draw
+    assert abs(float(incr.std()) - 1) < 0.01 and abs(float((incr * z).mean())) < 0.01
+    assert torch.allclose(base.double(), 1 + ou.x_prev, atol=1e-6)
+    ou2 = OUNoise(n, seed=4, device="cuda:0")
+    act2 = torch.zeros(n, 2, dtype=torch.float64, device="cuda:0")
+    ou2.add_to(act2)
+    assert torch.equal(act2, x1)
+
+
+def test_vectorised_training_loop_runs_and_learns_something():
+    from mr_rl_b200 import VecMREnv
+    from mr_rl_b200.ddpg import DDPGLearner, OUNoise, ReplayBuffer, train
+    env = VecMREnv(256, device="cuda:0", noise="philox", seed=0, auto_reset=True)
+    learner = DDPGLearner(device="cuda:0", seed=0)
+    before = learner.actor.clone()
+    rb = ReplayBuffer(10000, 0, device="cuda:0")
+    log = train(env, learner, OUNoise(256, device="cuda:0"), min_batch=64, steps=40, replay=rb)
+    assert log.shape == (40, 3) and np.isfinite(log).all()
+    assert rb.size() == 10000 and learner.updates == 40
+    assert not torch.equal(before, learner.actor) and torch.isfinite(learner.actor).all() and torch.isfinite(learner.critic).all()
+    # the critic learns the scale of the returns: its loss drops from the first updates
+    assert log[-5:, 1].mean() < log[:5, 1].mean()
+    env.check_status()
