@@ -4,7 +4,8 @@ Public surface (mirrors the reference's names):
     VecMREnv                      batched device env (reset / step / rollout)
     MR_Env, Simulator             single-env façades with the reference's class surface
     run_sim                       utils.run_sim as one fused rollout launch
-    LearningModule, DeviceGP      GP disturbance model with inference on the device
+    LearningModule, DeviceGP, DeviceGPR   GP disturbance model: fit, inference and heading correction on the device
+    DDPGLearner, ReplayBuffer, OUNoise, ddpg.train   the DDPG learner of RL/MR_ddpg.py on the device
     init_actor / pack_actor / actor_forward   DDPG actor forward for the in-loop policy
     experiment_dict / save_experiment          recorded rollouts in the reference's MRExperiment pickle layout
 
@@ -13,7 +14,9 @@ there is no CPU fallback (importing is cheap, the first compute call loads the l
 """
 from ._lib import MRLibraryError, load as load_library  # noqa: F401
 from .actor import actor_forward, init_actor, pack_actor  # noqa: F401
+from .ddpg import DDPGLearner, OUNoise, ReplayBuffer  # noqa: F401
 from .gp import DeviceGP  # noqa: F401
+from .gpr import DeviceGPR  # noqa: F401
 from .learning_module import LearningModule  # noqa: F401
 from .mr_env import MR_Env, Simulator  # noqa: F401
 from .recording import MRExperiment, experiment_dict, load_experiment, save_experiment  # noqa: F401

@@ -1,6 +1,6 @@
 """DDPG actor forward (RL/MR_ddpg.py:124-149) on the device: 5 -> FC64 -> BN -> ReLU -> FC64 -> BN
--> ReLU -> FC2 tanh -> * action_bound, fp32.  Only the acting path is in scope (the in-loop policy
-of the fused rollout); training, critic and replay are not part of the env hot path."""
+-> ReLU -> FC2 tanh -> * action_bound, fp32: the acting path (the in-loop policy of the fused rollout).
+Training, critic and replay live in ddpg.py."""
 from __future__ import annotations
 
 import ctypes as C

@@ -4,7 +4,7 @@
 //
 // The networks are tiny (5-64-64-2 and 5-64-(+2)-32-1) and the reference batch is 64, so an update is latency
 // bound, not throughput bound: one CTA keeps a 64-sample tile of every activation in shared memory and walks
-// the phases with CTA barriers; weights stay in L1/L2 (29 KB for all four networks).  Larger batches loop over
+// the phases with CTA barriers; the networks a phase reads are staged in shared memory (44 KB).  Larger batches loop over
 // 64-sample tiles and accumulate the weight gradients.  fp32 throughout, like the reference's TensorFlow graph.
 //
 // Batch norm: the reference never switches tflearn into training mode, so batch_normalization is the inference
@@ -35,6 +35,10 @@ constexpr int kCriticParams = kC_Bo + 1;                    // 2849 floats
 constexpr int kTile = 64;                                   // samples per shared-memory tile
 constexpr int kLd64 = 65, kLd32 = 33;                       // padded rows: lanes over samples hit distinct banks
 constexpr int kMaxBatch = 4096;
+#ifndef MR_DDPG_THREADS
+#define MR_DDPG_THREADS 1024                                // one CTA; the phases are short loops over <= 4160 work items
+#endif
+constexpr int kDdpgThreads = MR_DDPG_THREADS;
 
 struct DdpgHyper { float gamma, tau, lr_actor, lr_critic, bound0, bound1, beta1, beta2, eps; };
 
@@ -44,9 +48,17 @@ struct DdpgSmem {
     float Z1[kTile * kLd64], H1[kTile * kLd64], Z2[kTile * kLd64], H2[kTile * kLd64];
     float ZC[kTile * kLd64], C1[kTile * kLd64], G1[kTile * kLd64], G2[kTile * kLd64];
     float C2[kTile * kLd32], GC2[kTile * kLd32];
-    float red[256];
+    // the networks the current phase reads: L2 latency on every weight would otherwise dominate these short loops
+    float wA[kActorParams + 2];                  // target actor (critic phase), then the online actor
+    float wC[kCriticParams + 3];                 // online critic (kept in step with Adam's writes)
+    float wCt[kCriticParams + 3];                // target critic
     int idx[kMaxBatch];
 };
+
+__device__ void load_weights(float* dst, const float* src, int n) {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+}
 
 // ---- dense layers on shared-memory tiles; every helper is called by the whole CTA and ends with a barrier ----------
 // (weight pointers are deliberately NOT __restrict__/read-only here: Adam rewrites them between phases of one launch)
@@ -155,7 +167,7 @@ __device__ void critic_fwd_tile(DdpgSmem& sm, const float* X, const float* Act, 
 }
 
 // TF1 AdamOptimizer: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t);  theta -= lr_t m / (sqrt(v) + eps)
-__device__ void adam_step(float* p, const float* g, float* m, float* v, int n,
+__device__ void adam_step(float* p, float* p_smem, const float* g, float* m, float* v, int n,
                           int frozen_lo0, int frozen_hi0, int frozen_lo1, int frozen_hi1, float lr_t, const DdpgHyper& h) {
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         if ((k >= frozen_lo0 && k < frozen_hi0) || (k >= frozen_lo1 && k < frozen_hi1)) continue;
@@ -163,7 +175,9 @@ __device__ void adam_step(float* p, const float* g, float* m, float* v, int n,
         const float mk = h.beta1 * m[k] + (1.f - h.beta1) * gk;
         const float vk = h.beta2 * v[k] + (1.f - h.beta2) * gk * gk;
         m[k] = mk; v[k] = vk;
-        p[k] -= lr_t * mk / (sqrtf(vk) + h.eps);
+        const float pk = p[k] - lr_t * mk / (sqrtf(vk) + h.eps);
+        p[k] = pk;
+        if (p_smem) p_smem[k] = pk;
     }
     __syncthreads();
 }
@@ -181,7 +195,7 @@ __device__ void gather_tile(DdpgSmem& sm, int t0, int nb, const float* rs, const
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kDdpgThreads, 1)
 ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float* __restrict__ critic, float* __restrict__ critic_t,
                    float* __restrict__ am, float* __restrict__ av, float* __restrict__ cm, float* __restrict__ cv,
                    float* __restrict__ ga, float* __restrict__ gc,
@@ -197,21 +211,29 @@ ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float
     //      algorithm, one warp, Philox keyed by (seed; update index, draw)
     if (indices) {
         for (int k = tid; k < batch; k += blockDim.x) sm.idx[k] = (int)indices[k];
-    } else if (tid < 32) {
-        for (int t = 0; t < batch; ++t) {
-            const int64_t j = count - batch + t;
+    } else {
+        for (int t = tid; t < batch; t += blockDim.x) {       // all draws in parallel, then one warp resolves collisions
             uint32_t o0, o1, o2, o3;
             philox4x32_10((uint32_t)t | (4u << 28), (uint32_t)update_index, (uint32_t)(update_index >> 32), 0u, keys.rk, o0, o1, o2, o3);
-            int cand = (int)(((uint64_t)o0 * (uint64_t)(j + 1)) >> 32);           // uniform in [0, j]
-            bool hit = false;
-            for (int k = tid; k < t; k += 32) hit |= sm.idx[k] == cand;
-            if (__any_sync(0xffffffffu, hit)) cand = (int)j;
-            if (tid == 0) sm.idx[t] = cand;
-            __syncwarp();
+            const int64_t j = count - batch + t;
+            sm.idx[t] = (int)(((uint64_t)o0 * (uint64_t)(j + 1)) >> 32);          // uniform in [0, j]
+        }
+        __syncthreads();
+        if (tid < 32) {
+            for (int t = 0; t < batch; ++t) {
+                const int cand = sm.idx[t];
+                bool hit = false;
+                for (int k = tid; k < t; k += 32) hit |= sm.idx[k] == cand;
+                if (__any_sync(0xffffffffu, hit) && tid == 0) sm.idx[t] = (int)(count - batch + t);
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
 
+    load_weights(sm.wA, actor_t, kActorParams);
+    load_weights(sm.wCt, critic_t, kCriticParams);
+    load_weights(sm.wC, critic, kCriticParams);
     const float inv_b = 1.0f / (float)batch;
     float loss_acc = 0.f, q_acc = 0.f;                         // thread 0 only
     const int n_tiles = (batch + kTile - 1) / kTile;
@@ -221,11 +243,11 @@ ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float
         const int nb = min(kTile, batch - t * kTile);
         const bool acc = t > 0;
         gather_tile(sm, t * kTile, nb, rs, ra, rr, rd, rs2);
-        actor_fwd_tile(sm, sm.S2, nb, actor_t, h.bound0, h.bound1, sm.A2);
-        critic_fwd_tile(sm, sm.S2, sm.A2, nb, critic_t, sm.Q);
+        actor_fwd_tile(sm, sm.S2, nb, sm.wA, h.bound0, h.bound1, sm.A2);
+        critic_fwd_tile(sm, sm.S2, sm.A2, nb, sm.wCt, sm.Q);
         for (int s = tid; s < nb; s += blockDim.x) sm.Y[s] = sm.R[s] + h.gamma * sm.Q[s] * (1.f - sm.D[s]);
         __syncthreads();
-        critic_fwd_tile(sm, sm.S, sm.A, nb, critic, sm.Q);
+        critic_fwd_tile(sm, sm.S, sm.A, nb, sm.wC, sm.Q);
         for (int s = tid; s < nb; s += blockDim.x) sm.DQ[s] = 2.f * (sm.Q[s] - sm.Y[s]) * inv_b;
         __syncthreads();
         if (tid == 0) for (int s = 0; s < nb; ++s) { const float e = sm.Y[s] - sm.Q[s]; loss_acc += e * e; q_acc += sm.Q[s]; }
@@ -239,13 +261,13 @@ ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float
         }
         for (int e = tid; e < nb * 32; e += blockDim.x) {
             const int s = e >> 5, j = e & 31;
-            sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? sm.DQ[s] * critic[kC_Wo + j] : 0.f;
+            sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? sm.DQ[s] * sm.wC[kC_Wo + j] : 0.f;
         }
         __syncthreads();
         fc_bwd_w(sm.C1, kLd64, sm.GC2, kLd32, nb, 64, 32, gc + kC_T1, nullptr, acc);          // t1.b: no gradient
         fc_bwd_w(sm.A, 2, sm.GC2, kLd32, nb, 2, 32, gc + kC_T2, gc + kC_T2b, acc);
-        fc_bwd_x(sm.GC2, kLd32, nb, 32, critic + kC_T1, 64, sm.G1, kLd64);
-        bn_relu_bwd(sm.G1, sm.ZC, sm.C1, nb, critic + kC_Gc, critic + kC_Mc, critic + kC_Vc, gc + kC_Gc, gc + kC_Bec, acc);
+        fc_bwd_x(sm.GC2, kLd32, nb, 32, sm.wC + kC_T1, 64, sm.G1, kLd64);
+        bn_relu_bwd(sm.G1, sm.ZC, sm.C1, nb, sm.wC + kC_Gc, sm.wC + kC_Mc, sm.wC + kC_Vc, gc + kC_Gc, gc + kC_Bec, acc);
         fc_bwd_w(sm.S, 5, sm.G1, kLd64, nb, 5, 64, gc + kC_Wc1, gc + kC_Bc1, acc);
     }
     if (tid < 32) gc[kC_T1b + tid] = 0.f;
@@ -253,39 +275,40 @@ ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float
     {
         const float t = (float)update_index;
         const float lr_t = h.lr_critic * sqrtf(1.f - powf(h.beta2, t)) / (1.f - powf(h.beta1, t));
-        adam_step(critic, gc, cm, cv, kCriticParams, kC_Mc, kC_T1, 0, 0, lr_t, h);
+        adam_step(critic, sm.wC, gc, cm, cv, kCriticParams, kC_Mc, kC_T1, 0, 0, lr_t, h);
     }
+    load_weights(sm.wA, actor, kActorParams);
 
     // ---- actor: ascend Q(s, mu(s)) through the UPDATED critic; gradient = d scaled_out / d theta . (-dQ/da) / batch ------
     for (int t = 0; t < n_tiles; ++t) {
         const int nb = min(kTile, batch - t * kTile);
         const bool acc = t > 0;
         gather_tile(sm, t * kTile, nb, rs, ra, rr, rd, rs2);
-        actor_fwd_tile(sm, sm.S, nb, actor, h.bound0, h.bound1, sm.A2);          // sm.T keeps tanh(u)
-        critic_fwd_tile(sm, sm.S, sm.A2, nb, critic, nullptr);
+        actor_fwd_tile(sm, sm.S, nb, sm.wA, h.bound0, h.bound1, sm.A2);          // sm.T keeps tanh(u)
+        critic_fwd_tile(sm, sm.S, sm.A2, nb, sm.wC, nullptr);
         for (int e = tid; e < nb * 32; e += blockDim.x) {
             const int s = e >> 5, j = e & 31;
-            sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? critic[kC_Wo + j] : 0.f;
+            sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? sm.wC[kC_Wo + j] : 0.f;
         }
         __syncthreads();
-        fc_bwd_x(sm.GC2, kLd32, nb, 32, critic + kC_T2, 2, sm.DU, 2);            // dQ/da
+        fc_bwd_x(sm.GC2, kLd32, nb, 32, sm.wC + kC_T2, 2, sm.DU, 2);             // dQ/da
         for (int e = tid; e < nb * 2; e += blockDim.x) {
             const float th = sm.T[e];
             sm.DU[e] = -sm.DU[e] * inv_b * ((e & 1) ? h.bound1 : h.bound0) * (1.f - th * th);
         }
         __syncthreads();
         fc_bwd_w(sm.H2, kLd64, sm.DU, 2, nb, 64, 2, ga + kOffW3, ga + kOffB3, acc);
-        fc_bwd_x(sm.DU, 2, nb, 2, actor + kOffW3, 64, sm.G2, kLd64);
-        bn_relu_bwd(sm.G2, sm.Z2, sm.H2, nb, actor + kOffG2, actor + kOffM2, actor + kOffV2, ga + kOffG2, ga + kOffBe2, acc);
+        fc_bwd_x(sm.DU, 2, nb, 2, sm.wA + kOffW3, 64, sm.G2, kLd64);
+        bn_relu_bwd(sm.G2, sm.Z2, sm.H2, nb, sm.wA + kOffG2, sm.wA + kOffM2, sm.wA + kOffV2, ga + kOffG2, ga + kOffBe2, acc);
         fc_bwd_w(sm.H1, kLd64, sm.G2, kLd64, nb, 64, 64, ga + kOffW2, ga + kOffB2, acc);
-        fc_bwd_x(sm.G2, kLd64, nb, 64, actor + kOffW2, 64, sm.G1, kLd64);
-        bn_relu_bwd(sm.G1, sm.Z1, sm.H1, nb, actor + kOffG1, actor + kOffM1, actor + kOffV1, ga + kOffG1, ga + kOffBe1, acc);
+        fc_bwd_x(sm.G2, kLd64, nb, 64, sm.wA + kOffW2, 64, sm.G1, kLd64);
+        bn_relu_bwd(sm.G1, sm.Z1, sm.H1, nb, sm.wA + kOffG1, sm.wA + kOffM1, sm.wA + kOffV1, ga + kOffG1, ga + kOffBe1, acc);
         fc_bwd_w(sm.S, 5, sm.G1, kLd64, nb, 5, 64, ga + kOffW1, ga + kOffB1, acc);
     }
     {
         const float t = (float)update_index;
         const float lr_t = h.lr_actor * sqrtf(1.f - powf(h.beta2, t)) / (1.f - powf(h.beta1, t));
-        adam_step(actor, ga, am, av, kActorParams, kOffM1, kOffW2, kOffM2, kOffW3, lr_t, h);
+        adam_step(actor, nullptr, ga, am, av, kActorParams, kOffM1, kOffW2, kOffM2, kOffW3, lr_t, h);
     }
 
     // ---- soft target updates over the trainable variables (:98-103, :183-188) -----------------------------------------------
@@ -410,7 +433,7 @@ int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, 
         cudaFuncSetAttribute(ddpg_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DdpgSmem));
         attr[dev] = true;
     }
-    ddpg_update_kernel<<<1, 256, sizeof(DdpgSmem), (cudaStream_t)stream>>>(
+    ddpg_update_kernel<<<1, kDdpgThreads, sizeof(DdpgSmem), (cudaStream_t)stream>>>(
         st->actor, st->actor_target, st->critic, st->critic_target, st->adam_actor_m, st->adam_actor_v, st->adam_critic_m,
         st->adam_critic_v, st->grad_actor, st->grad_critic, rb->s, rb->a, rb->r, rb->d, rb->s2, count, batch, indices, keys,
         (uint64_t)update_index, h, info_out);
