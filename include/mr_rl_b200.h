@@ -19,6 +19,7 @@
  *                       (Learning_module.py:215, utils.py:194-196)
  *   mr_actor_forward <- ActorNetwork.predict    (RL/MR_ddpg.py:124-149)
  *   mr_ddpg_update, mr_replay_add, mr_ou_noise_add <- the learner of RL/MR_ddpg.py (:16-78, :163-231, :285-305)
+ *   mr_learn_preprocess <- LearningModule.estimateDisturbance / learn up to the fit (Learning_module.py:46-59, :63-120)
  *   mr_gp_fit        <- GaussianProcessRegressor.fit at given hyper-parameters: K, cholesky, alpha_, L^-1,
  *                       log marginal likelihood  (Learning_module.py:122-123; the optimiser stays on the host)
  *
@@ -237,6 +238,19 @@ int32_t mr_actor_param_count(void);
 /* obs is [5][obs_row_stride] (storage dtype), actions out is [n][2] (storage dtype). */
 int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
                      const double action_high[2], void* actions, void* stream);
+
+/* LearningModule.estimateDisturbance / learn up to the GPR fit (Learning_module.py:46-59, :63-120) for a trajectory
+ * px, py, time [n] already in HBM: uniform_filter1d(N, nearest) -> np.gradient(., time) -> uniform_filter1d(N/2)
+ * gives vx_out, vy_out [n]; scalars_out[0..1] = mean of vx, vy over [N, n-N) (the drift estimate Dx, Dy).
+ * With alpha_sim != NULL (learn): frames [N, n_valid-N) of the controller-on part (n_valid = n, or the cut the caller
+ * derived from alpha >= 500) give a0 = median(speed / freq) -> scalars_out[2], the sample count m -> scalars_out[3],
+ * x_out = alpha_sim, yx_out / yy_out = vx - a0 freq cos(alpha) / vy - a0 freq sin(alpha), m entries each — the
+ * inputs of mr_gp_fit.  subtract_t0 shifts the clock like learn() does (:70).  workspace: mr_learn_workspace_bytes(n). */
+int mr_learn_preprocess(const double* px, const double* py, const double* time, int32_t n, int32_t filter_n, int32_t subtract_t0,
+                        double drift_x, double drift_y, const double* alpha_sim, double freq, int32_t n_valid, double* vx_out,
+                        double* vy_out, double* x_out, double* yx_out, double* yy_out, double* scalars_out, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+int64_t mr_learn_workspace_bytes(int32_t n);
 
 /* ---- DDPG learner (RL/MR_ddpg.py:16-78,80-231,285-305) ---------------------------
  * Packed float32 critic parameters (input-major matrices), mr_critic_param_count() floats:

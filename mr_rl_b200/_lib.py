@@ -83,7 +83,8 @@ GP_PAD = 128
 
 EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time_table_host", "mr_env_reset",
            "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_gp_fit", "mr_gp_fit_workspace_bytes", "mr_actor_param_count",
-           "mr_critic_param_count", "mr_replay_add", "mr_ou_noise_add", "mr_ddpg_update",
+           "mr_critic_param_count", "mr_replay_add", "mr_ou_noise_add", "mr_ddpg_update", "mr_learn_preprocess",
+           "mr_learn_workspace_bytes",
            "mr_actor_forward")
 
 _lib = None
@@ -125,6 +126,12 @@ def load():
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_void_p]
     lib.mr_gp_fit.restype = C.c_int
+    lib.mr_learn_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                        C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mr_learn_preprocess.restype = C.c_int
+    lib.mr_learn_workspace_bytes.argtypes = [C.c_int32]
+    lib.mr_learn_workspace_bytes.restype = C.c_int64
     lib.mr_critic_param_count.restype = C.c_int32
     lib.mr_replay_add.argtypes = [P(Replay), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_int64, C.c_int32, C.c_void_p]

@@ -79,12 +79,17 @@ class DeviceGPR:
     def fit(self, X, y):
         import torch
         from sklearn.utils import check_random_state
-        X = np.asarray(X, dtype=np.float64)
-        X = X.reshape(len(X), -1)
-        y = np.asarray(y, dtype=np.float64).ravel()
+        if torch.is_tensor(X):                                   # already in HBM (mr_learn_preprocess): no round trip
+            self._Xd = X.to(device=self.device, dtype=torch.float64).reshape(X.shape[0], -1).contiguous()
+            self._yd = torch.as_tensor(y).to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+            X, y = self._Xd.cpu().numpy(), self._yd.cpu().numpy()
+        else:
+            X = np.asarray(X, dtype=np.float64)
+            X = X.reshape(len(X), -1)
+            y = np.asarray(y, dtype=np.float64).ravel()
+            self._Xd = torch.from_numpy(X).to(self.device)
+            self._yd = torch.from_numpy(y).to(self.device)
         self.X_train_, self.y_train_ = X, y
-        self._Xd = torch.from_numpy(X).to(self.device)
-        self._yd = torch.from_numpy(y).to(self.device)
         self._rng = check_random_state(self.random_state)
         theta0, bounds = self.kernel.theta, self.kernel.bounds
         if self.optimizer is not None:

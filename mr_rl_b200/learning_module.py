@@ -17,7 +17,12 @@ from .gp import DeviceGP
 
 
 class LearningModule:
-    def __init__(self, device="cuda", fit="device"):
+    def __init__(self, device="cuda", fit="device", preprocess=None):
+        """fit: "device" | "host" (sklearn).  preprocess: "device" | "host" (numpy/scipy as in the reference); defaults to
+        where the fit runs."""
+        self.preprocess = preprocess if preprocess is not None else fit
+        if self.preprocess not in ("device", "host"):
+            raise ValueError("preprocess must be 'device' or 'host'")
         if fit == "device":
             from .gpr import DeviceGPR
             # Learning_module.py:30-33: RBF(1.0, (1e-2, 10)) + WhiteKernel() (noise 1.0, bounds (1e-5, 1e5)), 5 restarts
@@ -51,8 +56,39 @@ class LearningModule:
         vy = uniform_filter1d(np.gradient(py, time), int(N / 2), mode="nearest")
         return N, px, py, vx, vy
 
+    def _device_preprocess(self, px, py, time, alpha_sim=None, freq=1.0, n_valid=None, subtract_t0=False):
+        """mr_learn_preprocess: the filters, gradient, drift means, a0 and GP targets on the device."""
+        import ctypes as C
+
+        from . import _lib as L
+        lib = L.load()
+        dev = torch.device(self.device)
+        to = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64) if not torch.is_tensor(a) else a).to(device=dev, dtype=torch.float64).contiguous()
+        px, py, time = to(px), to(py), to(time)
+        n = int(px.numel())
+        N = int(1 / 0.035 / 2)                                   # Learning_module.py:47,74
+        vx, vy = torch.empty_like(px), torch.empty_like(px)
+        scal = torch.zeros(4, dtype=torch.float64, device=dev)
+        ws = torch.empty(4 * n, dtype=torch.float64, device=dev)
+        al = to(alpha_sim) if alpha_sim is not None else None
+        n_valid = n if n_valid is None else int(n_valid)
+        m = max(n_valid - 2 * N, 0)
+        X, Yx, Yy = (torch.empty(m, dtype=torch.float64, device=dev) for _ in range(3))
+        with torch.cuda.device(dev):
+            rc = lib.mr_learn_preprocess(px.data_ptr(), py.data_ptr(), time.data_ptr(), n, N, 1 if subtract_t0 else 0,
+                                         float(self.Dx), float(self.Dy), al.data_ptr() if al is not None else None, float(freq),
+                                         n_valid, vx.data_ptr(), vy.data_ptr(), X.data_ptr(), Yx.data_ptr(), Yy.data_ptr(),
+                                         scal.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        L.check(rc, "mr_learn_preprocess")
+        return N, vx, vy, X, Yx, Yy, scal
+
     def estimateDisturbance(self, px, py, time):
         """Learning_module.py:46-59: drift = mean filtered velocity of an idle run."""
+        if getattr(self, "preprocess", "host") == "device":
+            *_, scal = self._device_preprocess(px, py, time)
+            self.Dx, self.Dy = (float(v) for v in scal[:2].cpu())
+            return
         N, _, _, vx, vy = self._velocities(np.asarray(px, float), np.asarray(py, float), np.asarray(time, float))
         self.Dx = np.mean(vx[N:-N])
         self.Dy = np.mean(vy[N:-N])
@@ -62,6 +98,22 @@ class LearningModule:
         actions = np.asarray(actions, float)
         freq = actions[0, 0]
         alpha = actions[:, 1]
+        if getattr(self, "preprocess", "host") == "device":
+            off = np.argwhere(alpha >= 500)                      # controller-off frames, :89-100
+            n_valid = int(off[0]) - 1 if len(off) > 0 else None
+            _, _, _, X, Yx, Yy, scal = self._device_preprocess(px, py, time, alpha_sim, freq, n_valid, subtract_t0=True)
+            a0 = float(scal[2].cpu())
+            X = X.reshape(-1, 1)
+            self.X, self.Yx, self.Yy = X.cpu().numpy(), Yx.cpu().numpy(), Yy.cpu().numpy()
+            if hasattr(self.gprX, "device_model"):               # DeviceGPR takes device tensors as they are
+                self.gprX.fit(X, Yx)
+                self.gprY.fit(X, Yy)
+            else:
+                self.gprX.fit(self.X, self.Yx)
+                self.gprY.fit(self.X, self.Yy)
+            self.a0, self.freq = a0, freq
+            self.upload()
+            return a0
         time = np.asarray(time, float) - time[0]
         N, px, py, vx, vy = self._velocities(np.asarray(px, float), np.asarray(py, float), time)
         speed = np.sqrt((vx - self.Dx) ** 2 + (vy - self.Dy) ** 2)

@@ -77,3 +77,58 @@ def test_main_flow_on_the_device(golden_learn, fit):
     err_c = torch.hypot(vxp + lm.Dx - vd_t[:, 0], vyp + lm.Dy - vd_t[:, 1]).mean()
     err_n = torch.hypot(vxn + lm.Dx - vd_t[:, 0], vyn + lm.Dy - vd_t[:, 1]).mean()
     assert float(err_c) <= float(err_n) + 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cut", [None, 0.7])
+def test_device_preprocessing_matches_the_host_restatement(golden_learn, cut):
+    """mr_learn_preprocess (filters, np.gradient, drift means, median a0, GP targets) against the numpy/scipy
+    restatement that the CPU test pins to the live reference (Learning_module.py:46-59, :63-120)."""
+    from mr_rl_b200.learning_module import LearningModule
+    g = golden_learn
+    host = LearningModule.__new__(LearningModule)
+    host.Dx = host.Dy = 0
+    host.preprocess = "host"
+    dev = LearningModule(device="cuda:0", fit="device")
+    assert dev.preprocess == "device"
+    host.estimateDisturbance(g["px_idle"], g["py_idle"], g["t_idle"])
+    dev.estimateDisturbance(g["px_idle"], g["py_idle"], g["t_idle"])
+    assert rel_err(dev.Dx, host.Dx) < 1e-10 and rel_err(dev.Dy, host.Dy) < 1e-10
+    assert rel_err(dev.Dx, g["Dx"]) < 1e-10
+    # the learn() half, optionally with controller-off frames (alpha >= 500) that truncate the record
+    actions = np.array(g["circ"], dtype=float)
+    time = np.asarray(g["time"], float)
+    if cut is not None:
+        cut = int(cut * len(time))
+        actions[cut:, 1] = 1000.0
+    N, _, _, vx, vy = host._velocities(g["px"].astype(float), g["py"].astype(float), time - time[0])
+    n_valid = len(time) if cut is None else cut - 1
+    al = np.asarray(g["alpha"], float)[:n_valid][N:-N]
+    freq = actions[0, 0]
+    speed = np.sqrt((vx - host.Dx) ** 2 + (vy - host.Dy) ** 2)[:n_valid][N:-N]
+    a0_ref = np.median(speed / freq)
+    _, dvx, dvy, X, Yx, Yy, scal = dev._device_preprocess(g["px"], g["py"], time, g["alpha"], freq, None if cut is None else n_valid,
+                                                          subtract_t0=True)
+    assert rel_err(dvx.cpu().numpy(), vx) < 1e-10 and rel_err(dvy.cpu().numpy(), vy) < 1e-10
+    assert rel_err(float(scal[2]), a0_ref) < 1e-10 and int(scal[3]) == len(al)
+    assert np.array_equal(X.cpu().numpy(), al)
+    assert rel_err(Yx.cpu().numpy(), vx[:n_valid][N:-N] - a0_ref * freq * np.cos(al)) < 1e-9
+    assert rel_err(Yy.cpu().numpy(), vy[:n_valid][N:-N] - a0_ref * freq * np.sin(al)) < 1e-9
+    if cut is None:
+        assert rel_err(float(scal[2]), g["a0"]) < 1e-9 and rel_err(Yx.cpu().numpy(), g["Yx"]) < 1e-7
+
+
+@pytest.mark.gpu
+def test_learn_preprocess_argument_errors():
+    import torch
+    from mr_rl_b200 import _lib as L
+    lib = L.load()
+    d = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    p = d.data_ptr()
+    assert lib.mr_learn_preprocess(None, p, p, 100, 14, 0, 0.0, 0.0, None, 1.0, 100, p, p, None, None, None, p, p, 1 << 20, None) != 0
+    assert lib.mr_learn_preprocess(p, p, p, 20, 14, 0, 0.0, 0.0, None, 1.0, 20, p, p, None, None, None, p, p, 1 << 20, None) != 0
+    assert b"filter" in lib.mr_last_error()
+    assert lib.mr_learn_preprocess(p, p, p, 100, 14, 0, 0.0, 0.0, None, 1.0, 100, p, p, None, None, None, p, p, 8, None) != 0
+    assert b"workspace" in lib.mr_last_error()
+    assert lib.mr_learn_preprocess(p, p, p, 100, 14, 0, 0.0, 0.0, p, 1.0, 20, p, p, p, p, p, p, p, 1 << 20, None) != 0
+    assert b"n_valid" in lib.mr_last_error()

@@ -39,7 +39,7 @@ def main(path, envs_per_warp=None):
     h2 = src[hi]
     iS, iE, iW = h2.index('Source'), h2.index('Instructions Executed'), h2.index('Warp Stall Sampling (All Samples)')
     ops, total = collections.Counter(), 0
-    body = [r for r in src[hi + 1:] if len(r) > iW and r[iE].isdigit()]
+    body = [r for r in src[hi + 1:] if len(r) > max(iW, iE, iS) and r[iE].isdigit()]
     for r in body:
         m = re.match(r'\s*(@!?U?P\w+\s+)?([A-Z0-9_]+)', r[iS])
         ops[m.group(2) if m else '?'] += int(r[iE]); total += int(r[iE])
