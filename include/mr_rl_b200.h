@@ -138,6 +138,9 @@ typedef struct mr_step_out {
     uint8_t* done;      /* [n]; may be NULL */
     void* state_prime;  /* [2][n] Simulator.state_prime (MR_simulator.py:87); may be NULL */
     int64_t row_stride; /* elements between rows of obs / state_prime (0 = n) */
+    int32_t skip_goal_rows; /* != 0: leave obs rows 2, 3 (the constant goal (0, 0), MR_env.py:57) untouched — the caller
+                             * zeroed them once; saves 2 of the 5 obs rows when obs points at host memory */
+    int32_t reserved;
 } mr_step_out;
 
 int mr_abi_version(void);
@@ -157,6 +160,7 @@ int mr_env_reset(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_
                  const mr_step_out* out, void* stream);
 
 /* MR_Env.step for n envs.  actions is [n][2] (f_t, alpha_t), storage dtype. */
+/* (device buffers; the host-buffer form is mr_env_step_host below) */
 int mr_env_step(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
                 const mr_noise* nz, const mr_time_table* tt, const void* actions,
                 const mr_step_out* out, void* stream);
@@ -238,6 +242,37 @@ int32_t mr_actor_param_count(void);
 /* obs is [5][obs_row_stride] (storage dtype), actions out is [n][2] (storage dtype). */
 int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
                      const double action_high[2], void* actions, void* stream);
+
+/* ---- MR_Env.step with HOST buffers (what a caller holding numpy arrays does per control step, MR_env.py:70-98) ----
+ * Unlike every other entry point this one BLOCKS until the host buffers are filled.  Two strategies:
+ *   n_chunks == 0  DIRECT: the step kernel reads the actions from and writes obs / reward / done to the host buffers
+ *                  itself (one launch; its bulk copies cross PCIe in both directions while the state stays in HBM).
+ *                  The host buffers must be page-locked and device-addressable (cudaHostAlloc / cudaHostRegister under
+ *                  unified addressing, e.g. torch pinned memory), rows 16-byte aligned.  pl, actions_dev, out_dev may be
+ *                  NULL (out_dev->state_prime, if given, is still written on the device).  This is the fast path.
+ *   n_chunks >= 1  STAGED: H2D of the actions, the step kernel and D2H of the results, split into env ranges pipelined
+ *                  on three internal streams (copy-in of chunk i+1, kernel of chunk i, copy-out of chunk i-1 overlap).
+ *                  Works with any page-locked host memory.  The pipeline object owns only CUDA streams and events. */
+typedef struct mr_host_pipeline mr_host_pipeline;
+int mr_host_pipeline_create(int32_t max_chunks, mr_host_pipeline** out);
+void mr_host_pipeline_destroy(mr_host_pipeline* pl);
+
+typedef struct mr_host_step_io {
+    const void* actions_host;  /* HOST  [n][2] (f_t, alpha_t), storage dtype                                  */
+    void* actions_dev;         /* device staging [n][2]                                                       */
+    void* obs_host;            /* HOST  [5][host_row_stride]; rows 2, 3 (the constant goal) are copied only if  */
+    void* rew_host;            /* HOST  [n]                                     copy_goal_rows != 0           */
+    uint8_t* done_host;        /* HOST  [n]                                                                   */
+    int64_t host_row_stride;   /* elements between obs_host rows (0 = n)                                      */
+    int32_t copy_goal_rows;
+    int32_t reserved;
+} mr_host_step_io;
+
+/* out_dev: the device rows the kernel writes (obs, rew, done required).  `stream`: the caller's stream; the pipeline
+ * starts after the work already queued on it, and work queued on it afterwards sees the stepped state. */
+int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
+                     const mr_noise* nz, const mr_time_table* tt, const mr_host_step_io* io, const mr_step_out* out_dev,
+                     int32_t n_chunks, void* stream);
 
 /* LearningModule.estimateDisturbance / learn up to the GPR fit (Learning_module.py:46-59, :63-120) for a trajectory
  * px, py, time [n] already in HBM: uniform_filter1d(N, nearest) -> np.gradient(., time) -> uniform_filter1d(N/2)

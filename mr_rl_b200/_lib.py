@@ -48,7 +48,7 @@ class TimeTable(C.Structure):
 
 class StepOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p), ("state_prime", C.c_void_p),
-                ("row_stride", C.c_int64)]
+                ("row_stride", C.c_int64), ("skip_goal_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RolloutIO(C.Structure):
@@ -61,6 +61,11 @@ class GPModel(C.Structure):
     _fields_ = [("x_train_scaled", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p), ("n_train", C.c_int32),
                 ("n_pad", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
                 ("length_scale", C.c_double), ("noise_level", C.c_double)]
+
+
+class HostStepIO(C.Structure):
+    _fields_ = [("actions_host", C.c_void_p), ("actions_dev", C.c_void_p), ("obs_host", C.c_void_p), ("rew_host", C.c_void_p),
+                ("done_host", C.c_void_p), ("host_row_stride", C.c_int64), ("copy_goal_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DDPGState(C.Structure):
@@ -84,7 +89,7 @@ GP_PAD = 128
 EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time_table_host", "mr_env_reset",
            "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_gp_fit", "mr_gp_fit_workspace_bytes", "mr_actor_param_count",
            "mr_critic_param_count", "mr_replay_add", "mr_ou_noise_add", "mr_ddpg_update", "mr_learn_preprocess",
-           "mr_learn_workspace_bytes",
+           "mr_learn_workspace_bytes", "mr_host_pipeline_create", "mr_host_pipeline_destroy", "mr_env_step_host",
            "mr_actor_forward")
 
 _lib = None
@@ -126,6 +131,13 @@ def load():
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                               C.c_void_p]
     lib.mr_gp_fit.restype = C.c_int
+    lib.mr_host_pipeline_create.argtypes = [C.c_int32, P(C.c_void_p)]
+    lib.mr_host_pipeline_create.restype = C.c_int
+    lib.mr_host_pipeline_destroy.argtypes = [C.c_void_p]
+    lib.mr_host_pipeline_destroy.restype = None
+    lib.mr_env_step_host.argtypes = [C.c_void_p, P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), P(TimeTable),
+                                     P(HostStepIO), P(StepOut), C.c_int32, C.c_void_p]
+    lib.mr_env_step_host.restype = C.c_int
     lib.mr_learn_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
                                         C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]

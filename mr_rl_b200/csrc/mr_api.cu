@@ -2,6 +2,7 @@
 // per-(storage dtype, noise mode) launchers.  No CPU fallback exists: every call launches CUDA.
 #include <cstdarg>
 #include <cstdio>
+#include <new>
 
 #include "mr_common.cuh"
 
@@ -47,8 +48,9 @@ static StateView<T> state_view(const mr_env_state& s) {
 template <class T>
 static OutView<T> out_view(const mr_step_out* o, int64_t n) {
     OutView<T> v;
-    if (!o) { v.obs = nullptr; v.rew = nullptr; v.done = nullptr; v.sp = nullptr; v.stride = n; return v; }
+    if (!o) { v.obs = nullptr; v.rew = nullptr; v.done = nullptr; v.sp = nullptr; v.stride = n; v.goal = true; return v; }
     v.obs = (T*)o->obs; v.rew = (T*)o->rew; v.done = o->done; v.sp = (T*)o->state_prime;
+    v.goal = o->skip_goal_rows == 0;
     v.stride = o->row_stride ? o->row_stride : n;
     return v;
 }
@@ -188,6 +190,128 @@ int mr_env_step(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_p
     cudaStream_t s = (cudaStream_t)stream;
     return dtype == MR_F64 ? mr::do_step<double>(*st, n, pp, nz, tv, actions, out, s)
                            : mr::do_step<float>(*st, n, pp, nz, tv, actions, out, s);
+}
+
+// ---- MR_Env.step with HOST buffers: the pipelined H2D -> step -> D2H path in one call ------------------------------
+struct mr_host_pipeline {
+    int device;
+    int max_chunks;
+    cudaStream_t s_in, s_k, s_out;
+    cudaEvent_t ev_start, ev_done;
+    cudaEvent_t* ev_in;      // [max_chunks]
+    cudaEvent_t* ev_k;       // [max_chunks]
+};
+
+int mr_host_pipeline_create(int32_t max_chunks, mr_host_pipeline** out) {
+    if (!out || max_chunks < 1 || max_chunks > 64) return mr::fail(MR_ERR_ARG, "mr_host_pipeline_create: need 1 <= max_chunks <= 64");
+    mr_host_pipeline* pl = new (std::nothrow) mr_host_pipeline();
+    if (!pl) return mr::fail(MR_ERR_CUDA, "mr_host_pipeline_create: out of host memory");
+    pl->max_chunks = max_chunks;
+    cudaGetDevice(&pl->device);
+    pl->ev_in = new (std::nothrow) cudaEvent_t[max_chunks];
+    pl->ev_k = new (std::nothrow) cudaEvent_t[max_chunks];
+    cudaError_t e = cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_k, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_done, cudaEventDisableTiming);
+    for (int i = 0; i < max_chunks && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_k[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_host_pipeline_create: %s", cudaGetErrorString(e));
+    *out = pl;
+    return MR_OK;
+}
+
+void mr_host_pipeline_destroy(mr_host_pipeline* pl) {
+    if (!pl) return;
+    cudaStreamDestroy(pl->s_in); cudaStreamDestroy(pl->s_k); cudaStreamDestroy(pl->s_out);
+    cudaEventDestroy(pl->ev_start); cudaEventDestroy(pl->ev_done);
+    for (int i = 0; i < pl->max_chunks; ++i) { cudaEventDestroy(pl->ev_in[i]); cudaEventDestroy(pl->ev_k[i]); }
+    delete[] pl->ev_in; delete[] pl->ev_k;
+    delete pl;
+}
+
+int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
+                     const mr_noise* nz, const mr_time_table* tt, const mr_host_step_io* io, const mr_step_out* out_dev,
+                     int32_t n_chunks, void* stream) {
+    int rc = mr::check_common("mr_env_step_host", st, n, dtype, p, nz);
+    if (rc) return rc;
+    if (!io) return mr::fail(MR_ERR_ARG, "mr_env_step_host: null io");
+    if (!io->actions_host || !io->obs_host || !io->rew_host || !io->done_host)
+        return mr::fail(MR_ERR_ARG, "mr_env_step_host: null host buffer");
+    if (n == 0) return MR_OK;
+    const int64_t el = dtype == MR_F64 ? 8 : 4;
+    const int64_t hstride = io->host_row_stride ? io->host_row_stride : n;
+    if (n_chunks == 0) {
+        // direct mode: the step kernel itself reads the actions from and writes obs / rew / done to the page-locked
+        // host buffers (device-addressable under unified addressing) — its TMA bulk copies go over PCIe in both
+        // directions at once, there is no staging pass, no per-copy latency and the goal rows are never sent
+        mr_step_out oh;
+        oh.obs = io->obs_host; oh.rew = io->rew_host; oh.done = io->done_host;
+        oh.state_prime = out_dev ? out_dev->state_prime : nullptr;
+        oh.row_stride = hstride;
+        if (oh.state_prime && (out_dev->row_stride ? out_dev->row_stride : n) != hstride)
+            return mr::fail(MR_ERR_ARG, "mr_env_step_host: direct mode shares one row stride between obs_host and state_prime");
+        oh.skip_goal_rows = io->copy_goal_rows ? 0 : 1;
+        oh.reserved = 0;
+        rc = mr_env_step(st, n, dtype, p, nz, tt, io->actions_host, &oh, stream);
+        if (rc) return rc;
+        const cudaError_t e0 = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e0 != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_env_step_host: %s", cudaGetErrorString(e0));
+        return MR_OK;
+    }
+    if (!pl || !out_dev) return mr::fail(MR_ERR_ARG, "mr_env_step_host: staged mode needs a pipeline and device output rows");
+    if (!io->actions_dev) return mr::fail(MR_ERR_ARG, "mr_env_step_host: staged mode needs the device staging buffer for actions");
+    if (!out_dev->obs || !out_dev->rew || !out_dev->done) return mr::fail(MR_ERR_ARG, "mr_env_step_host: device obs/rew/done rows required");
+    const int64_t dstride = out_dev->row_stride ? out_dev->row_stride : n;
+    // chunk edges are multiples of 256 envs (tile- and 16-byte aligned sub-ranges); table noise indexes the table by
+    // the launch-local env index, so it stays in one piece
+    int chunks = n_chunks < 1 ? 1 : (n_chunks > pl->max_chunks ? pl->max_chunks : n_chunks);
+    if (nz && nz->mode == MR_NOISE_TABLE) chunks = 1;
+    int64_t per = (n / chunks) / 256 * 256;
+    if (per == 0) { chunks = 1; per = n; }
+    cudaStream_t cur = (cudaStream_t)stream;
+    cudaEventRecord(pl->ev_start, cur);
+    cudaStreamWaitEvent(pl->s_in, pl->ev_start, 0);
+    cudaStreamWaitEvent(pl->s_k, pl->ev_start, 0);
+    cudaStreamWaitEvent(pl->s_out, pl->ev_start, 0);
+    for (int c = 0; c < chunks; ++c) {
+        const int64_t lo = c * per, hi = c == chunks - 1 ? n : lo + per, m = hi - lo;
+        cudaMemcpyAsync((char*)io->actions_dev + 2 * lo * el, (const char*)io->actions_host + 2 * lo * el, (size_t)(2 * m * el),
+                        cudaMemcpyHostToDevice, pl->s_in);
+        cudaEventRecord(pl->ev_in[c], pl->s_in);
+        cudaStreamWaitEvent(pl->s_k, pl->ev_in[c], 0);
+        mr_env_state sc = *st;
+        sc.x = (char*)st->x + lo * el; sc.y = (char*)st->y + lo * el; sc.fx = (char*)st->fx + lo * el;
+        sc.fy = (char*)st->fy + lo * el; sc.h = (char*)st->h + lo * el;
+        sc.counter = st->counter + lo; sc.status = st->status + lo;
+        if (st->cursor) sc.cursor = st->cursor + lo;
+        mr_step_out oc = *out_dev;
+        oc.obs = (char*)out_dev->obs + lo * el; oc.rew = (char*)out_dev->rew + lo * el; oc.done = out_dev->done + lo;
+        if (out_dev->state_prime) oc.state_prime = (char*)out_dev->state_prime + lo * el;
+        oc.row_stride = dstride;
+        mr_noise nc;
+        const mr_noise* nzp = nz;
+        if (nz) { nc = *nz; nc.env_base = nz->env_base + (uint64_t)lo; nzp = &nc; }
+        rc = mr_env_step(&sc, m, dtype, p, nzp, tt, (const char*)io->actions_dev + 2 * lo * el, &oc, pl->s_k);
+        if (rc) return rc;
+        cudaEventRecord(pl->ev_k[c], pl->s_k);
+        cudaStreamWaitEvent(pl->s_out, pl->ev_k[c], 0);
+        for (int row = 0; row < 5; ++row) {
+            if ((row == 2 || row == 3) && !io->copy_goal_rows) continue;     // the goal is the constant (0, 0) (MR_env.py:57)
+            cudaMemcpyAsync((char*)io->obs_host + (row * hstride + lo) * el, (const char*)out_dev->obs + (row * dstride + lo) * el,
+                            (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out);
+        }
+        cudaMemcpyAsync((char*)io->rew_host + lo * el, (const char*)out_dev->rew + lo * el, (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out);
+        cudaMemcpyAsync(io->done_host + lo, out_dev->done + lo, (size_t)m, cudaMemcpyDeviceToHost, pl->s_out);
+    }
+    cudaEventRecord(pl->ev_done, pl->s_k);
+    cudaStreamWaitEvent(cur, pl->ev_done, 0);                  // later work on the caller's stream sees the new state
+    const cudaError_t e = cudaStreamSynchronize(pl->s_out);     // the host buffers are valid when this returns
+    if (e != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_env_step_host: %s", cudaGetErrorString(e));
+    return mr::check_launch("mr_env_step_host");
 }
 
 int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,

@@ -38,6 +38,7 @@ struct OutView {
     uint8_t* done;
     T* sp;            // [2][stride]
     int64_t stride;
+    bool goal;        // write the constant goal rows obs[2], obs[3] (off when the caller keeps them pre-zeroed)
 };
 
 struct NoiseView {

@@ -123,7 +123,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         // outputs of the LAST step (after an auto reset: the first observation of the new episode)
         if (out.obs) {
             out.obs[i] = (T)e.x; out.obs[out.stride + i] = (T)e.y;
-            out.obs[2 * out.stride + i] = (T)0; out.obs[3 * out.stride + i] = (T)0;
+            if (out.goal) { out.obs[2 * out.stride + i] = (T)0; out.obs[3 * out.stride + i] = (T)0; }
             out.obs[4 * out.stride + i] = (T)sqrt(e.x * e.x + e.y * e.y);
         }
         if (out.rew) out.rew[i] = (T)o.rew;

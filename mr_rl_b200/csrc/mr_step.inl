@@ -87,8 +87,10 @@ env_step_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, 
         for (int j = 0; j < VEC; ++j) zero.v[j] = (T)0;
         store_pack<T, VEC>(out.obs, i0, ox);
         store_pack<T, VEC>(out.obs + out.stride, i0, oy);
-        store_pack<T, VEC>(out.obs + 2 * out.stride, i0, zero);       // goal is always (0,0), MR_env.py:57
-        store_pack<T, VEC>(out.obs + 3 * out.stride, i0, zero);
+        if (out.goal) {
+            store_pack<T, VEC>(out.obs + 2 * out.stride, i0, zero);   // goal is always (0,0), MR_env.py:57
+            store_pack<T, VEC>(out.obs + 3 * out.stride, i0, zero);
+        }
         store_pack<T, VEC>(out.obs + 4 * out.stride, i0, od);
     }
     if (out.rew) store_pack<T, VEC>(out.rew, i0, orew);
@@ -132,7 +134,7 @@ env_reset_kernel(StateView<T> st, const T* __restrict__ init_xy, const uint8_t* 
     st.status[i] = (uint8_t)e.status;
     if (out.obs) {
         out.obs[i] = (T)e.x; out.obs[out.stride + i] = (T)e.y;
-        out.obs[2 * out.stride + i] = (T)0; out.obs[3 * out.stride + i] = (T)0;
+        if (out.goal) { out.obs[2 * out.stride + i] = (T)0; out.obs[3 * out.stride + i] = (T)0; }
         out.obs[4 * out.stride + i] = (T)sqrt(e.x * e.x + e.y * e.y);
     }
     if (out.rew) out.rew[i] = (T)0;

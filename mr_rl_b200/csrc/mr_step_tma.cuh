@@ -82,12 +82,19 @@ struct StepSmem {
     alignas(8) uint64_t full[kStagesIn];
 };
 
-// at least 16 warps per SM (<= 128 registers): the generated-noise variant would otherwise take 136
+// at least 16 warps per SM (<= 128 registers): the generated-noise variant would otherwise take 136.
+// Measured at 2^20 envs (sigma 0 / 1): fp64 storage 16 warps 29.1 / 32.6 us, 20 warps 30.0 / 35.4, 24 warps 30.5 / 35.3
+// (the spills cost more than the occupancy gives); fp32 storage 16 warps 27.4 / 32.3 us, 24 warps 23.9 / 29.7 us
+// (half the bytes per env: latency hiding matters more) -> 24 warps for the 256-env fp32 tile.
 #ifndef MR_TMA_WARPS
 #define MR_TMA_WARPS 16
 #endif
+#ifndef MR_TMA_WARPS_F32
+#define MR_TMA_WARPS_F32 24
+#endif
+template <class T> struct TmaWarps { static constexpr int value = sizeof(T) == 4 ? MR_TMA_WARPS_F32 : MR_TMA_WARPS; };
 template <class T, int MODE, bool MISM>
-__global__ void __launch_bounds__(TileOf<T>::value, MR_TMA_WARPS * 32 / TileOf<T>::value)
+__global__ void __launch_bounds__(TileOf<T>::value, TmaWarps<T>::value * 32 / TileOf<T>::value)
 env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
                     Params p, int64_t n_tiles, int64_t n_total) {
     constexpr int kTile = TileOf<T>::value;
@@ -202,8 +209,8 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
             if (out.obs) {
                 if (warp == 6 % kWarps) bulk_store(out.obs + i0, bo.x, kRow);
                 if (warp == 7 % kWarps) bulk_store(out.obs + out.stride + i0, bo.y, kRow);
-                if (warp == 8 % kWarps) bulk_store(out.obs + 2 * out.stride + i0, sm.zero, kRow);   // goal = (0,0), MR_env.py:57
-                if (warp == 9 % kWarps) bulk_store(out.obs + 3 * out.stride + i0, sm.zero, kRow);
+                if (out.goal && warp == 8 % kWarps) bulk_store(out.obs + 2 * out.stride + i0, sm.zero, kRow);   // goal = (0,0), MR_env.py:57
+                if (out.goal && warp == 9 % kWarps) bulk_store(out.obs + 3 * out.stride + i0, sm.zero, kRow);
                 if (warp == 10 % kWarps) bulk_store(out.obs + 4 * out.stride + i0, bo.d, kRow);
             }
             if (out.rew && warp == 11 % kWarps) bulk_store(out.rew + i0, bo.rew, kRow);

@@ -257,8 +257,10 @@ class VecMREnv:
     def step_host(self, actions):
         """The reference-facing call with HOST buffers: actions [N, 2] (numpy array, or a pinned torch
         tensor which is used without a staging copy) in, numpy (obs [N,5], rew [N], done [N] bool) out.
-        Host<->device copies run on the current stream; the call returns after the device->host
-        copies have completed.  The returned arrays are views of pinned buffers reused by the next call."""
+        The call returns when the host arrays are filled; they are views of pinned buffers reused by the next call.
+        ``host_mode = "direct"`` (default): the step kernel reads the actions from and writes the results to the pinned
+        host buffers itself — the device-side obs / rew / done rows are NOT refreshed by this call (state, counters
+        and state_prime are).  ``host_mode = "staged"``: copies through the device rows in pipelined chunks."""
         n = self.num_envs
         if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() \
                 and actions.dtype == self.dtype and actions.is_contiguous() and actions.numel() == 2 * n:
@@ -273,75 +275,50 @@ class VecMREnv:
         if a_dev is None:
             a_dev = self._pinned["act_dev"] = torch.empty(n, 2, dtype=self.dtype, device=self.device)
         fresh = "obs" not in self._pinned
-        o_pin = self._pinned_buf("obs", (5, n), self.dtype)
+        o_pin = self._pinned_buf("obs", (5, self._np), self.dtype)    # same row stride as the device rows
         r_pin = self._pinned_buf("rew", (n,), self.dtype)
         d_pin = self._pinned_buf("done", (n,), torch.uint8)
         if fresh:
             o_pin.zero_()          # goal rows 2, 3 are always 0 (MR_env.py:57): written once, never re-copied
-        chunks = self._host_chunks(n)
-        if len(chunks) == 1:
-            a_dev.copy_(a_pin, non_blocking=True)
-            self.step(a_dev)
-            for row in (0, 1, 4):
-                o_pin[row].copy_(self._obs[row, :n], non_blocking=True)
-            r_pin.copy_(self._rew[:n], non_blocking=True)
-            d_pin.copy_(self._done[:n], non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-        else:
-            self._step_host_pipelined(chunks, a_pin, a_dev, o_pin, r_pin, d_pin)
-        return o_pin.numpy().T, r_pin.numpy(), d_pin.numpy().view(np.bool_), {}
-
-    def _host_chunks(self, n, min_chunk=1 << 18, max_chunks=2):
-        """Env-index ranges for the pipelined host step (multiples of 256 so every chunk starts tile- and
-        16-byte-aligned); small batches stay in one piece.  Measured at 2^20 envs: 1 chunk 1.00 ms, 2 chunks
-        0.94 ms, 4 chunks 0.94 ms, 8 chunks 1.13 ms — the host link tops out at ~55 GB/s for both directions."""
-        k = min(max_chunks, n // min_chunk)
-        if k <= 1 or self.noise_kind == "table":
-            return [(0, n)]
-        per = (n // k) // 256 * 256
-        edges = [i * per for i in range(k)] + [n]
-        return [(edges[i], edges[i + 1]) for i in range(k)]
-
-    def _step_host_pipelined(self, chunks, a_pin, a_dev, o_pin, r_pin, d_pin):
-        """H2D of chunk i+1, the step kernel of chunk i and D2H of chunk i-1 overlap on three streams
-        (PCIe is full duplex).  Each chunk is an ordinary mr_env_step call on an index sub-range: the
-        Philox streams are keyed by the global env index, so the result equals the single-launch step."""
-        dev = self.device
-        if "streams" not in self._pinned:
-            self._pinned["streams"] = [torch.cuda.Stream(dev) for _ in range(3)]
-        s_in, s_k, s_out = self._pinned["streams"]
-        cur = torch.cuda.current_stream(dev)
-        for st in (s_in, s_k, s_out):
-            st.wait_stream(cur)
-        el = self._state.element_size()
-        nz = self._noise_for(self.params.noise_var)
-        base = int(self._c_noise.env_base)
-        out_c = self._c_out if self.want_state_prime else self._c_out_lean
-        ev_in = [torch.cuda.Event() for _ in chunks]
-        ev_k = [torch.cuda.Event() for _ in chunks]
-        for i, (lo, hi) in enumerate(chunks):
-            with torch.cuda.stream(s_in):
-                a_dev[lo:hi].copy_(a_pin[lo:hi], non_blocking=True)
-                ev_in[i].record(s_in)
-            s_k.wait_event(ev_in[i])
-            stc = L.EnvState(*[self._c_state_ptr(f, lo) for f in ("x", "y", "fx", "fy", "h", "counter", "cursor", "status")])
-            outc = L.StepOut(self._obs.data_ptr() + lo * el, self._rew.data_ptr() + lo * el, self._done.data_ptr() + lo,
-                             (self._sp.data_ptr() + lo * el) if out_c.state_prime else None, self._np)
-            nzc = L.Noise(nz.mode, 0, nz.table, nz.table_len, nz.seed, nz.offset, base + lo)
-            rc = self.lib.mr_env_step(C.byref(stc), hi - lo, self._dt, self._b_params, C.byref(nzc), self._b_tt,
-                                      a_dev.data_ptr() + 2 * lo * el, C.byref(outc), s_k.cuda_stream)
-            L.check(rc, "mr_env_step")
-            ev_k[i].record(s_k)
-            s_out.wait_event(ev_k[i])
-            with torch.cuda.stream(s_out):
-                for row in (0, 1, 4):                      # contiguous 1-D pieces -> plain cudaMemcpyAsync
-                    o_pin[row, lo:hi].copy_(self._obs[row, lo:hi], non_blocking=True)
-                r_pin[lo:hi].copy_(self._rew[lo:hi], non_blocking=True)
-                d_pin[lo:hi].copy_(self._done[lo:hi], non_blocking=True)
-            self.kernel_launches += 1
+        # one C call.  "direct": the step kernel reads / writes the pinned host buffers itself (zero-copy over PCIe);
+        # "staged": H2D, kernel(s) and D2H pipelined over env chunks on the library's own streams
+        chunks = 0 if self.host_mode == "direct" else self._host_chunks(n)
+        with torch.cuda.device(self.device):
+            pl = self._pinned.get("pipeline")
+            if pl is None and chunks:
+                h = C.c_void_p()
+                L.check(self.lib.mr_host_pipeline_create(8, C.byref(h)), "mr_host_pipeline_create")
+                pl = self._pinned["pipeline"] = h
+            io = L.HostStepIO(a_pin.data_ptr(), a_dev.data_ptr(), o_pin.data_ptr(), r_pin.data_ptr(), d_pin.data_ptr(),
+                              self._np, 0, 0)
+            nz = self._noise_for(self.params.noise_var)
+            rc = self.lib.mr_env_step_host(pl, self._b_state, n, self._dt, self._b_params, C.byref(nz), self._b_tt, C.byref(io),
+                                           self._b_out if self.want_state_prime else self._b_out_lean, chunks,
+                                           torch.cuda.current_stream(self.device).cuda_stream)
+        L.check(rc, "mr_env_step_host")
+        self.kernel_launches += max(chunks, 1)
         self._step_index += 1
-        s_out.synchronize()
-        cur.wait_stream(s_k)
+        return o_pin[:, :n].numpy().T, r_pin.numpy(), d_pin.numpy().view(np.bool_), {}
+
+    # Host-buffer step strategy.  Measured at 2^20 envs (fp64, sigma = 1): staged 1 / 2 / 4 / 8 chunks 1.01 / 0.91 / 0.91 /
+    # 0.99 ms (each of the 5 D2H pieces per chunk costs a few us of DMA set-up), direct see tools/e2ebench.py.
+    host_mode = "direct"
+    host_chunks = 2
+
+    def _host_chunks(self, n, min_chunk=1 << 16):
+        """Number of env ranges for the staged host step; small batches and table noise stay in one piece."""
+        if self.noise_kind == "table":
+            return 1
+        return max(1, min(int(self.host_chunks), n // min_chunk))
+
+    def __del__(self):
+        try:
+            pl = self._pinned.get("pipeline")
+            if pl is not None:
+                self.lib.mr_host_pipeline_destroy(pl)
+                self._pinned["pipeline"] = None
+        except Exception:
+            pass
 
     def _c_state_ptr(self, field, lo):
         t = {"x": self._state[0], "y": self._state[1], "fx": self._state[2], "fy": self._state[3], "h": self._state[4],

@@ -521,16 +521,19 @@ def test_long_soak_generated_noise_auto_reset():
 
 
 def test_pipelined_host_step_equals_single_launch_step():
-    """step_host splits large batches into chunks (H2D / kernel / D2H overlapped on three streams); the result
-    must equal the one-launch device step bit for bit, generated noise included (global env index keys)."""
+    """step_host = one mr_env_step_host call: large batches are split into chunks (H2D / kernel / D2H overlapped on
+    the library's three streams); the result must equal the one-launch device step bit for bit, generated noise
+    included (global env index keys)."""
     n = (1 << 19) + 777
     rng = np.random.default_rng(3)
     acts = np.stack([rng.uniform(0, 20, n), rng.uniform(0, 6.28, n)], -1)
     e1 = make_env(n, noise="philox", seed=21); e2 = make_env(n, noise="philox", seed=21)
     for e in (e1, e2):
         e.reset(init=None, noise_var=1.0, a0=1.0)
-    assert len(e1._host_chunks(n)) == 2
-    for _ in range(3):
+    assert e1.host_mode == "direct"
+    for k in range(6):
+        e1.host_mode = "direct" if k in (0, 5) else "staged"
+        e1.host_chunks = (0, 4, 3, 8, 1, 0)[k]
         o1, r1, d1, _ = e1.step_host(acts)
         o2, r2, d2, _ = e2.step(torch.as_tensor(acts, device="cuda:0"))
         assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(d1, d2.cpu().numpy().astype(bool))

@@ -3,12 +3,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mr_rl_b200 import VecMREnv
 n = 1 << 20
-for maxc in (1, 2, 4, 8):
+for maxc in (0, 1, 2, 4):
     env = VecMREnv(n, device="cuda:0", noise="philox", seed=1, auto_reset=True)
     env.want_state_prime = False
     env.reset(init=None, noise_var=1.0, a0=1.0)
-    orig = env._host_chunks
-    env._host_chunks = (lambda nn, _o=orig, _m=maxc: _o(nn, max_chunks=_m))
+    env.host_mode = "direct" if maxc == 0 else "staged"
+    env.host_chunks = maxc
     acts = [(torch.rand(n, 2, dtype=torch.float64) * torch.tensor([20.0, 6.28], dtype=torch.float64)).pin_memory() for _ in range(4)]
     for k in range(3): env.step_host(acts[k % 4])
     torch.cuda.synchronize(); t = time.perf_counter()
