@@ -301,7 +301,9 @@ class VecMREnv:
         return o_pin[:, :n].numpy().T, r_pin.numpy(), d_pin.numpy().view(np.bool_), {}
 
     # Host-buffer step strategy.  Measured at 2^20 envs (fp64, sigma = 1): staged 1 / 2 / 4 / 8 chunks 1.01 / 0.91 / 0.91 /
-    # 0.99 ms (each of the 5 D2H pieces per chunk costs a few us of DMA set-up), direct see tools/e2ebench.py.
+    # 0.99 ms (each of the 5 D2H pieces per chunk costs a few us of DMA set-up); direct 0.82 ms.  Tried and dropped: a
+    # hybrid (copy-engine H2D of the actions in chunks + kernel writing straight to the host) 0.89 / 0.93 / 0.97 ms with
+    # 2 / 4 / 8 chunks — the smaller launches lose more than the DMA read gains.
     host_mode = "direct"
     host_chunks = 2
 
