@@ -15,4 +15,11 @@ ncu --set full --clock-control none --import-source on -k regex:env_step_tma -s 
 PCMD="python tools/profile_paths.py"
 $PCMD > gpurun_out/paths_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"env_rollout_kernel|gp_var_kernel|gp_kq_mean" -c 8 -f -o gpurun_out/prof_paths $PCMD > gpurun_out/ncu_paths.log 2>&1
+NCMD="python tools/next_rows_once.py"
+$NCMD > gpurun_out/next_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/next_rows_launches.csv $NCMD > gpurun_out/ncu_next_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"ddpg_update|gp_lml_grad" -c 2 -f -o gpurun_out/prof_next_rows $NCMD > gpurun_out/ncu_next.log 2>&1
+python tools/gpfitbench.py > gpurun_out/gpfit.log 2>&1
+python tools/ddpgbench.py > gpurun_out/ddpg.log 2>&1
+python tools/e2ebench.py > gpurun_out/e2e.log 2>&1
 ls -la gpurun_out
