@@ -167,7 +167,7 @@ __device__ __forceinline__ void block_gemm_epilogue(const double (&acc)[8][4][2]
 
 // panel: L_ik = A_ik M_kk^T for i = k+1 .. nb-1 (blockIdx.x = i - k - 1), in place over A_ik
 __global__ void __launch_bounds__(256)
-chol_panel_kernel(double* __restrict__ A, int ld, int k, const double* __restrict__ M, double* __restrict__ tmp) {
+chol_panel_kernel(double* __restrict__ A, int ld, int k, const double* __restrict__ M) {
     extern __shared__ __align__(16) double smem[];
     const int i = k + 1 + blockIdx.x;
     double acc[8][4][2] = {};
@@ -175,7 +175,6 @@ chol_panel_kernel(double* __restrict__ A, int ld, int k, const double* __restric
     dmma_tile_tn(Aik, ld, M, NB, NB / GP_BK, acc, smem);        // C[m][n] = sum_c A_ik[m][c] M[n][c]
     // in place: every thread's loads of A_ik finished inside the mainloop (its last __syncthreads)
     block_gemm_epilogue(acc, Aik, ld, nullptr, 0, 0);
-    (void)tmp;
 }
 
 // trailing update: A_ij -= L_ik L_jk^T for k < j <= i < nb; blockIdx.x enumerates the (i, j) pairs
@@ -360,17 +359,24 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     else gp_build_k_kernel<2><<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(x_train, n_train, n_pad, length_scale, noise_level, jitter, x_scaled_out, K);
 
     const size_t diag_smem = kDiagSmemBytes;
-    cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem);
-    cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
-    cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
-    cudaFuncSetAttribute(inv_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
-    cudaFuncSetAttribute(inv_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+    static bool attr[kMaxDevices] = {};                   // opt-in shared-memory sizes, once per device
+    const int dev = current_device();
+    if (!attr[dev]) {
+        cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem);
+        cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(inv_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(inv_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(gp_lml_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        cudaFuncSetAttribute(gp_lml_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+        attr[dev] = true;
+    }
 
     for (int k = 0; k < nb; ++k) {
         chol_diag_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(K, ld, k * NB, Mall + (int64_t)k * NB * NB, info);
         const int r = nb - k - 1;
         if (r > 0) {
-            chol_panel_kernel<<<r, 256, kDmmaSmemBytes, s>>>(K, ld, k, Mall + (int64_t)k * NB * NB, tmp);
+            chol_panel_kernel<<<r, 256, kDmmaSmemBytes, s>>>(K, ld, k, Mall + (int64_t)k * NB * NB);
             chol_update_kernel<<<r * (r + 1) / 2, 256, kDmmaSmemBytes, s>>>(K, ld, k, nb);
         }
     }
@@ -387,10 +393,8 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     const int n_partial = nb * (nb + 1) / 2;
     if (grad_out) {                                       // needs WT with its identity padding, alpha, scaled inputs
         if (dim == 1) {
-            cudaFuncSetAttribute(gp_lml_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
             gp_lml_grad_kernel<1><<<n_partial, 256, kDmmaSmemBytes, s>>>(WT, ld, nb, n_train, x_scaled_out, alpha_out, partial);
         } else {
-            cudaFuncSetAttribute(gp_lml_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
             gp_lml_grad_kernel<2><<<n_partial, 256, kDmmaSmemBytes, s>>>(WT, ld, nb, n_train, x_scaled_out, alpha_out, partial);
         }
     }

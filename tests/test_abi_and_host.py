@@ -34,25 +34,41 @@ def test_library_exports_every_declared_symbol():
     assert lib.mr_actor_param_count() == 5 * 64 + 5 * 64 + 64 * 64 + 5 * 64 + 64 * 2 + 2
 
 
+def lib_counts():
+    from mr_rl_b200 import _lib
+    lib = _lib.load()
+    return lib.mr_actor_param_count(), lib.mr_critic_param_count()
+
+
 def test_ctypes_structs_match_c_layout(tmp_path):
     from mr_rl_b200 import _lib
     prog = tmp_path / "sizes.c"
-    structs = ["mr_sim_params", "mr_env_state", "mr_noise", "mr_time_table", "mr_step_out", "mr_rollout_io", "mr_gp_model"]
+    structs = ["mr_sim_params", "mr_env_state", "mr_noise", "mr_time_table", "mr_step_out", "mr_rollout_io", "mr_gp_model",
+               "mr_host_step_io", "mr_ddpg_state", "mr_replay", "mr_ddpg_hyper"]
     body = "\n".join(f'printf("{s} %zu\\n", sizeof({s}));' for s in structs)
     prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{HEADER}"\nint main(void){{{body}\n'
                     'printf("off_action_high %zu\\n", offsetof(mr_sim_params, action_high));\n'
                     'printf("off_stats %zu\\n", offsetof(mr_rollout_io, stats));\n'
-                    'printf("off_noise %zu\\n", offsetof(mr_gp_model, noise_level));return 0;}\n')
+                    'printf("off_noise %zu\\n", offsetof(mr_gp_model, noise_level));\n'
+                    'printf("off_skip %zu\\n", offsetof(mr_step_out, skip_goal_rows));\n'
+                    'printf("off_bound %zu\\n", offsetof(mr_ddpg_hyper, action_bound));\n'
+                    'printf("off_cap %zu\\n", offsetof(mr_replay, capacity));return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(prog), "-o", str(exe)], check=True)   # the header is plain C
     out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
     py = {"mr_sim_params": _lib.SimParams, "mr_env_state": _lib.EnvState, "mr_noise": _lib.Noise, "mr_time_table": _lib.TimeTable,
-          "mr_step_out": _lib.StepOut, "mr_rollout_io": _lib.RolloutIO, "mr_gp_model": _lib.GPModel}
+          "mr_step_out": _lib.StepOut, "mr_rollout_io": _lib.RolloutIO, "mr_gp_model": _lib.GPModel,
+          "mr_host_step_io": _lib.HostStepIO, "mr_ddpg_state": _lib.DDPGState, "mr_replay": _lib.Replay,
+          "mr_ddpg_hyper": _lib.DDPGHyper}
     for name, cls in py.items():
         assert C.sizeof(cls) == int(out[name]), name
     assert _lib.SimParams.action_high.offset == int(out["off_action_high"])
     assert _lib.RolloutIO.stats.offset == int(out["off_stats"])
     assert _lib.GPModel.noise_level.offset == int(out["off_noise"])
+    assert _lib.StepOut.skip_goal_rows.offset == int(out["off_skip"])
+    assert _lib.DDPGHyper.action_bound.offset == int(out["off_bound"])
+    assert _lib.Replay.capacity.offset == int(out["off_cap"])
+    assert lib_counts() == (5186, 2849)
 
 
 def test_default_params_mirror_reference_constants():
