@@ -303,7 +303,9 @@ class VecMREnv:
     # Host-buffer step strategy.  Measured at 2^20 envs (fp64, sigma = 1): staged 1 / 2 / 4 / 8 chunks 1.01 / 0.91 / 0.91 /
     # 0.99 ms (each of the 5 D2H pieces per chunk costs a few us of DMA set-up); direct 0.82 ms.  Tried and dropped: a
     # hybrid (copy-engine H2D of the actions in chunks + kernel writing straight to the host) 0.89 / 0.93 / 0.97 ms with
-    # 2 / 4 / 8 chunks — the smaller launches lose more than the DMA read gains.
+    # 2 / 4 / 8 chunks — the smaller launches lose more than the DMA read gains; and a "streamed" variant (ONE kernel whose
+    # loader waits on per-chunk arrival flags while the copy engine delivers the actions) 0.88 / 0.91 / 1.03 ms with
+    # 4 / 8 / 16 chunks: correct, but DMA reads + SM writes to the host interfere more than SM reads + SM writes do.
     host_mode = "direct"
     host_chunks = 2
 
