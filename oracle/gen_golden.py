@@ -187,9 +187,38 @@ def gen_learn():
     print("learn: a0", a0, "D", lm.Dx, lm.Dy, "n", len(lm.X), "draws", used1, used2)
 
 
+def gen_learn_fit():
+    """The GPR fit itself, through the reference's LearningModule with its own settings (5 optimiser restarts,
+    Learning_module.py:28-33,122-123) on the trajectory of learn.npz.  The restarts draw from numpy's global RandomState,
+    seeded here; recorded: the fitted hyper-parameters, log marginal likelihoods, posterior on a grid and predict()."""
+    mods = lr.load()
+    LM = mods["Learning_module"]
+    import contextlib, io
+    g = np.load(os.path.join(GOLDEN_DIR, "learn.npz"))
+    seed = 123
+    with contextlib.redirect_stdout(io.StringIO()):
+        lm = LM.LearningModule()
+        lm.estimateDisturbance(g["px_idle"], g["py_idle"], g["t_idle"])
+        np.random.seed(seed)
+        a0 = lm.learn(g["px"].copy(), g["py"].copy(), g["alpha"].copy(), g["time"].copy(), g["circ"])
+        grid = np.linspace(-3.0, 3.0, 97)
+        mx, sx = lm.gprX.predict(grid.reshape(-1, 1), return_std=True)
+        my, sy = lm.gprY.predict(grid.reshape(-1, 1), return_std=True)
+        freq = g["circ"][0, 0]
+        ang = np.linspace(0.1, 2 * np.pi - 0.1, 12)
+        vd = a0 * freq * np.stack([np.cos(ang), np.sin(ang)], 1)
+        pred = np.array([[float(np.ravel(v)[0]) for v in lm.predict(v_)] for v_ in vd])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "learn_fit.npz"), versions=versions(), seed=seed, a0=a0,
+                        theta_x=lm.gprX.kernel_.theta, theta_y=lm.gprY.kernel_.theta,
+                        lml_x=lm.gprX.log_marginal_likelihood_value_, lml_y=lm.gprY.log_marginal_likelihood_value_,
+                        grid=grid, grid_mx=mx, grid_sx=sx, grid_my=my, grid_sy=sy, vd=vd, predict=pred)
+    print("learn_fit: theta", lm.gprX.kernel_.theta, lm.gprY.kernel_.theta, "lml", lm.gprX.log_marginal_likelihood_value_)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     gen_single()
     gen_batch()
     gen_gp()
     gen_learn()
+    gen_learn_fit()

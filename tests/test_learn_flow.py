@@ -132,3 +132,35 @@ def test_learn_preprocess_argument_errors():
     assert b"workspace" in lib.mr_last_error()
     assert lib.mr_learn_preprocess(p, p, p, 100, 14, 0, 0.0, 0.0, p, 1.0, 20, p, p, p, p, p, p, p, 1 << 20, None) != 0
     assert b"n_valid" in lib.mr_last_error()
+
+
+@pytest.mark.gpu
+def test_device_learn_reproduces_the_live_reference_fit(golden_learn):
+    """LearningModule(fit="device").learn against the live reference's learn() with its own settings (5 restarts of
+    sklearn's optimiser, restart points from numpy's global RandomState seeded identically): fitted hyper-parameters,
+    log marginal likelihoods, the posterior on a grid and predict() (Learning_module.py:28-33,122-123,198-224;
+    golden made by oracle/gen_golden.py:gen_learn_fit)."""
+    import torch
+    from mr_rl_b200 import LearningModule
+    g, f = golden_learn, Golden("learn_fit.npz")
+    lm = LearningModule(device="cuda:0", fit="device")
+    lm.estimateDisturbance(g["px_idle"], g["py_idle"], g["t_idle"])
+    np.random.seed(int(f["seed"]))
+    a0 = lm.learn(g["px"].copy(), g["py"].copy(), g["alpha"].copy(), g["time"].copy(), g["circ"])
+    assert rel_err(a0, f["a0"]) < 1e-9
+    # the optimum: same basin, converged to the optimiser's own tolerance (noise_level sits near its lower bound here,
+    # K is conditioned ~1e5, so theta agrees to ~1e-3 and the likelihood to ~1e-7)
+    assert np.allclose(lm.gprX.kernel_.theta, f["theta_x"], atol=5e-3) and np.allclose(lm.gprY.kernel_.theta, f["theta_y"], atol=5e-3)
+    assert abs(lm.gprX.log_marginal_likelihood_value_ - f["lml_x"]) < 1e-6 * abs(f["lml_x"])
+    assert abs(lm.gprY.log_marginal_likelihood_value_ - f["lml_y"]) < 1e-6 * abs(f["lml_y"])
+    q = torch.as_tensor(f["grid"], device="cuda:0")
+    mx, my, sx, sy = lm.gp_batch(q, True)
+    scale = np.abs(f["grid_mx"]).max()
+    assert np.abs(mx.cpu().numpy() - f["grid_mx"]).max() < 1e-3 * scale and np.abs(my.cpu().numpy() - f["grid_my"]).max() < 1e-3 * scale
+    inside = np.abs(f["grid"]) < 2.8                     # away from the edge of the data the std is well determined
+    assert np.allclose(sx.cpu().numpy()[inside], f["grid_sx"][inside], rtol=2e-2, atol=1e-5)
+    alpha, pmx, pmy, psx, psy = lm.predict_batch(f["vd"])
+    ref = f["predict"]
+    d_alpha = np.angle(np.exp(1j * (alpha.cpu().numpy() - ref[:, 0])))
+    assert np.abs(d_alpha).max() < 2e-3
+    assert np.abs(pmx.cpu().numpy() - ref[:, 1]).max() < 2e-3 * scale and np.abs(pmy.cpu().numpy() - ref[:, 2]).max() < 2e-3 * scale
