@@ -1,8 +1,11 @@
 """TEST INFRASTRUCTURE — CPU restatement of the reference's DDPG learner (RL/MR_ddpg.py), plain torch + autograd.
 
-PARITY UNPINNED: the reference learner is TensorFlow-1 / tflearn code and neither package exists in this image,
-so this restatement cannot be checked against the reference running here; it follows the published semantics of
-the ops the reference calls, each cited below.  Only tests/ may import it.
+PARITY UNPINNED for the networks and optimisers: the reference learner is TensorFlow-1 / tflearn code and neither
+package exists in this image, so that part of the restatement cannot be checked against the reference running here;
+it follows the published semantics of the ops the reference calls, each cited below.  PINNED: the two TensorFlow-free
+classes — OUNoise and ReplayBuffer are imported from the reference tree behind stubs (oracle/live_reference.load_ddpg)
+and their behaviour is recorded in tests/golden/ddpg_host.npz (oracle/gen_golden.py:gen_ddpg_host).
+Only tests/ may import this module.
 
   networks           ActorNetwork.create_actor_network   RL/MR_ddpg.py:124-139
                      CriticNetwork.create_critic_network RL/MR_ddpg.py:202-222 (action enters the 2nd hidden layer;

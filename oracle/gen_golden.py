@@ -215,6 +215,26 @@ def gen_learn_fit():
     print("learn_fit: theta", lm.gprX.kernel_.theta, lm.gprY.kernel_.theta, "lml", lm.gprX.log_marginal_likelihood_value_)
 
 
+def gen_ddpg_host():
+    """The two TensorFlow-free classes of RL/MR_ddpg.py run as they are: OUNoise on a fixed normal stream, and
+    ReplayBuffer's ring / sampling behaviour (which transitions survive an overflow, batches without repeats)."""
+    dd = lr.load_ddpg()
+    z = np.random.default_rng(41).standard_normal(2 * 40)
+    ou = dd.OUNoise(mu=np.zeros(2))
+    with lr.patched_noise(z) as ns:
+        xs = np.array([ou() for _ in range(40)])
+        assert ns.cursor == 80
+    rb = dd.ReplayBuffer(8, 0)
+    for k in range(11):                                   # transition k: s = [k]*5, a = [k, -k], r = 10 + k, t = k % 3 == 0
+        rb.add(np.full(5, float(k)), np.array([float(k), -float(k)]), 10.0 + k, k % 3 == 0, np.full(5, k + 0.5))
+    kept = np.array([e[2] - 10.0 for e in rb.buffer])     # ids of the transitions still stored, oldest first
+    s_b, a_b, r_b, t_b, s2_b = rb.sample_batch(4)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "ddpg_host.npz"), versions=versions(), ou_z=z, ou_x=xs,
+                        ou_params=np.array([ou.theta, ou.sigma, ou.dt]), kept=kept, size=rb.size(),
+                        batch_ids=r_b - 10.0, batch_s=s_b, batch_t=np.asarray(t_b, dtype=np.float64))
+    print("ddpg_host: OU last", xs[-1], "kept", kept, "batch", r_b - 10.0)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     gen_single()
@@ -222,3 +242,4 @@ if __name__ == "__main__":
     gen_gp()
     gen_learn()
     gen_learn_fit()
+    gen_ddpg_host()

@@ -113,6 +113,26 @@ def load():
     return _loaded
 
 
+def load_ddpg():
+    """RL/MR_ddpg.py imported from the reference tree behind stubs for tensorflow / tflearn (absent from the image):
+    its ReplayBuffer (:16-56) and OUNoise (:58-78) are plain Python / numpy and run as they are; the TensorFlow
+    networks cannot (so the learner's graph stays unpinned, see oracle/ddpg_oracle.py)."""
+    if "MR_ddpg" in _loaded:
+        return _loaded["MR_ddpg"]
+    load()
+    for name in ("tensorflow", "tflearn", "tflearn.layers", "tflearn.layers.normalization", "tflearn.activations",
+                 "tflearn.initializations"):
+        if name not in sys.modules:
+            sys.modules[name] = _StubModule(name)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("MR_ddpg", os.path.join(REFERENCE_ROOT, "RL", "MR_ddpg.py"))
+    mod = importlib.util.module_from_spec(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mod)
+    _loaded["MR_ddpg"] = mod
+    return mod
+
+
 class NoiseStream:
     """Replacement for ``numpy.random.normal`` popping from a fixed z-stream."""
 

@@ -165,3 +165,27 @@ def test_vectorised_training_loop_runs_and_learns_something():
     # the critic learns the scale of the returns: its loss drops from the first updates
     assert log[-5:, 1].mean() < log[:5, 1].mean()
     env.check_status()
+
+
+def test_replay_ring_keeps_what_the_reference_deque_keeps():
+    """The same 11 transitions pushed through RL/MR_ddpg.py's ReplayBuffer(8) (golden ddpg_host.npz) and through the
+    device ring: the same transitions survive the overflow, the size saturates at the capacity."""
+    from conftest import Golden
+    from mr_rl_b200.ddpg import OUNoise, ReplayBuffer
+    g = Golden("ddpg_host.npz")
+    rb = ReplayBuffer(8, 0, device="cuda:0")
+    ids = np.arange(11, dtype=np.float64)
+    for lo, hi in ((0, 4), (4, 8), (8, 11)):
+        k = torch.as_tensor(ids[lo:hi], device="cuda:0")
+        obs = k.repeat(5, 1).contiguous()                              # SoA rows [5][m]
+        rb.add(obs, torch.stack([k, -k], 1).contiguous(), 10.0 + k, (k % 3 == 0).to(torch.uint8), (obs + 0.5).contiguous(), hi - lo)
+    assert rb.size() == int(g["size"])
+    stored = np.sort(rb.r.cpu().numpy().astype(np.float64) - 10.0)
+    assert np.array_equal(stored, np.sort(g["kept"]))
+    row = {float(r - 10.0): i for i, r in enumerate(rb.r.cpu().numpy())}
+    i9 = row[9.0]
+    assert rb.s.cpu()[i9].tolist() == [9.0] * 5 and rb.s2.cpu()[i9].tolist() == [9.5] * 5
+    assert rb.a.cpu()[i9].tolist() == [9.0, -9.0] and rb.d.cpu()[i9] == 1.0
+    # the device OU process uses the reference's default parameters
+    ou = OUNoise(4, device="cuda:0")
+    assert (ou.theta, ou.sigma, ou.dt) == tuple(g["ou_params"])

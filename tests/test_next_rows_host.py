@@ -73,3 +73,16 @@ def test_device_gpr_kernel_parameterisation_matches_sklearn():
     sk2 = RBF(0.3, (1e-2, 10.0)) + WhiteKernel(0.02)
     assert np.allclose(_RBFWhite(0.3, 0.02, (1e-2, 10.0), (1e-5, 1e5)).theta, sk2.theta)
     assert "RBF(length_scale=0.3)" in repr(_RBFWhite(0.3, 0.02, (1e-2, 10.0), (1e-5, 1e5)))
+
+
+def test_ou_oracle_matches_the_reference_class():
+    """oracle.OUNoise against RL/MR_ddpg.py's own OUNoise run on a fixed normal stream (golden ddpg_host.npz)."""
+    from conftest import Golden
+    from oracle.ddpg_oracle import OUNoise
+    g = Golden("ddpg_host.npz")
+    theta, sigma, dt = g["ou_params"]
+    ou = OUNoise((2,), sigma=sigma, theta=theta, dt=dt)
+    z = g["ou_z"].reshape(-1, 2)
+    xs = np.array([ou(z[k]).numpy().copy() for k in range(len(z))])
+    assert np.allclose(xs, g["ou_x"], rtol=1e-14, atol=1e-16)
+    assert (theta, sigma, dt) == (0.15, 0.3, 1e-2)                  # the defaults our device OUNoise mirrors
