@@ -215,6 +215,46 @@ def gen_learn_fit():
     print("learn_fit: theta", lm.gprX.kernel_.theta, lm.gprY.kernel_.theta, "lml", lm.gprX.log_marginal_likelihood_value_)
 
 
+def gen_learn_2d():
+    """Learning_module_2d.py through the reference's run_sim: idle run -> estimateDisturbance, a circle driven at a
+    varying frequency (main_2d.py:149-158) -> learn(px, py, alpha, freq, time); then error() and predict()."""
+    mods = lr.load()
+    LM2, utils = lr.load_2d(), mods["utils"]
+    import contextlib, io
+    a0_def, dt, sigma = 1.5, 0.030, 0.3
+    idle = np.zeros((60, 3)); idle[:, 2] = np.arange(60) * dt
+    T = 300
+    act = np.zeros((T, 3)); act[:, 1] = np.tile(np.linspace(-np.pi, np.pi, 100), 3)
+    act[:, 0] = (np.cos(np.arange(T) / 5) + 1) / 2 * 4.9 + 0.1; act[:, 2] = np.arange(T) * dt
+    z1 = np.random.default_rng(51).standard_normal(60 * 1500)
+    z2 = np.random.default_rng(52).standard_normal(T * 1500)
+    seed = 77
+    with contextlib.redirect_stdout(io.StringIO()):
+        with lr.patched_noise(z1):
+            px_i, py_i, _, t_i, _ = utils.run_sim(idle, init_pos=np.array([0, 0]), noise_var=sigma, a0=a0_def, is_mismatched=True)
+        with lr.patched_noise(z2):
+            px, py, al, tm, fr = utils.run_sim(act, init_pos=np.array([0, 0]), noise_var=sigma, a0=a0_def, is_mismatched=True)
+        lm = LM2.LearningModule()
+        lm.estimateDisturbance(px_i, py_i, t_i)
+        np.random.seed(seed)
+        a0 = lm.learn(px.copy(), py.copy(), np.asarray(al, float).copy(), np.asarray(fr, float).copy(), np.asarray(tm, float).copy())
+        lm.a0 = a0                                        # the reference's learn() returns a0 without storing it
+        ang = np.linspace(-2.5, 2.5, 6)
+        vd = np.stack([a0 * 2.5 * np.cos(ang), a0 * 2.5 * np.sin(ang)], 1)
+        err = np.array([[float(np.ravel(v)[0]) for v in lm.error(v_)] for v_ in vd])
+        pred = []
+        for v_ in vd:
+            X, mx, my, sx, sy = lm.predict(v_)
+            pred.append([X[0], X[1], float(mx[0]), float(my[0]), float(sx[0]), float(sy[0])])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "learn_2d.npz"), versions=versions(), seed=seed, px_idle=px_i, py_idle=py_i,
+                        t_idle=t_i, px=px, py=py, alpha=np.asarray(al, float), freq=np.asarray(fr, float), time=np.asarray(tm, float),
+                        Dx=lm.Dx, Dy=lm.Dy, a0=a0, X=lm.X, Yx=lm.Yx, Yy=lm.Yy, theta_x=lm.gprX.kernel_.theta,
+                        theta_y=lm.gprY.kernel_.theta, lml_x=lm.gprX.log_marginal_likelihood_value_,
+                        lml_y=lm.gprY.log_marginal_likelihood_value_, vd=vd, error=err, predict=np.array(pred))
+    print("learn_2d: a0", a0, "theta", lm.gprX.kernel_.theta, lm.gprY.kernel_.theta, "n", len(lm.X))
+    print("   predict", np.array(pred)[:2])
+
+
 def gen_ddpg_host():
     """The two TensorFlow-free classes of RL/MR_ddpg.py run as they are: OUNoise on a fixed normal stream, and
     ReplayBuffer's ring / sampling behaviour (which transitions survive an overflow, batches without repeats)."""
@@ -242,4 +282,5 @@ if __name__ == "__main__":
     gen_gp()
     gen_learn()
     gen_learn_fit()
+    gen_learn_2d()
     gen_ddpg_host()

@@ -113,6 +113,16 @@ def load():
     return _loaded
 
 
+def load_2d():
+    """Learning_module_2d.py (the (alpha, f) variant of the disturbance GPs) from the reference tree."""
+    if "Learning_module_2d" not in _loaded:
+        load()
+        import importlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            _loaded["Learning_module_2d"] = importlib.import_module("Learning_module_2d")
+    return _loaded["Learning_module_2d"]
+
+
 def load_ddpg():
     """RL/MR_ddpg.py imported from the reference tree behind stubs for tensorflow / tflearn (absent from the image):
     its ReplayBuffer (:16-56) and OUNoise (:58-78) are plain Python / numpy and run as they are; the TensorFlow
