@@ -333,15 +333,13 @@ def run_ours(args):
             # BASELINE configs[3]: GP disturbance model, 2000 training points, 262144 queries (both GPs, mean + std)
             try:
                 from mr_rl_b200 import DeviceGP
-                from oracle import mr_oracle as mo
                 rng = np.random.default_rng(0)
                 X = np.sort(rng.uniform(-np.pi, np.pi, 2000))
                 yx = 0.2 + 0.5 * np.cos(X + 0.3) + 0.09 * rng.standard_normal(2000)
                 yy = -0.1 + 0.4 * np.sin(X - 0.2) + 0.09 * rng.standard_normal(2000)
                 gps = []
                 for yv, ls in ((yx, 0.2), (yy, 0.25)):
-                    m = mo.fit_fixed_gp(X, yv, ls, 0.008)            # host fit (sklearn's job in the reference)
-                    gps.append(DeviceGP(m.X_train, m.alpha, m.L, m.length_scale, m.noise_level, device=dev))
+                    gps.append(DeviceGP.fit(X, yv, ls, 0.008, device=dev))     # fixed kernels, fitted on the device
                 q = env.last_pos[:262144, 1].contiguous() * 0 + torch.rand(262144, device=dev, dtype=torch.float64) * 6.28 - 3.14
                 for gp_ in gps:
                     gp_.predict(q, True)
@@ -365,6 +363,43 @@ def run_ours(args):
                 del gps
             except Exception as ex:                                  # never let a side number break the headline
                 extras["config3_gp_262k_queries_2k_train"] = {"error": str(ex)[:160]}
+            # the GPR fit with sklearn's 5-restart search driven from the host, the DDPG learner
+            try:
+                import time as _time
+                from mr_rl_b200 import DDPGLearner, DeviceGPR, OUNoise, ReplayBuffer, VecMREnv as _Env
+                from mr_rl_b200.ddpg import train as _train
+                rng = np.random.default_rng(1)
+                Xf = np.sort(rng.uniform(-np.pi, np.pi, size=(1970, 1)), axis=0)
+                yf = 0.8 * np.sin(2 * Xf[:, 0]) + 0.3 * np.cos(Xf[:, 0]) + 0.15 * rng.standard_normal(1970)
+                DeviceGPR(n_restarts_optimizer=0, random_state=3, device=dev).fit(Xf[:256], yf[:256])
+                torch.cuda.synchronize()
+                t0 = _time.perf_counter()
+                gpr = DeviceGPR(n_restarts_optimizer=5, random_state=3, device=dev).fit(Xf, yf)
+                torch.cuda.synchronize()
+                t_fit = _time.perf_counter() - t0
+                rb = ReplayBuffer(10000, 0, device=dev)
+                env_t = _Env(4096, device=dev, noise="philox", seed=0, auto_reset=True)
+                learner, ou = DDPGLearner(device=dev), OUNoise(4096, device=dev)
+                _train(env_t, learner, ou, min_batch=64, steps=20, replay=rb)
+                torch.cuda.synchronize()
+                t0 = _time.perf_counter()
+                _train(env_t, learner, ou, min_batch=64, steps=200, replay=rb)
+                torch.cuda.synchronize()
+                t_it = (_time.perf_counter() - t0) / 200
+                ev0.record()
+                for _ in range(50):
+                    learner.update(rb, 64)
+                ev1.record()
+                torch.cuda.synchronize()
+                extras["next_rows"] = {
+                    "gpr_search_n1970_5_restarts_s": t_fit, "gpr_objective_evals": gpr.n_objective_evals,
+                    "gpr_theta": [float(v) for v in gpr.kernel_.theta],
+                    "ddpg_update_batch64_us": ev0.elapsed_time(ev1) / 50 * 1e3,
+                    "ddpg_train_iteration_4096_envs_ms": t_it * 1e3,
+                    "note": "mr_gp_fit per objective evaluation; one mr_ddpg_update launch per learner update"}
+                del env_t, learner, rb
+            except Exception as ex:
+                extras["next_rows"] = {"error": str(ex)[:160]}
         barrier()
 
     if rank == 0:
