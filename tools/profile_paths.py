@@ -7,7 +7,6 @@ import numpy as np
 import torch
 
 from mr_rl_b200 import DeviceGP, VecMREnv, init_actor, pack_actor
-from oracle import mr_oracle as mo
 
 n = int(os.environ.get("PROF_ENVS", 1 << 18))
 K = int(os.environ.get("PROF_K", 16))
@@ -29,8 +28,7 @@ env.check_status()
 rng = np.random.default_rng(0)
 X = np.sort(rng.uniform(-np.pi, np.pi, ntr))
 y = 0.2 + 0.5 * np.cos(X + 0.3) + 0.09 * rng.standard_normal(ntr)
-m = mo.fit_fixed_gp(X, y, 0.2, 0.008)
-gp = DeviceGP(m.X_train, m.alpha, m.L, m.length_scale, m.noise_level, device="cuda:0")
+gp = DeviceGP.fit(X, y, 0.2, 0.008, device="cuda:0")
 q = torch.rand(nq, device="cuda:0", dtype=torch.float64) * 6.28 - 3.14
 for _ in range(2):
     mean, std = gp.predict(q, True)
