@@ -151,10 +151,11 @@ def test_ou_noise_follows_the_reference_recurrence():
     assert torch.equal(act2, x1)
 
 
-def test_vectorised_training_loop_runs_and_learns_something():
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_vectorised_training_loop_runs_and_learns_something(dt):
     from mr_rl_b200 import VecMREnv
     from mr_rl_b200.ddpg import DDPGLearner, OUNoise, ReplayBuffer, train
-    env = VecMREnv(256, device="cuda:0", noise="philox", seed=0, auto_reset=True)
+    env = VecMREnv(256, device="cuda:0", dtype=dt, noise="philox", seed=0, auto_reset=True)
     learner = DDPGLearner(device="cuda:0", seed=0)
     before = learner.actor.clone()
     rb = ReplayBuffer(10000, 0, device="cuda:0")
@@ -165,6 +166,10 @@ def test_vectorised_training_loop_runs_and_learns_something():
     # the critic learns the scale of the returns: its loss drops from the first updates
     assert log[-5:, 1].mean() < log[:5, 1].mean()
     env.check_status()
+    # what went into the ring is what the env produced: states are [x, y, 0, 0, d] rows, rewards the constant 10
+    s = rb.s.cpu().numpy()
+    assert np.allclose(s[:, 4], np.hypot(s[:, 0], s[:, 1]), rtol=1e-6) and np.all(s[:, 2:4] == 0)
+    assert np.all(rb.r.cpu().numpy() == 10.0) and set(np.unique(rb.d.cpu().numpy())) <= {0.0, 1.0}
 
 
 def test_replay_ring_keeps_what_the_reference_deque_keeps():
