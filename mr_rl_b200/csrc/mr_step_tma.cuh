@@ -18,7 +18,9 @@ namespace mr {
 #define MR_STAGES_IN 3
 #endif
 // envs per tile == threads per CTA.  Measured on B200 (2^20 envs): fp64 128 -> 30.9 us, 256 -> 32.2 us;
-// fp32 128 -> 27.6 us, 256 -> 25.6 us.
+// fp32 128 -> 27.6 us, 256 -> 25.6 us.  Later, with generated noise (sigma 0 / 1, fp64): 128 -> 29.1 / 32.8 us,
+// 64 -> 28.8 / 35.6 us, 32 (one warp per CTA, no CTA barrier needed) -> 30.8 / 36.3 us; and issuing the loads from
+// warp 0 and the stores from warp 1 (to halve the issuing warp's extra work): 28.6 / 33.8 us — no gain.
 #ifdef MR_TILE
 template <class T> struct TileOf { static constexpr int value = MR_TILE; };
 #else
