@@ -342,7 +342,18 @@ int mr_ou_noise_add(double* ou_state, void* actions, const uint8_t* reset_mask, 
  * step (Adam on d scaled_out/d theta . (-dQ/da) / batch), soft target updates.  update_index = 1, 2, ... is Adam's
  * step count.  info_out (2 floats, may be NULL): critic loss and mean Q before the update. */
 int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
-                   uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, float* info_out, void* stream);
+                   uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, float* info_out, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* Minibatches above 256 samples run data-parallel over one CTA per SM (four launches: critic gradients, critic Adam,
+ * actor gradients, actor Adam; per-CTA partial gradients summed in a fixed order) when a workspace of
+ * mr_ddpg_workspace_bytes(batch) bytes is passed; without one (NULL) the single-CTA kernel handles up to 4096 samples.
+ * Sampling in that path is mr_replay_sample's. */
+int64_t mr_ddpg_workspace_bytes(int32_t batch);
+
+/* `batch` distinct ring rows out of the first `count`, uniformly at random (random.sample, RL/MR_ddpg.py:43-46), in
+ * parallel: a keyed bijection (4-round Feistel network, keys from Philox(seed; update_index)) of a power-of-four domain
+ * cycle-walked into [0, count).  indices_out: device int64 [batch]. */
+int mr_replay_sample(int64_t count, int32_t batch, uint64_t seed, int64_t update_index, int64_t* indices_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,8 @@
 // The networks are tiny (5-64-64-2 and 5-64-(+2)-32-1) and the reference batch is 64, so an update is latency
 // bound, not throughput bound: one CTA keeps a 64-sample tile of every activation in shared memory and walks
 // the phases with CTA barriers; the networks a phase reads are staged in shared memory (44 KB).  Larger batches loop over
-// 64-sample tiles and accumulate the weight gradients.  fp32 throughout, like the reference's TensorFlow graph.
+// 64-sample tiles and accumulate the weight gradients; above 256 samples a data-parallel variant (one CTA per SM, see
+// below) takes over.  fp32 throughout, like the reference's TensorFlow graph.
 //
 // Batch norm: the reference never switches tflearn into training mode, so batch_normalization is the inference
 // transform gamma * (x - moving_mean) / sqrt(moving_var + 1e-5) + beta with trainable gamma / beta and frozen
@@ -34,7 +35,9 @@ constexpr int kCriticParams = kC_Bo + 1;                    // 2849 floats
 
 constexpr int kTile = 64;                                   // samples per shared-memory tile
 constexpr int kLd64 = 65, kLd32 = 33;                       // padded rows: lanes over samples hit distinct banks
-constexpr int kMaxBatch = 4096;
+constexpr int kMaxBatch = 4096;                             // single-CTA kernel (indices live in shared memory)
+constexpr int kWideBatch = 256;                             // above this the data-parallel kernels take over (if a workspace is given)
+constexpr int kMaxCtas = 256;
 #ifndef MR_DDPG_THREADS
 #define MR_DDPG_THREADS 1024                                // one CTA; the phases are short loops over <= 4160 work items
 #endif
@@ -238,6 +241,64 @@ __device__ void gather_tile(DdpgSmem& sm, int t0, int nb, const float* rs, const
     __syncthreads();
 }
 
+// ---- one 64-sample tile of the critic step: y = r + gamma Q'(s2, mu'(s2)) (1 - done); d/dtheta of mean (y - Q(s, a))^2 -----
+// expects the tile gathered in sm.S/A/R/D/S2 and sm.wA = target actor, sm.wCt = target critic, sm.wC = online critic
+__device__ void critic_tile(DdpgSmem& sm, int nb, bool acc, float inv_b, const DdpgHyper& h, float* gc, float& loss_acc, float& q_acc) {
+    const int tid = threadIdx.x;
+    actor_fwd_tile(sm, sm.S2, nb, sm.wA, h.bound0, h.bound1, sm.A2);
+    critic_fwd_tile(sm, sm.S2, sm.A2, nb, sm.wCt, sm.Q);
+    for (int s = tid; s < nb; s += blockDim.x) sm.Y[s] = sm.R[s] + h.gamma * sm.Q[s] * (1.f - sm.D[s]);
+    __syncthreads();
+    critic_fwd_tile(sm, sm.S, sm.A, nb, sm.wC, sm.Q);
+    for (int s = tid; s < nb; s += blockDim.x) sm.DQ[s] = 2.f * (sm.Q[s] - sm.Y[s]) * inv_b;
+    __syncthreads();
+    if (tid == 0) for (int s = 0; s < nb; ++s) { const float e = sm.Y[s] - sm.Q[s]; loss_acc += e * e; q_acc += sm.Q[s]; }
+    // output layer: gWo[j] = sum_s C2[s][j] dQ[s], gbo = sum_s dQ[s];  dC2 = dQ Wo (C2 > 0)
+    if (tid < 33) {
+        float v = 0.f;
+        if (tid < 32) { for (int s = 0; s < nb; ++s) v = fmaf(sm.C2[s * kLd32 + tid], sm.DQ[s], v); }
+        else          { for (int s = 0; s < nb; ++s) v += sm.DQ[s]; }
+        float* dst = gc + kC_Wo + tid;                    // kC_Bo = kC_Wo + 32
+        *dst = acc ? *dst + v : v;
+    }
+    for (int e = tid; e < nb * 32; e += blockDim.x) {
+        const int s = e >> 5, j = e & 31;
+        sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? sm.DQ[s] * sm.wC[kC_Wo + j] : 0.f;
+    }
+    __syncthreads();
+    fc_bwd_w(sm.C1, kLd64, sm.GC2, kLd32, nb, 64, 32, gc + kC_T1, nullptr, acc);          // t1.b: no gradient
+    fc_bwd_w(sm.A, 2, sm.GC2, kLd32, nb, 2, 32, gc + kC_T2, gc + kC_T2b, acc);
+    fc_bwd_x(sm.GC2, kLd32, nb, 32, sm.wC + kC_T1, 64, sm.G1, kLd64);
+    bn_relu_bwd(sm.G1, sm.ZC, sm.C1, nb, sm.wC + kC_Gc, sm.wC + kC_Mc, sm.wC + kC_Vc, gc + kC_Gc, gc + kC_Bec, acc);
+    fc_bwd_w(sm.S, 5, sm.G1, kLd64, nb, 5, 64, gc + kC_Wc1, gc + kC_Bc1, acc);
+}
+
+// ---- one tile of the actor step: ascend Q(s, mu(s)) through the critic in sm.wC; d scaled_out/d theta . (-dQ/da) / batch ------
+// expects sm.S gathered and sm.wA = online actor
+__device__ void actor_tile(DdpgSmem& sm, int nb, bool acc, float inv_b, const DdpgHyper& h, float* ga) {
+    const int tid = threadIdx.x;
+    actor_fwd_tile(sm, sm.S, nb, sm.wA, h.bound0, h.bound1, sm.A2);          // sm.T keeps tanh(u)
+    critic_fwd_tile(sm, sm.S, sm.A2, nb, sm.wC, nullptr);
+    for (int e = tid; e < nb * 32; e += blockDim.x) {
+        const int s = e >> 5, j = e & 31;
+        sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? sm.wC[kC_Wo + j] : 0.f;
+    }
+    __syncthreads();
+    fc_bwd_x(sm.GC2, kLd32, nb, 32, sm.wC + kC_T2, 2, sm.DU, 2);             // dQ/da
+    for (int e = tid; e < nb * 2; e += blockDim.x) {
+        const float th = sm.T[e];
+        sm.DU[e] = -sm.DU[e] * inv_b * ((e & 1) ? h.bound1 : h.bound0) * (1.f - th * th);
+    }
+    __syncthreads();
+    fc_bwd_w(sm.H2, kLd64, sm.DU, 2, nb, 64, 2, ga + kOffW3, ga + kOffB3, acc);
+    fc_bwd_x(sm.DU, 2, nb, 2, sm.wA + kOffW3, 64, sm.G2, kLd64);
+    bn_relu_bwd(sm.G2, sm.Z2, sm.H2, nb, sm.wA + kOffG2, sm.wA + kOffM2, sm.wA + kOffV2, ga + kOffG2, ga + kOffBe2, acc);
+    fc_bwd_w(sm.H1, kLd64, sm.G2, kLd64, nb, 64, 64, ga + kOffW2, ga + kOffB2, acc);
+    fc_bwd_x(sm.G2, kLd64, nb, 64, sm.wA + kOffW2, 64, sm.G1, kLd64);
+    bn_relu_bwd(sm.G1, sm.Z1, sm.H1, nb, sm.wA + kOffG1, sm.wA + kOffM1, sm.wA + kOffV1, ga + kOffG1, ga + kOffBe1, acc);
+    fc_bwd_w(sm.S, 5, sm.G1, kLd64, nb, 5, 64, ga + kOffW1, ga + kOffB1, acc);
+}
+
 __global__ void __launch_bounds__(kDdpgThreads, 1)
 ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float* __restrict__ critic, float* __restrict__ critic_t,
                    float* __restrict__ am, float* __restrict__ av, float* __restrict__ cm, float* __restrict__ cv,
@@ -286,32 +347,7 @@ ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float
         const int nb = min(kTile, batch - t * kTile);
         const bool acc = t > 0;
         gather_tile(sm, t * kTile, nb, rs, ra, rr, rd, rs2);
-        actor_fwd_tile(sm, sm.S2, nb, sm.wA, h.bound0, h.bound1, sm.A2);
-        critic_fwd_tile(sm, sm.S2, sm.A2, nb, sm.wCt, sm.Q);
-        for (int s = tid; s < nb; s += blockDim.x) sm.Y[s] = sm.R[s] + h.gamma * sm.Q[s] * (1.f - sm.D[s]);
-        __syncthreads();
-        critic_fwd_tile(sm, sm.S, sm.A, nb, sm.wC, sm.Q);
-        for (int s = tid; s < nb; s += blockDim.x) sm.DQ[s] = 2.f * (sm.Q[s] - sm.Y[s]) * inv_b;
-        __syncthreads();
-        if (tid == 0) for (int s = 0; s < nb; ++s) { const float e = sm.Y[s] - sm.Q[s]; loss_acc += e * e; q_acc += sm.Q[s]; }
-        // output layer: gWo[j] = sum_s C2[s][j] dQ[s], gbo = sum_s dQ[s];  dC2 = dQ Wo (C2 > 0)
-        if (tid < 33) {
-            float v = 0.f;
-            if (tid < 32) { for (int s = 0; s < nb; ++s) v = fmaf(sm.C2[s * kLd32 + tid], sm.DQ[s], v); }
-            else          { for (int s = 0; s < nb; ++s) v += sm.DQ[s]; }
-            float* dst = gc + kC_Wo + tid;                    // kC_Bo = kC_Wo + 32
-            *dst = acc ? *dst + v : v;
-        }
-        for (int e = tid; e < nb * 32; e += blockDim.x) {
-            const int s = e >> 5, j = e & 31;
-            sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? sm.DQ[s] * sm.wC[kC_Wo + j] : 0.f;
-        }
-        __syncthreads();
-        fc_bwd_w(sm.C1, kLd64, sm.GC2, kLd32, nb, 64, 32, gc + kC_T1, nullptr, acc);          // t1.b: no gradient
-        fc_bwd_w(sm.A, 2, sm.GC2, kLd32, nb, 2, 32, gc + kC_T2, gc + kC_T2b, acc);
-        fc_bwd_x(sm.GC2, kLd32, nb, 32, sm.wC + kC_T1, 64, sm.G1, kLd64);
-        bn_relu_bwd(sm.G1, sm.ZC, sm.C1, nb, sm.wC + kC_Gc, sm.wC + kC_Mc, sm.wC + kC_Vc, gc + kC_Gc, gc + kC_Bec, acc);
-        fc_bwd_w(sm.S, 5, sm.G1, kLd64, nb, 5, 64, gc + kC_Wc1, gc + kC_Bc1, acc);
+        critic_tile(sm, nb, acc, inv_b, h, gc, loss_acc, q_acc);
     }
     if (tid < 32) gc[kC_T1b + tid] = 0.f;
     __syncthreads();
@@ -327,26 +363,7 @@ ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float
         const int nb = min(kTile, batch - t * kTile);
         const bool acc = t > 0;
         gather_tile(sm, t * kTile, nb, rs, ra, rr, rd, rs2);
-        actor_fwd_tile(sm, sm.S, nb, sm.wA, h.bound0, h.bound1, sm.A2);          // sm.T keeps tanh(u)
-        critic_fwd_tile(sm, sm.S, sm.A2, nb, sm.wC, nullptr);
-        for (int e = tid; e < nb * 32; e += blockDim.x) {
-            const int s = e >> 5, j = e & 31;
-            sm.GC2[s * kLd32 + j] = sm.C2[s * kLd32 + j] > 0.f ? sm.wC[kC_Wo + j] : 0.f;
-        }
-        __syncthreads();
-        fc_bwd_x(sm.GC2, kLd32, nb, 32, sm.wC + kC_T2, 2, sm.DU, 2);             // dQ/da
-        for (int e = tid; e < nb * 2; e += blockDim.x) {
-            const float th = sm.T[e];
-            sm.DU[e] = -sm.DU[e] * inv_b * ((e & 1) ? h.bound1 : h.bound0) * (1.f - th * th);
-        }
-        __syncthreads();
-        fc_bwd_w(sm.H2, kLd64, sm.DU, 2, nb, 64, 2, ga + kOffW3, ga + kOffB3, acc);
-        fc_bwd_x(sm.DU, 2, nb, 2, sm.wA + kOffW3, 64, sm.G2, kLd64);
-        bn_relu_bwd(sm.G2, sm.Z2, sm.H2, nb, sm.wA + kOffG2, sm.wA + kOffM2, sm.wA + kOffV2, ga + kOffG2, ga + kOffBe2, acc);
-        fc_bwd_w(sm.H1, kLd64, sm.G2, kLd64, nb, 64, 64, ga + kOffW2, ga + kOffB2, acc);
-        fc_bwd_x(sm.G2, kLd64, nb, 64, sm.wA + kOffW2, 64, sm.G1, kLd64);
-        bn_relu_bwd(sm.G1, sm.Z1, sm.H1, nb, sm.wA + kOffG1, sm.wA + kOffM1, sm.wA + kOffV1, ga + kOffG1, ga + kOffBe1, acc);
-        fc_bwd_w(sm.S, 5, sm.G1, kLd64, nb, 5, 64, ga + kOffW1, ga + kOffB1, acc);
+        actor_tile(sm, nb, acc, inv_b, h, ga);
     }
     {
         const float t = (float)update_index;
@@ -364,6 +381,115 @@ ddpg_update_kernel(float* __restrict__ actor, float* __restrict__ actor_t, float
         critic_t[k] = h.tau * critic[k] + (1.f - h.tau) * critic_t[k];
     }
     if (tid == 0 && info_out) { info_out[0] = loss_acc * inv_b; info_out[1] = q_acc * inv_b; }
+}
+
+// =====================================================================================================================
+// Large minibatches: the same update, data-parallel over CTAs (one per SM).  Every CTA walks its share of the 64-sample
+// tiles and leaves its partial weight gradients in its own slab; a second kernel adds the slabs in a fixed order
+// (deterministic), applies Adam and the soft target update.  critic grads -> critic Adam -> actor grads (through the
+// updated critic) -> actor Adam: four launches instead of one, but 148x the arithmetic throughput.
+// =====================================================================================================================
+constexpr int kSlab = 5248;                                  // floats per CTA slab: >= max(kActorParams, kCriticParams) + 2
+
+__device__ void tile_indices(DdpgSmem& sm, const int64_t* idx, int t0, int nb) {
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) sm.idx[k] = (int)idx[t0 + k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kDdpgThreads, 1)
+ddpg_critic_grad_kernel(const float* __restrict__ actor_t, const float* __restrict__ critic, const float* __restrict__ critic_t,
+                        const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr,
+                        const float* __restrict__ rd, const float* __restrict__ rs2, const int64_t* __restrict__ idx,
+                        int batch, DdpgHyper h, float* __restrict__ slabs) {
+    extern __shared__ __align__(16) unsigned char ddpg_smem_raw[];
+    DdpgSmem& sm = *reinterpret_cast<DdpgSmem*>(ddpg_smem_raw);
+    load_weights(sm.wA, actor_t, kActorParams);
+    load_weights(sm.wCt, critic_t, kCriticParams);
+    load_weights(sm.wC, critic, kCriticParams);
+    float* gc = slabs + (int64_t)blockIdx.x * kSlab;
+    const float inv_b = 1.0f / (float)batch;
+    float loss_acc = 0.f, q_acc = 0.f;
+    const int n_tiles = (batch + kTile - 1) / kTile;
+    bool acc = false;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, acc = true) {
+        const int nb = min(kTile, batch - t * kTile);
+        tile_indices(sm, idx, t * kTile, nb);
+        gather_tile(sm, 0, nb, rs, ra, rr, rd, rs2);
+        critic_tile(sm, nb, acc, inv_b, h, gc, loss_acc, q_acc);
+    }
+    if (threadIdx.x < 32) gc[kC_T1b + threadIdx.x] = 0.f;
+    if (threadIdx.x >= 64 && threadIdx.x < 128) { gc[kC_Mc + threadIdx.x - 64] = 0.f; gc[kC_Vc + threadIdx.x - 64] = 0.f; }
+    if (threadIdx.x == 0) { gc[kCriticParams] = loss_acc; gc[kCriticParams + 1] = q_acc; }
+}
+
+__global__ void __launch_bounds__(kDdpgThreads, 1)
+ddpg_actor_grad_kernel(const float* __restrict__ actor, const float* __restrict__ critic,
+                       const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr,
+                       const float* __restrict__ rd, const float* __restrict__ rs2, const int64_t* __restrict__ idx,
+                       int batch, DdpgHyper h, float* __restrict__ slabs) {
+    extern __shared__ __align__(16) unsigned char ddpg_smem_raw[];
+    DdpgSmem& sm = *reinterpret_cast<DdpgSmem*>(ddpg_smem_raw);
+    load_weights(sm.wA, actor, kActorParams);
+    load_weights(sm.wC, critic, kCriticParams);
+    float* ga = slabs + (int64_t)blockIdx.x * kSlab;
+    const float inv_b = 1.0f / (float)batch;
+    const int n_tiles = (batch + kTile - 1) / kTile;
+    bool acc = false;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, acc = true) {
+        const int nb = min(kTile, batch - t * kTile);
+        tile_indices(sm, idx, t * kTile, nb);
+        gather_tile(sm, 0, nb, rs, ra, rr, rd, rs2);
+        actor_tile(sm, nb, acc, inv_b, h, ga);
+    }
+}
+
+// sum the CTA slabs in order, TF1 Adam, soft target update; one thread per parameter
+__global__ void ddpg_reduce_adam_kernel(float* __restrict__ p, float* __restrict__ p_target, float* __restrict__ m,
+                                        float* __restrict__ v, const float* __restrict__ slabs, int n_slabs, int n,
+                                        int frozen_lo0, int frozen_hi0, int frozen_lo1, int frozen_hi1, float lr_t, DdpgHyper h,
+                                        float inv_b, float* __restrict__ info_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && !((k >= frozen_lo0 && k < frozen_hi0) || (k >= frozen_lo1 && k < frozen_hi1))) {
+        float g = 0.f;
+        for (int c = 0; c < n_slabs; ++c) g += slabs[(int64_t)c * kSlab + k];
+        const float mk = h.beta1 * m[k] + (1.f - h.beta1) * g;
+        const float vk = h.beta2 * v[k] + (1.f - h.beta2) * g * g;
+        m[k] = mk; v[k] = vk;
+        const float pk = p[k] - lr_t * mk / (sqrtf(vk) + h.eps);
+        p[k] = pk;
+        p_target[k] = h.tau * pk + (1.f - h.tau) * p_target[k];
+    }
+    if (info_out && k < 2) {                                   // critic call only: loss and mean Q ride in the slab tails
+        float a = 0.f;
+        for (int c = 0; c < n_slabs; ++c) a += slabs[(int64_t)c * kSlab + n + k];
+        info_out[k] = a * inv_b;
+    }
+}
+
+// ---- minibatch rows without replacement, any size, in parallel: a keyed bijection of [0, 2^(2w)) >= count (4-round
+//      Feistel network, round keys from Philox(seed; update index)) walked until it lands below count -----------------------
+__global__ void replay_sample_kernel(int64_t count, int batch, PhiloxKeys keys, uint64_t update_index, int64_t* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    uint32_t rk[4];
+    philox4x32_10(5u << 28, (uint32_t)update_index, (uint32_t)(update_index >> 32), 0u, keys.rk, rk[0], rk[1], rk[2], rk[3]);
+    int w = 1;
+    while (((int64_t)1 << (2 * w)) < count) ++w;               // half width: the domain is 2^(2w) in [count, 4 count)
+    const uint32_t mask = w >= 32 ? 0xFFFFFFFFu : ((1u << w) - 1u);
+    uint64_t x = (uint64_t)i;
+    do {
+        uint32_t l = (uint32_t)(x >> w) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            uint32_t f = r * 0x9E3779B1u ^ rk[round];
+            f ^= f >> 15; f *= 0x85EBCA77u; f ^= f >> 13; f *= 0xC2B2AE3Du; f ^= f >> 16;
+            const uint32_t nl = r;
+            r = (l ^ f) & mask;
+            l = nl;
+        }
+        x = ((uint64_t)l << w) | r;
+    } while ((int64_t)x >= count);                             // cycle walking keeps the map a bijection on [0, count)
+    idx[i] = (int64_t)x;
 }
 
 // ---- replay ring ----------------------------------------------------------------------------------------------------
@@ -455,31 +581,80 @@ int mr_ou_noise_add(double* ou_state, void* actions, const uint8_t* reset_mask, 
     return check_launch("mr_ou_noise_add");
 }
 
+int64_t mr_ddpg_workspace_bytes(int32_t batch) {
+    if (batch <= 0) return 0;
+    const int64_t tiles = (batch + mr::kTile - 1) / mr::kTile;
+    const int64_t ctas = tiles < mr::kMaxCtas ? tiles : mr::kMaxCtas;
+    return (int64_t)batch * 8 + ctas * mr::kSlab * 4 + 64;
+}
+
+int mr_replay_sample(int64_t count, int32_t batch, uint64_t seed, int64_t update_index, int64_t* indices_out, void* stream) {
+    using namespace mr;
+    if (!indices_out) return fail(MR_ERR_ARG, "mr_replay_sample: null output");
+    if (batch <= 0 || count < batch) return fail(MR_ERR_ARG, "mr_replay_sample: need 0 < batch <= count");
+    PhiloxKeys keys;
+    philox_make_keys(seed, keys);
+    replay_sample_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(count, batch, keys, (uint64_t)update_index, indices_out);
+    return check_launch("mr_replay_sample");
+}
+
 int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
-                   uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, float* info_out, void* stream) {
+                   uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, float* info_out, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
     using namespace mr;
     if (!st || !st->actor || !st->actor_target || !st->critic || !st->critic_target || !st->adam_actor_m || !st->adam_actor_v ||
         !st->adam_critic_m || !st->adam_critic_v || !st->grad_actor || !st->grad_critic)
         return fail(MR_ERR_ARG, "mr_ddpg_update: null learner state");
     if (!rb || !rb->s || !rb->a || !rb->r || !rb->d || !rb->s2) return fail(MR_ERR_ARG, "mr_ddpg_update: null replay buffer");
     if (!hp) return fail(MR_ERR_ARG, "mr_ddpg_update: null hyper-parameters");
-    if (batch <= 0 || batch > kMaxBatch) return fail(MR_ERR_ARG, "mr_ddpg_update: batch must be in 1..%d", kMaxBatch);
+    const bool wide = workspace != nullptr && batch > kWideBatch;              // data-parallel path for large minibatches
+    if (batch <= 0 || (!wide && batch > kMaxBatch))
+        return fail(MR_ERR_ARG, "mr_ddpg_update: batch must be in 1..%d (larger ones need the workspace of mr_ddpg_workspace_bytes)", kMaxBatch);
     if (count < batch || count > rb->capacity) return fail(MR_ERR_ARG, "mr_ddpg_update: need batch <= count <= capacity (the reference waits for min_batch transitions)");
     if (update_index < 1) return fail(MR_ERR_ARG, "mr_ddpg_update: update_index is Adam's step count, starting at 1");
     DdpgHyper h{(float)hp->gamma, (float)hp->tau, (float)hp->lr_actor, (float)hp->lr_critic, (float)hp->action_bound[0],
                 (float)hp->action_bound[1], (float)hp->adam_beta1, (float)hp->adam_beta2, (float)hp->adam_eps};
     PhiloxKeys keys;
     philox_make_keys(seed, keys);
+    cudaStream_t s = (cudaStream_t)stream;
     static bool attr[kMaxDevices] = {};
     const int dev = current_device();
     if (!attr[dev]) {
         cudaFuncSetAttribute(ddpg_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DdpgSmem));
+        cudaFuncSetAttribute(ddpg_critic_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DdpgSmem));
+        cudaFuncSetAttribute(ddpg_actor_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DdpgSmem));
         attr[dev] = true;
     }
-    ddpg_update_kernel<<<1, kDdpgThreads, sizeof(DdpgSmem), (cudaStream_t)stream>>>(
-        st->actor, st->actor_target, st->critic, st->critic_target, st->adam_actor_m, st->adam_actor_v, st->adam_critic_m,
-        st->adam_critic_v, st->grad_actor, st->grad_critic, rb->s, rb->a, rb->r, rb->d, rb->s2, count, batch, indices, keys,
-        (uint64_t)update_index, h, info_out);
+    if (!wide) {
+        ddpg_update_kernel<<<1, kDdpgThreads, sizeof(DdpgSmem), s>>>(
+            st->actor, st->actor_target, st->critic, st->critic_target, st->adam_actor_m, st->adam_actor_v, st->adam_critic_m,
+            st->adam_critic_v, st->grad_actor, st->grad_critic, rb->s, rb->a, rb->r, rb->d, rb->s2, count, batch, indices, keys,
+            (uint64_t)update_index, h, info_out);
+        return check_launch("mr_ddpg_update");
+    }
+    if (workspace_bytes < mr_ddpg_workspace_bytes(batch)) return fail(MR_ERR_ARG, "mr_ddpg_update: workspace too small");
+    if ((uintptr_t)workspace & 15u) return fail(MR_ERR_ARG, "mr_ddpg_update: workspace must be 16-byte aligned");
+    int64_t* idx = (int64_t*)workspace;
+    float* slabs = (float*)((char*)workspace + (((int64_t)batch * 8 + 63) / 64) * 64);
+    const int tiles = (batch + kTile - 1) / kTile;
+    static int sm_counts[kMaxDevices] = {};
+    if (!sm_counts[dev]) cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_counts[dev] > 0 ? sm_counts[dev] : 1;
+    const int ctas = tiles < sms ? tiles : (sms < kMaxCtas ? sms : kMaxCtas);
+    if (indices) cudaMemcpyAsync(idx, indices, (size_t)batch * 8, cudaMemcpyDeviceToDevice, s);
+    else replay_sample_kernel<<<(batch + 255) / 256, 256, 0, s>>>(count, batch, keys, (uint64_t)update_index, idx);
+    const float t = (float)update_index, inv_b = 1.0f / (float)batch;
+    const float corr = sqrtf(1.f - powf(h.beta2, t)) / (1.f - powf(h.beta1, t));
+    ddpg_critic_grad_kernel<<<ctas, kDdpgThreads, sizeof(DdpgSmem), s>>>(st->actor_target, st->critic, st->critic_target, rb->s, rb->a,
+                                                                         rb->r, rb->d, rb->s2, idx, batch, h, slabs);
+    ddpg_reduce_adam_kernel<<<(kCriticParams + 255) / 256, 256, 0, s>>>(st->critic, st->critic_target, st->adam_critic_m, st->adam_critic_v,
+                                                                        slabs, ctas, kCriticParams, kC_Mc, kC_T1, 0, 0,
+                                                                        h.lr_critic * corr, h, inv_b, info_out);
+    ddpg_actor_grad_kernel<<<ctas, kDdpgThreads, sizeof(DdpgSmem), s>>>(st->actor, st->critic, rb->s, rb->a, rb->r, rb->d, rb->s2, idx,
+                                                                        batch, h, slabs);
+    ddpg_reduce_adam_kernel<<<(kActorParams + 255) / 256, 256, 0, s>>>(st->actor, st->actor_target, st->adam_actor_m, st->adam_actor_v,
+                                                                       slabs, ctas, kActorParams, kOffM1, kOffW2, kOffM2, kOffW3,
+                                                                       h.lr_actor * corr, h, inv_b, nullptr);
     return check_launch("mr_ddpg_update");
 }
 

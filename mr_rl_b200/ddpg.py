@@ -102,6 +102,15 @@ class ReplayBuffer:
     def size(self):
         return self.count
 
+    def sample_indices(self, batch_size, update_index=1):
+        """``batch_size`` distinct rows of the filled part of the ring (random.sample, :43-46) as a device int64 tensor."""
+        idx = torch.empty(int(batch_size), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.mr_replay_sample(self.count, int(batch_size), self.random_seed, int(update_index), idx.data_ptr(),
+                                           _stream(self.device))
+        L.check(rc, "mr_replay_sample")
+        return idx
+
     def clear(self):
         self.count = 0
         self.head = 0
@@ -167,6 +176,7 @@ class DDPGLearner:
         self.seed = int(seed)
         self.updates = 0
         self._info = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._ws = None
         self.kernel_launches = 0
 
     def predict(self, obs_soa, n=None):
@@ -183,10 +193,16 @@ class DDPGLearner:
             batch_size = int(indices.numel())
             idx_ptr = indices.data_ptr()
         self.updates += 1
+        ws_ptr, ws_bytes = None, 0
+        if batch_size > 256:                       # data-parallel kernels (one CTA per SM) need per-CTA gradient slabs
+            ws_bytes = int(self.lib.mr_ddpg_workspace_bytes(int(batch_size)))
+            if self._ws is None or self._ws.numel() * 8 < ws_bytes:
+                self._ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)
+            ws_ptr = self._ws.data_ptr()
         with torch.cuda.device(self.device):
             rc = self.lib.mr_ddpg_update(C.byref(self._c), C.byref(replay._c), replay.count, int(batch_size), idx_ptr,
                                          self.seed ^ replay.random_seed, self.updates, C.byref(self.hyper), self._info.data_ptr(),
-                                         _stream(self.device))
+                                         ws_ptr, ws_bytes, _stream(self.device))
         if rc:
             self.updates -= 1
         L.check(rc, "mr_ddpg_update")

@@ -12,14 +12,17 @@ pytestmark = pytest.mark.gpu
 BOUND = (20.0, 2 * math.pi)
 
 
-def make_pair(seed=0, **kw):
+def make_pair(seed=0, ref_dtype=torch.float32, **kw):
     from mr_rl_b200.actor import init_actor
     from mr_rl_b200.ddpg import DDPGLearner, init_critic
     from oracle.ddpg_oracle import DDPGOracle
     a, c, at, ct = init_actor(seed), init_critic(seed + 1), init_actor(seed + 2), init_critic(seed + 3)
     dev = DDPGLearner(a, c, BOUND, actor_target_init=at, critic_target_init=ct, device="cuda:0", **kw)
-    ref = DDPGOracle(a, c, at, ct, BOUND, **kw)
+    ref = DDPGOracle(a, c, at, ct, BOUND, dtype=ref_dtype, **kw)
     return dev, ref
+
+
+
 
 
 def fill_replay(n, seed=0):
@@ -48,18 +51,36 @@ def assert_params_close(dev, ref, atol=3e-6, rtol=2e-4):
                 f"{name}.{k}: max abs diff {float((g - w.reshape(g.shape)).abs().max()):.3e}"
 
 
-@pytest.mark.parametrize("batch", [64, 50, 256])
+@pytest.mark.parametrize("batch", [64, 50, 256, 1000, 4096])
 def test_update_matches_torch_restatement(batch):
+    """batch <= 256: the one-launch single-CTA kernel; above: the data-parallel path (one CTA per SM, partial gradients
+    summed in a fixed order) — same numbers either way."""
     dev, ref = make_pair(0)
-    rb, (s, a, r, d, s2) = fill_replay(1000, seed=batch)
+    rb, (s, a, r, d, s2) = fill_replay(max(1000, batch), seed=batch)
     g = torch.Generator().manual_seed(5)
     for it in range(6):
-        idx = torch.randperm(1000, generator=g)[:batch]
+        idx = torch.randperm(max(1000, batch), generator=g)[:batch]
         info = dev.update(rb, indices=idx.cuda()).cpu()
         loss, qm = ref.update(s[idx], a[idx], r[idx], d[idx], s2[idx])
         assert abs(float(info[0]) - loss) <= 1e-4 * abs(loss) + 1e-5, (it, float(info[0]), loss)
         assert abs(float(info[1]) - qm) <= 1e-4 * abs(qm) + 1e-5
-    assert_params_close(dev, ref)
+    if batch <= 1000:
+        assert_params_close(dev, ref)
+    else:
+        # Thousands of samples per update make "ReLU knife-edge" events likely: a pre-activation within fp32 rounding
+        # of zero flips the mask of one hidden unit in one implementation, and Adam's normalisation turns that into a
+        # visible step for that unit's ~40 parameters.  Measured over seeds (tools history): it happens to torch's own
+        # fp32 run against float64 as often as to the device.  So judge against the same update in float64, robustly:
+        # nearly all parameters agree to fp32 noise, at most one or two units may have taken a different branch.
+        _, ref64 = make_pair(0, ref_dtype=torch.float64)
+        g = torch.Generator().manual_seed(5)
+        for it in range(6):
+            idx = torch.randperm(max(1000, batch), generator=g)[:batch]
+            ref64.update(s[idx], a[idx], r[idx], d[idx], s2[idx])
+        for got, r64 in ((dev.actor_params(), ref64.actor), (dev.critic_params(), ref64.critic),
+                         (dev.actor_params(True), ref64.actor_t), (dev.critic_params(True), ref64.critic_t)):
+            err = torch.cat([(got[k].double() - r64[k].reshape(got[k].shape)).abs().reshape(-1) for k in r64])
+            assert float(err.median()) < 5e-7 and float((err > 1e-5).double().mean()) < 0.03 and float(err.max()) < 5e-3
     # the unused t1 bias never moves, the moving statistics stay frozen
     assert torch.all(dev.critic_params()["t1b"] == 0) and torch.all(dev.critic_params()["vc"] == 1)
     assert torch.all(dev.actor_params()["m1"] == 0) and torch.all(dev.actor_params()["v2"] == 1)
@@ -194,3 +215,35 @@ def test_replay_ring_keeps_what_the_reference_deque_keeps():
     # the device OU process uses the reference's default parameters
     ou = OUNoise(4, device="cuda:0")
     assert (ou.theta, ou.sigma, ou.dt) == tuple(g["ou_params"])
+
+
+def test_parallel_sampler_draws_distinct_uniform_rows():
+    """mr_replay_sample: a keyed bijection walked into [0, count) — every batch is duplicate-free, in range, reproducible,
+    changes with the update index, and covers the ring evenly."""
+    from mr_rl_b200.ddpg import ReplayBuffer
+    for count, batch in ((64, 64), (1000, 64), (10000, 4096), (1 << 20, 65536), (3, 2)):
+        rb = ReplayBuffer(max(count, 4), 7, device="cuda:0")
+        rb.count = count
+        a = rb.sample_indices(batch, 1).cpu().numpy()
+        assert a.min() >= 0 and a.max() < count and len(np.unique(a)) == batch
+        assert np.array_equal(a, rb.sample_indices(batch, 1).cpu().numpy())
+        if count > 64:
+            assert not np.array_equal(a, rb.sample_indices(batch, 2).cpu().numpy())
+    rb = ReplayBuffer(10000, 3, device="cuda:0")
+    rb.count = 10000
+    hits = np.zeros(10000)
+    for u in range(1, 401):
+        hits[rb.sample_indices(250, u).cpu().numpy()] += 1               # 100000 draws over 10000 rows: mean 10 per row
+    assert abs(hits.mean() - 10.0) < 1e-9 and 2.8 < hits.std() < 3.5   # binomial(400, 1/40): sigma = 3.12
+    assert hits.max() < 30 and (hits == 0).sum() < 10
+
+
+def test_wide_update_with_internal_sampling_is_deterministic():
+    rb, _ = fill_replay(50000, seed=9)
+    a, _ = make_pair(4)
+    b, _ = make_pair(4)
+    for _ in range(3):
+        ia, ib = a.update(rb, 8192).clone(), b.update(rb, 8192).clone()
+        assert torch.equal(ia, ib) and torch.isfinite(ia).all()
+    assert torch.equal(a.actor, b.actor) and torch.equal(a.critic_target, b.critic_target)
+    assert not torch.equal(a.actor, make_pair(4)[0].actor)
