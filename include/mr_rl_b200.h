@@ -344,7 +344,7 @@ int mr_ou_noise_add(double* ou_state, void* actions, const uint8_t* reset_mask, 
 int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
                    uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, float* info_out, void* workspace,
                    int64_t workspace_bytes, void* stream);
-/* Minibatches above 256 samples run data-parallel over one CTA per SM (four launches: critic gradients, critic Adam,
+/* Minibatches above 64 samples run data-parallel over one CTA per SM (four launches: critic gradients, critic Adam,
  * actor gradients, actor Adam; per-CTA partial gradients summed in a fixed order) when a workspace of
  * mr_ddpg_workspace_bytes(batch) bytes is passed; without one (NULL) the single-CTA kernel handles up to 4096 samples.
  * Sampling in that path is mr_replay_sample's. */

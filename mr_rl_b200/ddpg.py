@@ -194,7 +194,7 @@ class DDPGLearner:
             idx_ptr = indices.data_ptr()
         self.updates += 1
         ws_ptr, ws_bytes = None, 0
-        if batch_size > 256:                       # data-parallel kernels (one CTA per SM) need per-CTA gradient slabs
+        if batch_size > 64:                        # data-parallel kernels (one CTA per SM) need per-CTA gradient slabs
             ws_bytes = int(self.lib.mr_ddpg_workspace_bytes(int(batch_size)))
             if self._ws is None or self._ws.numel() * 8 < ws_bytes:
                 self._ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)

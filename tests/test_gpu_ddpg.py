@@ -53,7 +53,7 @@ def assert_params_close(dev, ref, atol=3e-6, rtol=2e-4):
 
 @pytest.mark.parametrize("batch", [64, 50, 256, 1000, 4096])
 def test_update_matches_torch_restatement(batch):
-    """batch <= 256: the one-launch single-CTA kernel; above: the data-parallel path (one CTA per SM, partial gradients
+    """batch <= 64: the one-launch single-CTA kernel; above: the data-parallel path (one CTA per SM, partial gradients
     summed in a fixed order) — same numbers either way."""
     dev, ref = make_pair(0)
     rb, (s, a, r, d, s2) = fill_replay(max(1000, batch), seed=batch)
