@@ -355,6 +355,11 @@ int64_t mr_ddpg_workspace_bytes(int32_t batch);
  * cycle-walked into [0, count).  indices_out: device int64 [batch]. */
 int mr_replay_sample(int64_t count, int32_t batch, uint64_t seed, int64_t update_index, int64_t* indices_out, void* stream);
 
+/* mr_actor_forward for MR_Env observations — obs rows 2, 3 (the goal) are identically zero (MR_env.py:57) and are not
+ * read — with the hidden layer on the tensor cores (tcgen05, 3xTF32 ~ fp32 accuracy).  Same arguments. */
+int mr_actor_forward_env(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
+                         const double action_high[2], void* actions, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

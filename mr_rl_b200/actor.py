@@ -61,14 +61,16 @@ def torch_reference(params, obs, action_high=(20.0, 2 * np.pi), eps=1e-5):
     return torch.tanh(h @ p["w3"] + p["b3"]) * torch.tensor(action_high, dtype=torch.float32)
 
 
-def actor_forward(packed, obs_soa, n=None, action_high=(20.0, 2 * np.pi)):
-    """obs_soa: [5, stride] device tensor (SoA rows, e.g. VecMREnv._obs).  Returns actions [n, 2]."""
+def actor_forward(packed, obs_soa, n=None, action_high=(20.0, 2 * np.pi), env_obs=False):
+    """obs_soa: [5, stride] device tensor (SoA rows, e.g. VecMREnv._obs).  Returns actions [n, 2].
+    env_obs=True: the rows come from MR_Env (goal rows 2, 3 identically zero) -> tensor-core kernel."""
     lib = L.load()
     n = int(n if n is not None else obs_soa.shape[1])
     dt = {torch.float64: L.MR_F64, torch.float32: L.MR_F32}[obs_soa.dtype]
     out = torch.empty(n, 2, dtype=obs_soa.dtype, device=obs_soa.device)
     hi = (C.c_double * 2)(float(action_high[0]), float(action_high[1]))
     stream = C.c_void_p(torch.cuda.current_stream(obs_soa.device).cuda_stream)
-    rc = lib.mr_actor_forward(packed.data_ptr(), obs_soa.data_ptr(), obs_soa.stride(0), n, dt, hi, out.data_ptr(), stream)
-    L.check(rc, "mr_actor_forward")
+    fn = lib.mr_actor_forward_env if env_obs else lib.mr_actor_forward
+    rc = fn(packed.data_ptr(), obs_soa.data_ptr(), obs_soa.stride(0), n, dt, hi, out.data_ptr(), stream)
+    L.check(rc, "mr_actor_forward_env" if env_obs else "mr_actor_forward")
     return out

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "mr_actor.cuh"
+#include "mr_actor_tc.cuh"
 #include "mr_common.cuh"
 #include "mr_dmma.cuh"
 #include "mr_step_tma.cuh"   // mbarrier / cp.async.bulk helpers
@@ -346,6 +347,31 @@ actor_forward_kernel(const float* __restrict__ actor, const T* __restrict__ obs,
     actions[2 * i + 1] = (T)a2[1];
 }
 
+// The same network for MR_Env observations (goal components obs[2], obs[3] identically zero, MR_env.py:57) with the
+// hidden 64 x 64 layer on the tensor cores: persistent CTAs of 128 envs, tcgen05.mma 3xTF32 into TMEM
+// (mr_actor_tc.cuh, shared with the fused rollout).  Measured at 2^20 envs: see tools/ddpgbench.py.
+template <class T>
+__global__ void __launch_bounds__(kTcRows, 1)
+actor_forward_tc_kernel(const float* __restrict__ actor, const T* __restrict__ obs, int64_t stride, int64_t n, float hi0,
+                        float hi1, T* __restrict__ actions) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    ActorTcSmem& sm = *reinterpret_cast<ActorTcSmem*>(s_dyn);
+    actor_tc_setup(sm, actor);
+    __syncthreads();
+    const int64_t n_tiles = (n + kTcRows - 1) / kTcRows;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {     // every thread runs every iteration
+        const int64_t i = tile * kTcRows + threadIdx.x;
+        const bool live = i < n;
+        float o5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live) { o5[0] = (float)obs[i]; o5[1] = (float)obs[stride + i]; o5[4] = (float)obs[4 * stride + i]; }
+        float a2[2];
+        actor_tc_forward(sm, o5, hi0, hi1, it, a2);
+        if (live) { actions[2 * i] = (T)a2[0]; actions[2 * i + 1] = (T)a2[1]; }
+    }
+    actor_tc_teardown(sm);
+}
+
 }  // namespace mr
 
 extern "C" {
@@ -440,6 +466,34 @@ int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride
         actor_forward_kernel<float><<<blocks, threads, smem, s>>>(actor, (const float*)obs, stride, n, (float)action_high[0], (float)action_high[1], (float*)actions);
     else return fail(MR_ERR_ARG, "mr_actor_forward: bad dtype");
     return check_launch("mr_actor_forward");
+}
+
+int mr_actor_forward_env(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
+                         const double action_high[2], void* actions, void* stream) {
+    using namespace mr;
+    if (!actor || !obs || !actions || !action_high) return fail(MR_ERR_ARG, "mr_actor_forward_env: null argument");
+    if (n < 0) return fail(MR_ERR_ARG, "mr_actor_forward_env: bad n");
+    if (n == 0) return MR_OK;
+    if (dtype != MR_F64 && dtype != MR_F32) return fail(MR_ERR_ARG, "mr_actor_forward_env: bad dtype");
+    static int ctas[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!ctas[dev]) {
+        cudaFuncSetAttribute(actor_forward_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ActorTcSmem));
+        cudaFuncSetAttribute(actor_forward_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ActorTcSmem));
+        int sms = 0, occ = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, actor_forward_tc_kernel<double>, kTcRows, sizeof(ActorTcSmem));
+        ctas[dev] = (sms > 0 ? sms : 148) * (occ > 0 ? occ : 1);
+    }
+    const int64_t tiles = (n + kTcRows - 1) / kTcRows;
+    const unsigned grid = (unsigned)(tiles < ctas[dev] ? tiles : ctas[dev]);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t stride = obs_row_stride ? obs_row_stride : n;
+    if (dtype == MR_F64)
+        actor_forward_tc_kernel<double><<<grid, kTcRows, sizeof(ActorTcSmem), s>>>(actor, (const double*)obs, stride, n, (float)action_high[0], (float)action_high[1], (double*)actions);
+    else
+        actor_forward_tc_kernel<float><<<grid, kTcRows, sizeof(ActorTcSmem), s>>>(actor, (const float*)obs, stride, n, (float)action_high[0], (float)action_high[1], (float*)actions);
+    return check_launch("mr_actor_forward_env");
 }
 
 }  // extern "C"

@@ -182,7 +182,7 @@ class DDPGLearner:
     def predict(self, obs_soa, n=None):
         """ActorNetwork.predict (:146-149) for the env's SoA observation rows -> actions [n, 2] (obs dtype)."""
         self.kernel_launches += 1
-        return actor_forward(self.actor, obs_soa, n, self.action_bound)
+        return actor_forward(self.actor, obs_soa, n, self.action_bound, env_obs=True)
 
     def update(self, replay, batch_size=64, indices=None):
         """The update block of train() (:285-305).  ``indices`` (int64 device tensor) pins the minibatch; by default the

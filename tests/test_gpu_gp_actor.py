@@ -160,6 +160,30 @@ def test_tensor_core_actor_matches_fp32_actor_actions():
     assert np.allclose(f_got, np.abs(ref[:, 0]), rtol=1e-4, atol=1e-6)          # the 1e-4 bar on the action magnitude
 
 
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_standalone_tensor_core_actor_matches_fp32_reference(dt):
+    """mr_actor_forward_env (persistent CTAs, hidden layer on tcgen05) against the torch fp32 forward and the CUDA-core
+    kernel on MR_Env observations, ragged n (several tiles per CTA and a partial last tile)."""
+    from mr_rl_b200 import VecMREnv, actor_forward, init_actor, pack_actor
+    from mr_rl_b200.actor import torch_reference
+    params = init_actor(5)
+    g = torch.Generator().manual_seed(6)
+    params["w3"] = 0.4 * torch.randn(64, 2, generator=g)
+    params["m1"] = 0.05 * torch.randn(64, generator=g); params["v1"] = 0.5 + torch.rand(64, generator=g)
+    params["b2"] = 0.02 * torch.randn(64, generator=g); params["be2"] = 0.02 * torch.randn(64, generator=g)
+    packed = pack_actor(params, "cuda:0")
+    n = 128 * 700 + 37
+    env = VecMREnv(n, device="cuda:0", dtype=dt, noise="none")
+    env.reset(init=None, noise_var=0.0, a0=1.0)
+    a_tc = actor_forward(packed, env._obs, n, env_obs=True)
+    a_simt = actor_forward(packed, env._obs, n)
+    ref = torch_reference(params, env.obs.cpu().numpy())
+    hi = torch.tensor([20.0, 2 * np.pi])
+    assert a_tc.shape == (n, 2) and a_tc.dtype == dt
+    assert float(((a_tc.cpu().float() - ref).abs() / hi).max()) < 1e-4          # the 1e-4 bar, relative to the action range
+    assert float(((a_tc - a_simt).abs().cpu().float() / hi).max()) < 1e-4
+
+
 def test_actor_in_the_rollout_loop_matches_stepwise_composition():
     """Config-5 path at reduced size: fused rollout with the actor evaluated in-kernel ==
     actor_forward kernel + single-step kernel composed on the host (noise-free)."""
