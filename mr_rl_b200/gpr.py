@@ -93,6 +93,9 @@ class DeviceGPR:
         self._rng = check_random_state(self.random_state)
         theta0, bounds = self.kernel.theta, self.kernel.bounds
         if self.optimizer is not None:
+            # (tried: the independent restarts from host threads on separate streams, to fill the GPU during the serial
+            # diagonal-block steps — identical optima but 0.97 s instead of 0.37 s for the reference-sized fit: launches
+            # from several threads serialise in the driver and every stream grows its own allocator pool)
             optima = [self._optimise(theta0, bounds)]
             for _ in range(self.n_restarts_optimizer):
                 if not np.isfinite(bounds).all():
