@@ -3,7 +3,8 @@
 ``DeviceGP`` holds what sklearn's fitted ``GaussianProcessRegressor`` holds (X_train_, alpha_, L_,
 kernel_ = RBF(l) + WhiteKernel(noise); Learning_module.py:30-33,122-123) in HBM, padded for the
 tiled kernels, and evaluates ``predict(q, return_std)`` with the CUDA kernels in csrc/mr_gp.cu.
-Fitting stays on the host (sklearn), exactly where the reference does it.
+``DeviceGP.fit`` factorises on the device at given hyper-parameters (csrc/mr_gpfit.cu); the hyper-parameter search
+around it is gpr.DeviceGPR; ``from_sklearn`` takes a model fitted on the host instead.
 """
 from __future__ import annotations
 
