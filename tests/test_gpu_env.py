@@ -539,3 +539,66 @@ def test_pipelined_host_step_equals_single_launch_step():
         assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(d1, d2.cpu().numpy().astype(bool))
         assert np.array_equal(r1, r2.cpu().numpy())
     assert np.array_equal(e1._state.cpu().numpy(), e2._state.cpu().numpy())
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_regimes_against_c_oracle(seed):
+    """Randomised sweep of simulator regimes (noise level, a0, model mismatch, start positions from inside the goal
+    radius to beyond the observation bounds, actions outside the action space) — single-step kernel and fused rollout
+    against the plain-C oracle on the same noise streams: done flags and draw counts exact, positions 1e-9."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(1000 + seed)
+    n, T = 256, 40
+    scale = float(rng.choice([20.0, 150.0, 4000.0, 7000.0]))                  # |init| from inside d < 30 to out of bounds
+    # (close to the origin the error scale atol + rtol |y| is tiny: strong noise there makes scipy's step size collapse,
+    # the solver-failure case that has its own golden test; keep the noise small in that corner)
+    sigma = float(rng.choice([0.0, 0.02, 0.05] if scale < 100 else [0.0, 0.05, 0.5, 1.0]))
+    a0 = float(rng.choice([0.5, 1.0, 1.5, 4.0]))
+    mism = bool(rng.integers(0, 2))
+    init = rng.uniform(-scale, scale, (n, 2))
+    acts = np.stack([rng.uniform(-5, 30, (T, n)), rng.uniform(-7, 7, (T, n))], -1)
+    acts[rng.random((T, n)) < 0.05] = 0.0                                     # some idle steps (f = 0)
+    z = rng.standard_normal((n, 200 * T + 64))                               # up to ~25 RK45 attempts per step here
+    ref = c_oracle.rollout(init, acts, sigma, a0, mism=mism, mism_at_reset=False, z=z)
+    assert ref["bad"] == 0
+    for fused in (False, True):
+        env = make_env(n, noise="table", noise_table=np.ascontiguousarray(z.T))
+        env.reset(init=init, noise_var=sigma, a0=a0, is_mismatched=mism)
+        a_dev = torch.as_tensor(acts, device="cuda:0")
+        if fused:
+            res = env.rollout(actions=a_dev, record=True, record_done=True)
+            xy = res["xy"].cpu().numpy().transpose(0, 2, 1)
+            dn = res["done_traj"].cpu().numpy()
+        else:
+            xy, dn = [], []
+            for k in range(T):
+                _, _, d, _ = env.step(a_dev[k])
+                xy.append(env.last_pos.cpu().numpy().copy()); dn.append(d.cpu().numpy().copy())
+            xy, dn = np.stack(xy), np.stack(dn)
+        assert np.array_equal(dn.astype(bool), ref["done"].astype(bool)), (sigma, a0, mism, scale, fused)
+        assert np.array_equal(env._cursor[:n].cpu().numpy().astype(np.int64), ref["cursor"])
+        assert rel_err(xy, ref["pos"]) < FP64_TOL
+        env.check_status()
+
+
+def test_solver_failures_are_flagged_for_the_same_envs_as_the_oracle():
+    """Strong noise next to the origin (error scale atol + rtol |y| tiny): scipy's step size collapses below 10 ulp(t) and
+    the reference raises RuntimeError; here the env gets the sticky MR_ENV_SOLVER_FAILED bit.  The count of flagged envs
+    equals the C oracle's count of failed / overflowed envs on the same noise streams."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(77)
+    n, T = 256, 40
+    init = rng.uniform(-20, 20, (n, 2))
+    acts = np.stack([rng.uniform(0, 20, (T, n)), rng.uniform(0, 6.28, (T, n))], -1)
+    z = rng.standard_normal((n, 200 * T + 64))
+    ref = c_oracle.rollout(init, acts, 3.0, 1.5, mism=True, mism_at_reset=False, z=z)
+    assert 0 < ref["bad"] <= n
+    env = make_env(n, noise="table", noise_table=np.ascontiguousarray(z.T))
+    env.reset(init=init, noise_var=3.0, a0=1.5, is_mismatched=True)
+    a_dev = torch.as_tensor(acts, device="cuda:0")
+    for k in range(T):
+        env.step(a_dev[k])
+    flagged = int((env.status != 0).sum())
+    assert flagged == ref["bad"]
+    with pytest.raises(Exception):
+        env.check_status()
