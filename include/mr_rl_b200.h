@@ -196,12 +196,16 @@ int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_si
 typedef struct mr_gp_model {
     const double* x_train_scaled; /* [n_pad][dim]  GPR.X_train_ / length_scale (sklearn RBF scales first) */
     const double* alpha;     /* [n_pad]  GPR.alpha_ (0 in the padding) */
-    const double* linv;      /* [n_pad][n_pad] row-major inverse of the lower Cholesky factor GPR.L_,
-                                upper triangle and padding zero; NULL if std is never requested */
+    const double* linv;      /* proj_rows == 0: [n_pad][n_pad] row-major inverse of the lower Cholesky factor GPR.L_,
+                                upper triangle and padding zero.  proj_rows > 0: [proj_rows][n_pad] dense spectral
+                                projection P with |P k|^2 = k^T K^-1 k (rows u_i^T / sqrt(mu_i) of the leading
+                                eigenpairs of K; the RBF Gram matrix is numerically low rank, so a few hundred rows
+                                reproduce the triangular form to rounding at a fraction of its cost).
+                                NULL if std is never requested */
     int32_t n_train;
     int32_t n_pad;
     int32_t dim;             /* 1 (Learning_module.py) or 2 (Learning_module_2d.py) */
-    int32_t reserved;
+    int32_t proj_rows;       /* 0, or the number of projection rows (multiple of MR_GP_PAD) */
     double length_scale;     /* kernel_.k1.length_scale */
     double noise_level;      /* kernel_.k2.noise_level */
 } mr_gp_model;

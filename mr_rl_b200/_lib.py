@@ -59,7 +59,7 @@ class RolloutIO(C.Structure):
 
 class GPModel(C.Structure):
     _fields_ = [("x_train_scaled", C.c_void_p), ("alpha", C.c_void_p), ("linv", C.c_void_p), ("n_train", C.c_int32),
-                ("n_pad", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+                ("n_pad", C.c_int32), ("dim", C.c_int32), ("proj_rows", C.c_int32),
                 ("length_scale", C.c_double), ("noise_level", C.c_double)]
 
 

@@ -169,7 +169,7 @@ static void launch_kq_mean(const double* q, int64_t n_q, const mr_gp_model* gp, 
 // ---- kernel 2: triangular contraction + square-sum (mainloop: mr_dmma.cuh) --------------------
 __global__ void __launch_bounds__(256)
 gp_var_kernel(const double* __restrict__ kq, const double* __restrict__ linv, int n_pad, int64_t n_q_pad,
-              double* __restrict__ ssq) {
+              double* __restrict__ ssq, int dense) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_m = warp >> 2;
@@ -177,7 +177,8 @@ gp_var_kernel(const double* __restrict__ kq, const double* __restrict__ linv, in
     const int bn = (int)gridDim.y - 1 - (int)blockIdx.y;        // heaviest column blocks first
     const int64_t m0 = (int64_t)blockIdx.x * GP_BM;
     const int r0 = bn * GP_BN;
-    const int k_tiles = (r0 + GP_BN) / GP_BK;                   // c <= r: columns beyond the diagonal block are zero
+    // triangular L^-1: c <= r, columns beyond the diagonal block are zero; dense spectral projection: all columns
+    const int k_tiles = dense ? n_pad / GP_BK : (r0 + GP_BN) / GP_BK;
 
     double acc[8][4][2];
 #pragma unroll
@@ -400,6 +401,8 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
         return check_launch("mr_gp_predict(mean)");
     }
     if (!gp->linv) return fail(MR_ERR_ARG, "mr_gp_predict: std requested but model has no linv");
+    if (gp->proj_rows < 0 || gp->proj_rows % MR_GP_PAD != 0 || gp->proj_rows > gp->n_pad)
+        return fail(MR_ERR_ARG, "mr_gp_predict: proj_rows must be 0 or a multiple of %d up to n_pad", MR_GP_PAD);
     if (!workspace || workspace_bytes < mr_gp_workspace_bytes(gp, n_q, 1))
         return fail(MR_ERR_ARG, "mr_gp_predict: workspace too small (%lld < %lld)", (long long)workspace_bytes,
                     (long long)mr_gp_workspace_bytes(gp, n_q, 1));
@@ -417,8 +420,9 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
         if (gp->dim == 1) launch_kq_mean<1, true>(q + q0, nq, gp, kq, mean + q0, s);
         else launch_kq_mean<2, true>(q + q0 * 2, nq, gp, kq, mean + q0, s);
         cudaMemsetAsync(ssq, 0, (size_t)nq_pad * 8, s);
-        dim3 grid((unsigned)(nq_pad / GP_BM), (unsigned)(gp->n_pad / GP_BN));
-        gp_var_kernel<<<grid, 256, smem, s>>>(kq, gp->linv, gp->n_pad, nq_pad, ssq);
+        const int rows = gp->proj_rows > 0 ? gp->proj_rows : gp->n_pad;
+        dim3 grid((unsigned)(nq_pad / GP_BM), (unsigned)(rows / GP_BN));
+        gp_var_kernel<<<grid, 256, smem, s>>>(kq, gp->linv, gp->n_pad, nq_pad, ssq, gp->proj_rows > 0 ? 1 : 0);
         gp_std_finish_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(ssq, nq, 1.0 + gp->noise_level, std + q0);
         int rc = check_launch("mr_gp_predict");
         if (rc) return rc;

@@ -17,8 +17,10 @@ from . import _lib as L
 
 
 class DeviceGP:
-    def __init__(self, X_train, alpha, L_chol, length_scale, noise_level, device="cuda"):
+    def __init__(self, X_train, alpha, L_chol, length_scale, noise_level, device="cuda", jitter=1e-10):
         self.lib = L.load()
+        self.jitter = float(jitter)
+        self._proj = None
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.MRLibraryError("DeviceGP needs a CUDA device: there is no CPU fallback")
@@ -58,7 +60,8 @@ class DeviceGP:
         k = gpr.kernel_
         if getattr(gpr, "_y_train_std", 1.0) != 1.0 or np.any(np.asarray(getattr(gpr, "_y_train_mean", 0.0)) != 0.0):
             raise ValueError("normalize_y=True models are not supported (the reference uses the default False)")
-        return cls(gpr.X_train_, gpr.alpha_, gpr.L_ if with_std else None, k.k1.length_scale, k.k2.noise_level, device)
+        return cls(gpr.X_train_, gpr.alpha_, gpr.L_ if with_std else None, k.k1.length_scale, k.k2.noise_level, device,
+                   jitter=float(np.ravel(gpr.alpha)[0]) if np.ndim(gpr.alpha) == 0 or np.size(gpr.alpha) == 1 else 1e-10)
 
     @classmethod
     def fit(cls, X, y, length_scale, noise_level, jitter=1e-10, device="cuda", eval_gradient=False):
@@ -69,6 +72,8 @@ class DeviceGP:
         and ``log_marginal_likelihood_gradient_`` (w.r.t. log length_scale, log noise_level) — see gpr.DeviceGPR."""
         self = cls.__new__(cls)
         self.lib = L.load()
+        self.jitter = float(jitter)
+        self._proj = None
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.MRLibraryError("DeviceGP needs a CUDA device: there is no CPU fallback")
@@ -109,6 +114,45 @@ class DeviceGP:
         self._ws = None
         self.kernel_launches = 0
         return self
+
+    def enable_spectral_variance(self, tol=1e-9, n_probe=512, max_fraction=0.5):
+        """Replace the triangular variance contraction |L^-1 k|^2 (n^2 / 2 per query) by |P k|^2 with P the leading
+        eigenpairs of K scaled by mu^-1/2 (rows u_i^T / sqrt(mu_i)).  An RBF Gram matrix is numerically low rank — its
+        spectrum decays like exp(-i^2 c) down to the noise floor — and k(q, X) lives in the same leading subspace, so a
+        few hundred rows give k^T K^-1 k to rounding.  The switch is made only if the two forms agree to ``tol``
+        (relative, in the std) on ``n_probe`` queries spread over the training range; returns the number of rows used
+        (0 = kept the triangular form).  The eigendecomposition runs once per model (torch.linalg.eigh)."""
+        if self._linv is None or self._c.proj_rows:
+            return int(self._c.proj_rows)
+        n, n_pad = self.n_train, self.n_pad
+        with torch.cuda.device(self.device):
+            xs = self._xs[:n]
+            d2 = torch.cdist(xs, xs).square_()
+            K = torch.exp(-0.5 * d2)
+            K.diagonal().fill_(1.0 + self.noise_level + self.jitter)
+            mu, U = torch.linalg.eigh(K)                                   # ascending
+            floor = self.noise_level + self.jitter
+            r = int((mu - floor > 1e-12 * float(mu[-1])).sum())
+            r_pad = max(L.GP_PAD, (r + L.GP_PAD - 1) // L.GP_PAD * L.GP_PAD)
+            if r_pad > max_fraction * n_pad:
+                return 0
+            P = torch.zeros(r_pad, n_pad, dtype=torch.float64, device=self.device)
+            top = slice(n - min(r_pad, n), n)
+            P[: min(r_pad, n), :n] = (U[:, top] / torch.sqrt(mu[top])).T
+            lo, hi = self._xs[:n].min(0).values, self._xs[:n].max(0).values
+            g = torch.Generator(device=self.device).manual_seed(0)
+            probe = (lo + (hi - lo) * torch.rand(n_probe, self.dim, generator=g, device=self.device, dtype=torch.float64))
+            probe = probe * self.length_scale                             # predict() takes unscaled inputs
+            _, s_tri = self.predict(probe, True)
+            tri_ptr = self._c.linv
+            self._proj = P
+            self._c.linv, self._c.proj_rows = P.data_ptr(), r_pad
+            _, s_spec = self.predict(probe, True)
+            err = float(((s_spec - s_tri).abs() / s_tri.clamp_min(1e-300)).max())
+            if not err <= tol:
+                self._c.linv, self._c.proj_rows, self._proj = tri_ptr, 0, None
+                return 0
+        return r_pad
 
     def predict(self, q, return_std=False):
         """q: [n_q] or [n_q, dim] float64 (device tensor or array).  Returns mean[, std] device tensors."""

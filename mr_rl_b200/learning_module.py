@@ -17,6 +17,8 @@ from .gp import DeviceGP
 
 
 class LearningModule:
+    spectral_variance = True     # evaluate GP variances through the low-rank spectral projection when it is exact to 1e-9
+
     def __init__(self, device="cuda", fit="device", preprocess=None):
         """fit: "device" | "host" (sklearn).  preprocess: "device" | "host" (numpy/scipy as in the reference); defaults to
         where the fit runs."""
@@ -139,6 +141,9 @@ class LearningModule:
         as_device = lambda g: g.device_model() if hasattr(g, "device_model") else DeviceGP.from_sklearn(g, self.device)
         self._dx = as_device(self.gprX)
         self._dy = as_device(self.gprY)
+        if self.spectral_variance:                      # verified against the triangular form before it is used
+            self._dx.enable_spectral_variance()
+            self._dy.enable_spectral_variance()
 
     def set_models(self, gprX, gprY, a0, freq, Dx=0.0, Dy=0.0):
         """Install already-fitted GPRs (sklearn or DeviceGPR; e.g. fixed kernels, optimizer=None)."""

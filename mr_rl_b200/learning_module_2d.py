@@ -85,6 +85,8 @@ class LearningModule2D:
         as_device = lambda g: g.device_model() if hasattr(g, "device_model") else DeviceGP.from_sklearn(g, self.device)
         self._dx = as_device(self.gprX)
         self._dy = as_device(self.gprY)
+        self._dx.enable_spectral_variance()             # verified against the triangular form before it is used
+        self._dy.enable_spectral_variance()
 
     def set_models(self, gprX, gprY, a0, Dx=0.0, Dy=0.0):
         self.gprX, self.gprY, self.a0, self.Dx, self.Dy = gprX, gprY, a0, Dx, Dy

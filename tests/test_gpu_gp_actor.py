@@ -74,6 +74,38 @@ def test_gp_matches_sklearn_directly():
     assert np.allclose(s.cpu().numpy(), s_ref, rtol=1e-6, atol=1e-9)
 
 
+def test_spectral_variance_matches_triangular_and_sklearn():
+    """DeviceGP.enable_spectral_variance: |P k|^2 with the leading eigenpairs of K instead of |L^-1 k|^2 — same posterior
+    std as sklearn (and as the triangular form) at a fraction of the rows; refused when the kernel is not low rank."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    from mr_rl_b200 import DeviceGP
+    rng = np.random.default_rng(0)
+    X = np.sort(rng.uniform(-np.pi, np.pi, 2000)).reshape(-1, 1)
+    y = 0.2 + 0.5 * np.cos(X[:, 0] + 0.3) + 0.09 * rng.standard_normal(2000)
+    sk = GaussianProcessRegressor(kernel=RBF(0.2) + WhiteKernel(0.008), optimizer=None).fit(X, y)
+    gp = DeviceGP.from_sklearn(sk, "cuda:0")
+    q = rng.uniform(-np.pi, np.pi, 3000)
+    m0, s0 = gp.predict(q, True)
+    rows = gp.enable_spectral_variance()
+    assert 0 < rows <= 512 and rows % 128 == 0                   # ~80 significant eigenvalues at l = 0.2 on [-pi, pi]
+    m1, s1 = gp.predict(q, True)
+    mr, sr = sk.predict(q.reshape(-1, 1), return_std=True)
+    assert torch.equal(m0, m1)
+    assert float(((s1 - s0).abs() / s0).max()) < 1e-9
+    assert np.allclose(s1.cpu().numpy(), sr, rtol=1e-6, atol=1e-9) and np.allclose(m1.cpu().numpy(), mr, rtol=1e-8, atol=1e-8)
+    # outside the training range too (the std grows to the prior there)
+    far = np.linspace(-6, 6, 257)
+    _, sf = gp.predict(far, True)
+    assert np.allclose(sf.cpu().numpy(), sk.predict(far.reshape(-1, 1), return_std=True)[1], rtol=1e-6, atol=1e-9)
+    # a rough kernel is not low rank: the projection is refused and the triangular form stays
+    sk2 = GaussianProcessRegressor(kernel=RBF(0.003) + WhiteKernel(0.008), optimizer=None).fit(X, y)
+    gp2 = DeviceGP.from_sklearn(sk2, "cuda:0")
+    assert gp2.enable_spectral_variance() == 0
+    _, s2 = gp2.predict(q, True)
+    assert np.allclose(s2.cpu().numpy(), sk2.predict(q.reshape(-1, 1), return_std=True)[1], rtol=1e-6, atol=1e-9)
+
+
 def test_learning_module_facade_error_and_predict(golden_gp):
     """Reference surface: error(vd) -> four (1,) arrays; predict(vd) -> (alpha, muX, muY, sigX, sigY)."""
     from sklearn.gaussian_process import GaussianProcessRegressor
