@@ -40,6 +40,16 @@ def gp_bench(n_train=2000, n_q=262144):
             print(f"gp mean+std: {ms:8.2f} ms per GP  ({n_q/ms/1e3:.1f} Mquery/s, variance contraction {flops/ms/1e9:.2f} TFLOP/s fp64)")
         else:
             print(f"gp mean    : {ms:8.3f} ms per GP  ({pairs/ms/1e6:.1f} Gpair/s)")
+    rows = d.enable_spectral_variance()
+    d.predict(q, True); torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(3):
+        d.predict(q, True)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"gp mean+std, spectral variance ({rows} projection rows): {ms:8.2f} ms per GP  ({n_q/ms/1e3:.1f} Mquery/s, "
+          f"{2.0 * n_q * d.n_pad * max(rows, 1) / ms / 1e9:.2f} TFLOP/s fp64, K_q round trip {2 * n_q * d.n_pad * 8 / 1e9:.1f} GB)")
     # spot parity
     qs = q[:512].cpu().numpy().reshape(-1, 1)
     from sklearn.gaussian_process import GaussianProcessRegressor
