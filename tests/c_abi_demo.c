@@ -1,7 +1,9 @@
 /*
  * Plain-C client of the C ABI (include/mr_rl_b200.h): no Python, no torch — device buffers from the CUDA
  * runtime, one env, noise-free, a few MR_Env.step calls.  Prints the positions so the test can compare
- * them with the golden vectors of the live reference.  Build:
+ * them with the golden vectors of the live reference.  With MR_DEMO_HOST=1 in the environment every step goes through
+ * mr_env_step_host in direct mode instead: actions and results live in page-locked HOST buffers (cudaHostAlloc) that the
+ * kernel reads and writes itself — the call a numpy-holding caller of the reference would make.  Build:
  *   gcc c_abi_demo.c -I../include -I/usr/local/cuda/include -L../mr_rl_b200/_lib -lmr_rl_b200 \
  *       -L/usr/local/cuda/lib64 -lcudart -o c_abi_demo
  */
@@ -48,6 +50,25 @@ int main(int argc, char** argv) {
     const double xy[2] = {x0, y0};
     CK(cudaMemcpy(init, xy, sizeof(xy), cudaMemcpyHostToDevice));
     MR(mr_env_reset(&st, n, MR_F64, &p, NULL, init, NULL, 1, &out, NULL));
+    const char* host_mode = getenv("MR_DEMO_HOST");
+    if (host_mode && host_mode[0] == '1') {
+        double *h_act, *h_obs, *h_rew;
+        uint8_t* h_done;
+        CK(cudaHostAlloc((void**)&h_act, 2 * pad * sizeof(double), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&h_obs, 5 * pad * sizeof(double), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&h_rew, pad * sizeof(double), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&h_done, pad, cudaHostAllocDefault));
+        memset(h_obs, 0, 5 * pad * sizeof(double));          /* the goal rows stay zero: they are never re-sent */
+        mr_host_step_io io = {h_act, NULL, h_obs, h_rew, h_done, pad, 0, 0};
+        for (int k = 0; k < steps; ++k) {
+            h_act[0] = atof(argv[5 + 2 * k]); h_act[1] = atof(argv[6 + 2 * k]);
+            MR(mr_env_step_host(NULL, &st, n, MR_F64, &p, NULL, &tt, &io, NULL, 0, NULL));   /* blocks until filled */
+            printf("%.17g %.17g %.17g %.17g %d\n", h_obs[0], h_obs[pad], h_obs[4 * pad], h_rew[0], (int)h_done[0]);
+        }
+        if (h_obs[2 * pad] != 0.0 || h_obs[3 * pad] != 0.0) return 5;
+        if (mr_env_step_host(NULL, &st, n, MR_F64, &p, NULL, &tt, NULL, NULL, 0, NULL) != MR_ERR_ARG) return 4;
+        return 0;
+    }
     for (int k = 0; k < steps; ++k) {
         const double a[2] = {atof(argv[5 + 2 * k]), atof(argv[6 + 2 * k])};
         CK(cudaMemcpy(act, a, sizeof(a), cudaMemcpyHostToDevice));

@@ -24,14 +24,17 @@ def test_c_client_compiles_and_links(tmp_path):
 
 
 @pytest.mark.gpu
-def test_c_client_reproduces_reference_trajectory(tmp_path, golden_single):
+@pytest.mark.parametrize("host", [False, True])
+def test_c_client_reproduces_reference_trajectory(tmp_path, golden_single, host):
+    """host=True: every step through mr_env_step_host with page-locked host buffers from cudaHostAlloc (direct mode)."""
     g = golden_single.case("c1_sigma0")
     exe = build_demo(str(tmp_path))
     T = 60
     args = [repr(float(g["init"][0])), repr(float(g["init"][1])), "1.0", str(T)]
     for k in range(T):
         args += [repr(float(g["actions"][k, 0])), repr(float(g["actions"][k, 1]))]
-    out = subprocess.run([exe, *args], capture_output=True, text=True, check=True).stdout
+    env = dict(os.environ, MR_DEMO_HOST="1" if host else "0")
+    out = subprocess.run([exe, *args], capture_output=True, text=True, check=True, env=env).stdout
     rows = np.array([[float(v) for v in line.split()] for line in out.strip().splitlines()])
     assert rows.shape == (T, 5)
     assert rel_err(rows[:, :2], g["pos"][:T]) < 1e-9 and rel_err(rows[:, 2], g["obs"][:T, 4]) < 1e-9
