@@ -200,6 +200,108 @@ gp_var_kernel(const double* __restrict__ kq, const double* __restrict__ linv, in
     }
 }
 
+// ---- fused posterior for the spectral form: mean AND std of 128 queries per CTA in one pass, K_q never leaves the SM ----
+// Per 16-column slice of the training set every thread evaluates 8 kernel values (one query row, 8 training points)
+// straight into the A tile of the DMMA pipeline (and into its running mean), the B tile (projection rows) streams in
+// with cp.async; C = K_q P^T accumulates on the FP64 tensor pipe; the epilogue squares and sums the 128 columns.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+gp_posterior_spectral_kernel(const double* __restrict__ q, int64_t n_q, const double* __restrict__ xs, const double* __restrict__ alpha,
+                             const double* __restrict__ proj, int n_pad, int proj_rows, double ls, double diag,
+                             double* __restrict__ mean, double* __restrict__ std) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double s_tab[64];
+    __shared__ double s_ssq[GP_BM];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_m = warp >> 2, warp_n = warp & 3, g = lane >> 2, t4 = lane & 3;
+    exp_table_init(s_tab);
+    if (tid < GP_BM) s_ssq[tid] = 0.0;
+    const int64_t m0 = (int64_t)blockIdx.x * GP_BM;
+    const int my_row = tid >> 1, my_half = tid & 1;            // this thread's query row and 8-column half of a slice
+    double qv[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) qv[c] = (m0 + my_row < n_q) ? q[(m0 + my_row) * DIM + c] / ls : 0.0;   // RBF scales both operands
+    const int k_tiles = n_pad / GP_BK;
+    double mean_acc = 0.0;
+    __syncthreads();
+
+    for (int rb = 0; rb < proj_rows / GP_BN; ++rb) {
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const double* b_src = proj + (int64_t)rb * GP_BN * n_pad;
+        auto load_b = [&](int stage, int kt) {                  // 128 rows x 16 doubles = 1024 16-byte chunks, 256 threads x 4
+            double* Bs = smem + stage * GP_STAGE + GP_BM * GP_LD;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int chunk = tid + it * 256;
+                const int r = chunk >> 3, cc = (chunk & 7) * 2;
+                cp_async16(Bs + r * GP_LD + cc, b_src + (int64_t)r * n_pad + kt * GP_BK + cc);
+            }
+        };
+        auto make_a = [&](int stage, int kt, bool with_mean) {  // kernel values of (my_row, 8 training points)
+            double* As = smem + stage * GP_STAGE + my_row * GP_LD + my_half * 8;
+            const int c0 = kt * GP_BK + my_half * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double d2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) { const double d = qv[c] - __ldg(xs + (int64_t)(c0 + j) * DIM + c); d2 = fma(d, d, d2); }
+                const double k = exp_neg_tab(-0.5 * d2, s_tab);
+                As[j] = k;
+                if (with_mean) mean_acc = fma(k, __ldg(alpha + c0 + j), mean_acc);
+            }
+        };
+        make_a(0, 0, rb == 0);
+        load_b(0, 0);
+        cp_async_commit();
+        if (k_tiles > 1) load_b(1, 1);
+        cp_async_commit();
+        for (int kt = 0; kt < k_tiles; ++kt) {
+            cp_async_wait<GP_STAGES - 2>();
+            __syncthreads();                                    // A(kt) written by everyone, B(kt) landed
+            if (kt + 2 < k_tiles) load_b((kt + 2) % GP_STAGES, kt + 2);
+            cp_async_commit();
+            if (kt + 1 < k_tiles) make_a((kt + 1) % GP_STAGES, kt + 1, rb == 0);
+            const double* As = smem + (kt % GP_STAGES) * GP_STAGE + (warp_m * 64) * GP_LD;
+            const double* Bs = smem + (kt % GP_STAGES) * GP_STAGE + GP_BM * GP_LD + (warp_n * 32) * GP_LD;
+#pragma unroll
+            for (int k4 = 0; k4 < GP_BK / 4; ++k4) {
+                double a[8], b[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = As[(i * 8 + g) * GP_LD + k4 * 4 + t4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Bs[(j * 8 + g) * GP_LD + k4 * 4 + t4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();                                        // the ring is reused by the next row block
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (t4 == 0) atomicAdd(&s_ssq[warp_m * 64 + i * 8 + g], s);
+        }
+    }
+    mean_acc += __shfl_xor_sync(0xffffffffu, mean_acc, 1);      // the two column halves of a row sit in adjacent lanes
+    __syncthreads();
+    if (my_half == 0 && m0 + my_row < n_q) {
+        mean[m0 + my_row] = mean_acc;
+        double v = diag - s_ssq[my_row];
+        if (v < 0.0) v = 0.0;                                   // sklearn clips negative variances to 0
+        std[m0 + my_row] = sqrt(v);
+    }
+}
+
 __global__ void gp_std_finish_kernel(const double* __restrict__ ssq, int64_t n_q, double diag, double* __restrict__ std) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_q) return;
@@ -325,6 +427,11 @@ gp_correct_heading_kernel(const double* __restrict__ vd, int64_t n, HeadingProbl
     }
 }
 
+static bool fused_spectral_disabled() {          // MR_GP_FUSED=0: keep the two-kernel path for the spectral form (A/B measurements)
+    static const bool off = [] { const char* e = getenv("MR_GP_FUSED"); return e && e[0] == '0'; }();
+    return off;
+}
+
 constexpr int64_t kGpChunk = 16384;   // queries per pass of the variance pipeline (K_q chunk = chunk * n_pad * 8 B)
 
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -403,6 +510,25 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
     if (!gp->linv) return fail(MR_ERR_ARG, "mr_gp_predict: std requested but model has no linv");
     if (gp->proj_rows < 0 || gp->proj_rows % MR_GP_PAD != 0 || gp->proj_rows > gp->n_pad)
         return fail(MR_ERR_ARG, "mr_gp_predict: proj_rows must be 0 or a multiple of %d up to n_pad", MR_GP_PAD);
+    if (gp->proj_rows > 0 && !fused_spectral_disabled()) {
+        // spectral form: one fused kernel, no K_q workspace
+        if ((uintptr_t)gp->linv & 15u) return fail(MR_ERR_ARG, "mr_gp_predict: projection must be 16-byte aligned");
+        static bool attr[kMaxDevices] = {};
+        const int dev = current_device();
+        if (!attr[dev]) {
+            cudaFuncSetAttribute(gp_posterior_spectral_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+            cudaFuncSetAttribute(gp_posterior_spectral_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+            attr[dev] = true;
+        }
+        const unsigned blocks = (unsigned)((n_q + GP_BM - 1) / GP_BM);
+        if (gp->dim == 1)
+            gp_posterior_spectral_kernel<1><<<blocks, 256, kDmmaSmemBytes, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->linv, gp->n_pad,
+                                                                               gp->proj_rows, gp->length_scale, 1.0 + gp->noise_level, mean, std);
+        else
+            gp_posterior_spectral_kernel<2><<<blocks, 256, kDmmaSmemBytes, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->linv, gp->n_pad,
+                                                                               gp->proj_rows, gp->length_scale, 1.0 + gp->noise_level, mean, std);
+        return check_launch("mr_gp_predict(spectral)");
+    }
     if (!workspace || workspace_bytes < mr_gp_workspace_bytes(gp, n_q, 1))
         return fail(MR_ERR_ARG, "mr_gp_predict: workspace too small (%lld < %lld)", (long long)workspace_bytes,
                     (long long)mr_gp_workspace_bytes(gp, n_q, 1));

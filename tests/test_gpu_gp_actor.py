@@ -91,7 +91,7 @@ def test_spectral_variance_matches_triangular_and_sklearn():
     assert 0 < rows <= 512 and rows % 128 == 0                   # ~80 significant eigenvalues at l = 0.2 on [-pi, pi]
     m1, s1 = gp.predict(q, True)
     mr, sr = sk.predict(q.reshape(-1, 1), return_std=True)
-    assert torch.equal(m0, m1)
+    assert float((m1 - m0).abs().max()) < 1e-11                  # fused kernel: another summation order (|mean| ~ 0.5)
     assert float(((s1 - s0).abs() / s0).max()) < 1e-9
     assert np.allclose(s1.cpu().numpy(), sr, rtol=1e-6, atol=1e-9) and np.allclose(m1.cpu().numpy(), mr, rtol=1e-8, atol=1e-8)
     # outside the training range too (the std grows to the prior there)

@@ -49,7 +49,7 @@ def gp_bench(n_train=2000, n_q=262144):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     print(f"gp mean+std, spectral variance ({rows} projection rows): {ms:8.2f} ms per GP  ({n_q/ms/1e3:.1f} Mquery/s, "
-          f"{2.0 * n_q * d.n_pad * max(rows, 1) / ms / 1e9:.2f} TFLOP/s fp64, K_q round trip {2 * n_q * d.n_pad * 8 / 1e9:.1f} GB)")
+          f"{2.0 * n_q * d.n_pad * max(rows, 1) / ms / 1e9:.2f} TFLOP/s fp64; fused kernel, K_q stays on chip; MR_GP_FUSED=0 for the two-kernel path)")
     # spot parity
     qs = q[:512].cpu().numpy().reshape(-1, 1)
     from sklearn.gaussian_process import GaussianProcessRegressor
