@@ -204,6 +204,8 @@ gp_var_kernel(const double* __restrict__ kq, const double* __restrict__ linv, in
 // Per 16-column slice of the training set every thread evaluates 8 kernel values (one query row, 8 training points)
 // straight into the A tile of the DMMA pipeline (and into its running mean), the B tile (projection rows) streams in
 // with cp.async; C = K_q P^T accumulates on the FP64 tensor pipe; the epilogue squares and sums the 128 columns.
+// (Training inputs / alpha are read with __ldg: staging them in shared memory per CTA was measured slower at config-3
+// size, 5.98 vs 5.59 ms per GP — 2048 CTAs each copying 48 KB costs more than the L1-resident reads.)
 template <int DIM>
 __global__ void __launch_bounds__(256)
 gp_posterior_spectral_kernel(const double* __restrict__ q, int64_t n_q, const double* __restrict__ xs, const double* __restrict__ alpha,

@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:env_step_tma -s 
 ncu --set full --clock-control none --import-source on -k regex:env_step_tma -s 8 -c 1 -f -o gpurun_out/prof_step_sigma0 $CMD --sigma 0 > gpurun_out/ncu_s0.log 2>&1
 PCMD="python tools/profile_paths.py"
 $PCMD > gpurun_out/paths_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"env_rollout_kernel|gp_var_kernel|gp_kq_mean" -c 8 -f -o gpurun_out/prof_paths $PCMD > gpurun_out/ncu_paths.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"env_rollout_kernel|gp_var_kernel|gp_kq_mean|gp_posterior_spectral" -c 8 -f -o gpurun_out/prof_paths $PCMD > gpurun_out/ncu_paths.log 2>&1
 NCMD="python tools/next_rows_once.py"
 $NCMD > gpurun_out/next_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/next_rows_launches.csv $NCMD > gpurun_out/ncu_next_launches.log 2>&1

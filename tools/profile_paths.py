@@ -32,5 +32,8 @@ gp = DeviceGP.fit(X, y, 0.2, 0.008, device="cuda:0")
 q = torch.rand(nq, device="cuda:0", dtype=torch.float64) * 6.28 - 3.14
 for _ in range(2):
     mean, std = gp.predict(q, True)
+rows = gp.enable_spectral_variance()          # verified low-rank form: the fused posterior kernel
+for _ in range(2):
+    mean, std = gp.predict(q, True)
 torch.cuda.synchronize()
 print("ok", float(mean.mean()), float(std.mean()), env.stats_dict()["env_steps"])
