@@ -361,8 +361,9 @@ def run_ours(args):
                     "mean_std_ms_both_gps": gms, "mean_only_ms_both_gps": gmm, "queries_per_s_mean_std": 262144 / (gms * 1e-3),
                     "variance_projection_rows": proj_rows,
                     "variance_contraction_tflops_fp64": sum(2 * 262144 * 2048.0 * (r if r else 1024) for r in proj_rows) / (gms * 1e-3) / 1e12,
-                    "kernels": "gp_kq_mean_kernel (fp64 exp) + gp_var_kernel (fp64 DMMA m8n8k4; spectral projection rows "
-                               "instead of the triangular L^-1 when verified exact to 1e-9)"}
+                    "kernels": "gp_posterior_spectral_kernel: mean + std fused, kernel values generated into the fp64 DMMA "
+                               "(m8n8k4) pipeline, spectral projection rows verified exact to 1e-9 (else gp_kq_mean_kernel + "
+                               "triangular gp_var_kernel)"}
                 del gps
             except Exception as ex:                                  # never let a side number break the headline
                 extras["config3_gp_262k_queries_2k_train"] = {"error": str(ex)[:160]}
