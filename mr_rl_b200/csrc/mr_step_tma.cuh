@@ -21,6 +21,10 @@ namespace mr {
 // fp32 128 -> 27.6 us, 256 -> 25.6 us.  Later, with generated noise (sigma 0 / 1, fp64): 128 -> 29.1 / 32.8 us,
 // 64 -> 28.8 / 35.6 us, 32 (one warp per CTA, no CTA barrier needed) -> 30.8 / 36.3 us; and issuing the loads from
 // warp 0 and the stores from warp 1 (to halve the issuing warp's extra work): 28.6 / 33.8 us — no gain.
+// Also measured: replacing the two CTA barriers per tile by mbarrier hand-offs (consumers arrive on "inputs read" /
+// "outputs written" barriers that only the issuing thread waits on, plus an "output stage free" barrier for the
+// consumers), so warps never wait for each other: 36.1 / 40.9 us with 128 arrivals, 37.0 / 41.5 us with one arrival
+// per warp — the barriers are the cheaper mechanism here.
 #ifdef MR_TILE
 template <class T> struct TileOf { static constexpr int value = MR_TILE; };
 #else
