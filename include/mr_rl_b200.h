@@ -354,6 +354,19 @@ int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, 
  * Sampling in that path is mr_replay_sample's. */
 int64_t mr_ddpg_workspace_bytes(int32_t batch);
 
+/* The two halves of the data-parallel update as separate steps, for learners that exchange gradients between ranks
+ * (one process per GPU, each with its own replay shard): mr_ddpg_gradients leaves the summed gradient of this rank's
+ * minibatch in grad_out — which = 0: critic, mr_critic_param_count() + 2 floats (the last two: the sums of the squared TD errors
+ * and of Q over the minibatch); which = 1: actor, mr_actor_param_count() floats, through the CURRENT
+ * critic — the caller all-reduces it (NCCL) and hands it to mr_ddpg_apply with grad_scale = 1 / world_size, which does
+ * Adam and the soft target update.  Order per update: gradients(0), apply(0), gradients(1), apply(1); both gradient
+ * calls of one update see the same rows (given, or regenerated from (seed, update_index)). */
+int mr_ddpg_gradients(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
+                      uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, int32_t which, float* grad_out,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int mr_ddpg_apply(const mr_ddpg_state* st, int32_t which, const float* grad, double grad_scale, int64_t update_index,
+                  const mr_ddpg_hyper* hp, void* stream);
+
 /* `batch` distinct ring rows out of the first `count`, uniformly at random (random.sample, RL/MR_ddpg.py:43-46), in
  * parallel: a keyed bijection (4-round Feistel network, keys from Philox(seed; update_index)) of a power-of-four domain
  * cycle-walked into [0, count).  indices_out: device int64 [batch]. */

@@ -467,6 +467,30 @@ __global__ void ddpg_reduce_adam_kernel(float* __restrict__ p, float* __restrict
     }
 }
 
+// ---- the same two halves as separate steps, for learners that exchange gradients (one rank per GPU): slabs -> one
+//      gradient vector (fixed order), and Adam + soft target update from a (reduced) gradient vector --------------------
+__global__ void ddpg_reduce_kernel(const float* __restrict__ slabs, int n_slabs, int n, float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float g = 0.f;
+    for (int c = 0; c < n_slabs; ++c) g += slabs[(int64_t)c * kSlab + k];
+    out[k] = g;
+}
+
+__global__ void ddpg_apply_kernel(float* __restrict__ p, float* __restrict__ p_target, float* __restrict__ m, float* __restrict__ v,
+                                  const float* __restrict__ grad, float grad_scale, int n, int frozen_lo0, int frozen_hi0,
+                                  int frozen_lo1, int frozen_hi1, float lr_t, DdpgHyper h) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || (k >= frozen_lo0 && k < frozen_hi0) || (k >= frozen_lo1 && k < frozen_hi1)) return;
+    const float g = grad[k] * grad_scale;
+    const float mk = h.beta1 * m[k] + (1.f - h.beta1) * g;
+    const float vk = h.beta2 * v[k] + (1.f - h.beta2) * g * g;
+    m[k] = mk; v[k] = vk;
+    const float pk = p[k] - lr_t * mk / (sqrtf(vk) + h.eps);
+    p[k] = pk;
+    p_target[k] = h.tau * pk + (1.f - h.tau) * p_target[k];
+}
+
 // ---- minibatch rows without replacement, any size, in parallel: a keyed bijection of [0, 2^(2w)) >= count (4-round
 //      Feistel network, round keys from Philox(seed; update index)) walked until it lands below count -----------------------
 __global__ void replay_sample_kernel(int64_t count, int batch, PhiloxKeys keys, uint64_t update_index, int64_t* __restrict__ idx) {
@@ -657,6 +681,76 @@ int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, 
                                                                        slabs, ctas, kActorParams, kOffM1, kOffW2, kOffM2, kOffW3,
                                                                        h.lr_actor * corr, h, inv_b, nullptr);
     return check_launch("mr_ddpg_update");
+}
+
+int mr_ddpg_gradients(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
+                      uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, int32_t which, float* grad_out,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace mr;
+    if (!st || !st->actor || !st->actor_target || !st->critic || !st->critic_target) return fail(MR_ERR_ARG, "mr_ddpg_gradients: null learner state");
+    if (!rb || !rb->s || !rb->a || !rb->r || !rb->d || !rb->s2) return fail(MR_ERR_ARG, "mr_ddpg_gradients: null replay buffer");
+    if (!hp || !grad_out) return fail(MR_ERR_ARG, "mr_ddpg_gradients: null argument");
+    if (which != 0 && which != 1) return fail(MR_ERR_ARG, "mr_ddpg_gradients: which must be 0 (critic) or 1 (actor)");
+    if (batch <= 0) return fail(MR_ERR_ARG, "mr_ddpg_gradients: bad batch");
+    if (count < batch || count > rb->capacity) return fail(MR_ERR_ARG, "mr_ddpg_gradients: need batch <= count <= capacity");
+    if (!workspace || workspace_bytes < mr_ddpg_workspace_bytes(batch)) return fail(MR_ERR_ARG, "mr_ddpg_gradients: workspace too small");
+    if ((uintptr_t)workspace & 15u) return fail(MR_ERR_ARG, "mr_ddpg_gradients: workspace must be 16-byte aligned");
+    DdpgHyper h{(float)hp->gamma, (float)hp->tau, (float)hp->lr_actor, (float)hp->lr_critic, (float)hp->action_bound[0],
+                (float)hp->action_bound[1], (float)hp->adam_beta1, (float)hp->adam_beta2, (float)hp->adam_eps};
+    PhiloxKeys keys;
+    philox_make_keys(seed, keys);
+    cudaStream_t s = (cudaStream_t)stream;
+    static bool attr[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!attr[dev]) {
+        cudaFuncSetAttribute(ddpg_critic_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DdpgSmem));
+        cudaFuncSetAttribute(ddpg_actor_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DdpgSmem));
+        attr[dev] = true;
+    }
+    int64_t* idx = (int64_t*)workspace;
+    float* slabs = (float*)((char*)workspace + (((int64_t)batch * 8 + 63) / 64) * 64);
+    const int tiles = (batch + kTile - 1) / kTile;
+    static int sm_counts[kMaxDevices] = {};
+    if (!sm_counts[dev]) cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_counts[dev] > 0 ? sm_counts[dev] : 1;
+    const int ctas = tiles < sms ? tiles : (sms < kMaxCtas ? sms : kMaxCtas);
+    // the same rows for the critic and the actor call of one update: given, or regenerated from (seed, update_index)
+    if (indices) cudaMemcpyAsync(idx, indices, (size_t)batch * 8, cudaMemcpyDeviceToDevice, s);
+    else replay_sample_kernel<<<(batch + 255) / 256, 256, 0, s>>>(count, batch, keys, (uint64_t)update_index, idx);
+    if (which == 0) {
+        ddpg_critic_grad_kernel<<<ctas, kDdpgThreads, sizeof(DdpgSmem), s>>>(st->actor_target, st->critic, st->critic_target, rb->s, rb->a,
+                                                                             rb->r, rb->d, rb->s2, idx, batch, h, slabs);
+        ddpg_reduce_kernel<<<(kCriticParams + 2 + 255) / 256, 256, 0, s>>>(slabs, ctas, kCriticParams + 2, grad_out);
+    } else {
+        ddpg_actor_grad_kernel<<<ctas, kDdpgThreads, sizeof(DdpgSmem), s>>>(st->actor, st->critic, rb->s, rb->a, rb->r, rb->d, rb->s2, idx,
+                                                                            batch, h, slabs);
+        ddpg_reduce_kernel<<<(kActorParams + 255) / 256, 256, 0, s>>>(slabs, ctas, kActorParams, grad_out);
+    }
+    return check_launch("mr_ddpg_gradients");
+}
+
+int mr_ddpg_apply(const mr_ddpg_state* st, int32_t which, const float* grad, double grad_scale, int64_t update_index,
+                  const mr_ddpg_hyper* hp, void* stream) {
+    using namespace mr;
+    if (!st || !st->actor || !st->actor_target || !st->critic || !st->critic_target || !st->adam_actor_m || !st->adam_actor_v ||
+        !st->adam_critic_m || !st->adam_critic_v)
+        return fail(MR_ERR_ARG, "mr_ddpg_apply: null learner state");
+    if (!hp || !grad) return fail(MR_ERR_ARG, "mr_ddpg_apply: null argument");
+    if (which != 0 && which != 1) return fail(MR_ERR_ARG, "mr_ddpg_apply: which must be 0 (critic) or 1 (actor)");
+    if (update_index < 1) return fail(MR_ERR_ARG, "mr_ddpg_apply: update_index is Adam's step count, starting at 1");
+    DdpgHyper h{(float)hp->gamma, (float)hp->tau, (float)hp->lr_actor, (float)hp->lr_critic, (float)hp->action_bound[0],
+                (float)hp->action_bound[1], (float)hp->adam_beta1, (float)hp->adam_beta2, (float)hp->adam_eps};
+    const float t = (float)update_index;
+    const float corr = sqrtf(1.f - powf(h.beta2, t)) / (1.f - powf(h.beta1, t));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (which == 0)
+        ddpg_apply_kernel<<<(kCriticParams + 255) / 256, 256, 0, s>>>(st->critic, st->critic_target, st->adam_critic_m, st->adam_critic_v, grad,
+                                                                      (float)grad_scale, kCriticParams, kC_Mc, kC_T1, 0, 0, h.lr_critic * corr, h);
+    else
+        ddpg_apply_kernel<<<(kActorParams + 255) / 256, 256, 0, s>>>(st->actor, st->actor_target, st->adam_actor_m, st->adam_actor_v, grad,
+                                                                     (float)grad_scale, kActorParams, kOffM1, kOffW2, kOffM2, kOffW3,
+                                                                     h.lr_actor * corr, h);
+    return check_launch("mr_ddpg_apply");
 }
 
 }  // extern "C"

@@ -209,6 +209,44 @@ class DDPGLearner:
         self.kernel_launches += 1
         return self._info
 
+    def update_distributed(self, replay, batch_size=64, indices=None, group=None):
+        """The same update with the gradient exchange of a data-parallel learner (one process per GPU, each with its own
+        replay shard and the same parameters): every rank computes the gradients of ITS minibatch, the gradient vectors
+        are summed over the ranks (torch.distributed all_reduce, NCCL) and every rank applies the mean — the effective
+        minibatch is world_size * batch_size.  Without an initialised process group this is the single-rank split path.
+        Returns the device tensor [critic loss, mean Q] over the global minibatch."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        idx_ptr = None
+        if indices is not None:
+            indices = torch.as_tensor(indices, dtype=torch.int64, device=self.device).contiguous()
+            batch_size = int(indices.numel())
+            idx_ptr = indices.data_ptr()
+        ws_bytes = int(self.lib.mr_ddpg_workspace_bytes(int(batch_size)))
+        if self._ws is None or self._ws.numel() * 8 < ws_bytes:
+            self._ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=self.device)
+        if getattr(self, "_gbuf", None) is None:
+            self._gbuf = torch.zeros(self.actor.numel() + 8, dtype=torch.float32, device=self.device)
+        g = self._gbuf
+        self.updates += 1
+        n_c, n_a = self.critic.numel(), self.actor.numel()
+        seed = self.seed ^ replay.random_seed
+        with torch.cuda.device(self.device):
+            for which, n in ((0, n_c + 2), (1, n_a)):
+                rc = self.lib.mr_ddpg_gradients(C.byref(self._c), C.byref(replay._c), replay.count, int(batch_size), idx_ptr, seed,
+                                                self.updates, C.byref(self.hyper), which, g.data_ptr(), self._ws.data_ptr(),
+                                                ws_bytes, _stream(self.device))
+                L.check(rc, "mr_ddpg_gradients")
+                if world > 1:
+                    dist.all_reduce(g[:n], group=group)
+                if which == 0:
+                    self._info.copy_(g[n_c:n_c + 2] / float(batch_size * world))
+                rc = self.lib.mr_ddpg_apply(C.byref(self._c), which, g.data_ptr(), 1.0 / world, self.updates, C.byref(self.hyper),
+                                            _stream(self.device))
+                L.check(rc, "mr_ddpg_apply")
+        self.kernel_launches += 8
+        return self._info
+
     def actor_params(self, target=False):
         return _unpack(self.actor_target if target else self.actor, ACTOR_ORDER, ACTOR_SHAPES)
 

@@ -247,3 +247,40 @@ def test_wide_update_with_internal_sampling_is_deterministic():
         assert torch.equal(ia, ib) and torch.isfinite(ia).all()
     assert torch.equal(a.actor, b.actor) and torch.equal(a.critic_target, b.critic_target)
     assert not torch.equal(a.actor, make_pair(4)[0].actor)
+
+
+def test_split_gradient_apply_path_equals_the_fused_wide_update():
+    """mr_ddpg_gradients + mr_ddpg_apply (the halves a multi-GPU learner puts its all-reduce between) on one rank ==
+    mr_ddpg_update on the data-parallel path (to the last bits: the two Adam kernels may contract their FMAs differently)."""
+    rb, _ = fill_replay(20000, seed=3)
+    a, _ = make_pair(6)
+    b, _ = make_pair(6)
+    for _ in range(4):
+        ia = a.update(rb, 2048).clone()
+        ib = b.update_distributed(rb, 2048).clone()
+        assert torch.allclose(ia, ib, rtol=1e-6, atol=1e-7)
+    for x, y in ((a.actor, b.actor), (a.critic, b.critic), (a.actor_target, b.actor_target), (a.critic_target, b.critic_target)):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run through gpurun --gpus 2)")
+def test_two_rank_learner_matches_one_rank_on_the_joint_minibatch(tmp_path):
+    """Two processes (one per GPU, NCCL): each takes the gradients of its own 512 rows, all-reduces, applies the mean ==
+    one rank updating on the 1024 rows together (fp32 summation order aside); both ranks end with identical parameters."""
+    import os
+    import subprocess
+    import sys
+    out = tmp_path / "dist.pt"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "dist_ddpg_worker.py"), str(out)]
+    subprocess.run(cmd, check=True, cwd=root, timeout=300)
+    res = torch.load(out)
+    assert torch.equal(res["rank0_actor"], res["rank1_actor"]) and torch.equal(res["rank0_critic"], res["rank1_critic"])
+    rb, _ = fill_replay(4096, seed=11)
+    single, _ = make_pair(8)
+    for u in range(3):
+        idx = torch.cat([res["idx"][0][u], res["idx"][1][u]])
+        single.update(rb, indices=idx.cuda())
+    assert torch.allclose(single.critic.cpu(), res["rank0_critic"], atol=3e-6, rtol=2e-4)
+    assert torch.allclose(single.actor.cpu(), res["rank0_actor"], atol=3e-6, rtol=2e-4)
