@@ -205,7 +205,7 @@ typedef struct mr_gp_model {
     int32_t n_train;
     int32_t n_pad;
     int32_t dim;             /* 1 (Learning_module.py) or 2 (Learning_module_2d.py) */
-    int32_t proj_rows;       /* 0, or the number of projection rows (multiple of MR_GP_PAD) */
+    int32_t proj_rows;       /* 0, or the number of projection rows: 32, 64, 96 or a multiple of MR_GP_PAD */
     double length_scale;     /* kernel_.k1.length_scale */
     double noise_level;      /* kernel_.k2.noise_level */
 } mr_gp_model;

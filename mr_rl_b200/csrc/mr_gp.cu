@@ -206,7 +206,8 @@ gp_var_kernel(const double* __restrict__ kq, const double* __restrict__ linv, in
 // with cp.async; C = K_q P^T accumulates on the FP64 tensor pipe; the epilogue squares and sums the 128 columns.
 // (Training inputs / alpha are read with __ldg: staging them in shared memory per CTA was measured slower at config-3
 // size, 5.98 vs 5.59 ms per GP — 2048 CTAs each copying 48 KB costs more than the L1-resident reads.)
-template <int DIM>
+// NT = n8 column tiles per warp: the CTA covers 32 NT projection rows per pass (96 rows when ~80 eigenvalues matter)
+template <int DIM, int NT>
 __global__ void __launch_bounds__(256)
 gp_posterior_spectral_kernel(const double* __restrict__ q, int64_t n_q, const double* __restrict__ xs, const double* __restrict__ alpha,
                              const double* __restrict__ proj, int n_pad, int proj_rows, double ls, double diag,
@@ -227,17 +228,18 @@ gp_posterior_spectral_kernel(const double* __restrict__ q, int64_t n_q, const do
     double mean_acc = 0.0;
     __syncthreads();
 
-    for (int rb = 0; rb < proj_rows / GP_BN; ++rb) {
-        double acc[8][4][2];
+    constexpr int BN = 32 * NT;
+    for (int rb = 0; rb < proj_rows / BN; ++rb) {
+        double acc[8][NT][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        const double* b_src = proj + (int64_t)rb * GP_BN * n_pad;
-        auto load_b = [&](int stage, int kt) {                  // 128 rows x 16 doubles = 1024 16-byte chunks, 256 threads x 4
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const double* b_src = proj + (int64_t)rb * BN * n_pad;
+        auto load_b = [&](int stage, int kt) {                  // BN rows x 16 doubles = 8 BN 16-byte chunks, 256 threads x NT
             double* Bs = smem + stage * GP_STAGE + GP_BM * GP_LD;
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
+            for (int it = 0; it < NT; ++it) {
                 const int chunk = tid + it * 256;
                 const int r = chunk >> 3, cc = (chunk & 7) * 2;
                 cp_async16(Bs + r * GP_LD + cc, b_src + (int64_t)r * n_pad + kt * GP_BK + cc);
@@ -268,18 +270,18 @@ gp_posterior_spectral_kernel(const double* __restrict__ q, int64_t n_q, const do
             cp_async_commit();
             if (kt + 1 < k_tiles) make_a((kt + 1) % GP_STAGES, kt + 1, rb == 0);
             const double* As = smem + (kt % GP_STAGES) * GP_STAGE + (warp_m * 64) * GP_LD;
-            const double* Bs = smem + (kt % GP_STAGES) * GP_STAGE + GP_BM * GP_LD + (warp_n * 32) * GP_LD;
+            const double* Bs = smem + (kt % GP_STAGES) * GP_STAGE + GP_BM * GP_LD + (warp_n * 8 * NT) * GP_LD;
 #pragma unroll
             for (int k4 = 0; k4 < GP_BK / 4; ++k4) {
-                double a[8], b[4];
+                double a[8], b[NT];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) a[i] = As[(i * 8 + g) * GP_LD + k4 * 4 + t4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Bs[(j * 8 + g) * GP_LD + k4 * 4 + t4];
+                for (int j = 0; j < NT; ++j) b[j] = Bs[(j * 8 + g) * GP_LD + k4 * 4 + t4];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < NT; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
         }
         cp_async_wait<0>();
@@ -288,7 +290,7 @@ gp_posterior_spectral_kernel(const double* __restrict__ q, int64_t n_q, const do
         for (int i = 0; i < 8; ++i) {
             double s = 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+            for (int j = 0; j < NT; ++j) s += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             if (t4 == 0) atomicAdd(&s_ssq[warp_m * 64 + i * 8 + g], s);
@@ -510,25 +512,28 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
         return check_launch("mr_gp_predict(mean)");
     }
     if (!gp->linv) return fail(MR_ERR_ARG, "mr_gp_predict: std requested but model has no linv");
-    if (gp->proj_rows < 0 || gp->proj_rows % MR_GP_PAD != 0 || gp->proj_rows > gp->n_pad)
-        return fail(MR_ERR_ARG, "mr_gp_predict: proj_rows must be 0 or a multiple of %d up to n_pad", MR_GP_PAD);
+    if (gp->proj_rows < 0 || gp->proj_rows % 32 != 0 || gp->proj_rows > gp->n_pad ||
+        (gp->proj_rows > MR_GP_PAD && gp->proj_rows % MR_GP_PAD != 0))
+        return fail(MR_ERR_ARG, "mr_gp_predict: proj_rows must be 0, 32/64/96/128 or a multiple of %d up to n_pad", MR_GP_PAD);
+    if (gp->proj_rows % MR_GP_PAD != 0 && fused_spectral_disabled())
+        return fail(MR_ERR_UNSUPPORTED, "mr_gp_predict: the two-kernel path needs proj_rows in multiples of %d", MR_GP_PAD);
     if (gp->proj_rows > 0 && !fused_spectral_disabled()) {
         // spectral form: one fused kernel, no K_q workspace
         if ((uintptr_t)gp->linv & 15u) return fail(MR_ERR_ARG, "mr_gp_predict: projection must be 16-byte aligned");
-        static bool attr[kMaxDevices] = {};
-        const int dev = current_device();
-        if (!attr[dev]) {
-            cudaFuncSetAttribute(gp_posterior_spectral_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
-            cudaFuncSetAttribute(gp_posterior_spectral_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
-            attr[dev] = true;
-        }
         const unsigned blocks = (unsigned)((n_q + GP_BM - 1) / GP_BM);
-        if (gp->dim == 1)
-            gp_posterior_spectral_kernel<1><<<blocks, 256, kDmmaSmemBytes, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->linv, gp->n_pad,
-                                                                               gp->proj_rows, gp->length_scale, 1.0 + gp->noise_level, mean, std);
-        else
-            gp_posterior_spectral_kernel<2><<<blocks, 256, kDmmaSmemBytes, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->linv, gp->n_pad,
-                                                                               gp->proj_rows, gp->length_scale, 1.0 + gp->noise_level, mean, std);
+        const int nt = gp->proj_rows >= MR_GP_PAD ? 4 : gp->proj_rows / 32;
+        auto launch = [&](auto kernel) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
+            kernel<<<blocks, 256, kDmmaSmemBytes, s>>>(q, n_q, gp->x_train_scaled, gp->alpha, gp->linv, gp->n_pad, gp->proj_rows,
+                                                       gp->length_scale, 1.0 + gp->noise_level, mean, std);
+        };
+        if (gp->dim == 1) {
+            if (nt == 4) launch(gp_posterior_spectral_kernel<1, 4>); else if (nt == 3) launch(gp_posterior_spectral_kernel<1, 3>);
+            else if (nt == 2) launch(gp_posterior_spectral_kernel<1, 2>); else launch(gp_posterior_spectral_kernel<1, 1>);
+        } else {
+            if (nt == 4) launch(gp_posterior_spectral_kernel<2, 4>); else if (nt == 3) launch(gp_posterior_spectral_kernel<2, 3>);
+            else if (nt == 2) launch(gp_posterior_spectral_kernel<2, 2>); else launch(gp_posterior_spectral_kernel<2, 1>);
+        }
         return check_launch("mr_gp_predict(spectral)");
     }
     if (!workspace || workspace_bytes < mr_gp_workspace_bytes(gp, n_q, 1))

@@ -133,7 +133,9 @@ class DeviceGP:
             mu, U = torch.linalg.eigh(K)                                   # ascending
             floor = self.noise_level + self.jitter
             r = int((mu - floor > 1e-12 * float(mu[-1])).sum())
-            r_pad = max(L.GP_PAD, (r + L.GP_PAD - 1) // L.GP_PAD * L.GP_PAD)
+            r_pad = max(32, (r + 31) // 32 * 32)                            # the fused kernel takes 32 / 64 / 96 / 128 rows ...
+            if r_pad > L.GP_PAD:
+                r_pad = (r + L.GP_PAD - 1) // L.GP_PAD * L.GP_PAD           # ... or whole 128-row passes
             if r_pad > max_fraction * n_pad:
                 return 0
             P = torch.zeros(r_pad, n_pad, dtype=torch.float64, device=self.device)
