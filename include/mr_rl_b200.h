@@ -238,6 +238,15 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
               double* lml_out, double* grad_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t mr_gp_fit_workspace_bytes(int32_t n_pad);
 
+/* mr_gp_correct_heading with the two GP means given as Chebyshev series on the search interval [-pi, pi]
+ * (mu(alpha) = sum_k coef[k] T_k(alpha / pi)): a GP mean with an RBF kernel is an entire function of the heading, so a
+ * few hundred coefficients carry it to the accuracy of the direct sum and one evaluation is a Clenshaw pass instead of
+ * 2 x n_train exponentials.  The caller samples the means with mr_gp_predict, builds the series and CHECKS them against
+ * mr_gp_predict before relying on this entry point (mr_rl_b200/learning_module.py does).  Same search, same outputs. */
+int mr_gp_correct_heading_cheb(const double* coef_x, const double* coef_y, int32_t n_coef, const double* vd, int64_t n,
+                               double a0, double freq, double drift_x, double drift_y, double* alpha_out, int32_t* nfev_out,
+                               void* stream);
+
 /* ---- DDPG actor forward (RL/MR_ddpg.py:124-149) --------------------------------------
  * Packed float32 parameters (input-major matrices W[in][out]):
  *   w1[5][64] b1[64] gamma1[64] beta1[64] mean1[64] var1[64]

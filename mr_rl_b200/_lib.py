@@ -89,7 +89,7 @@ GP_PAD = 128
 EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time_table_host", "mr_env_reset",
            "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_gp_fit", "mr_gp_fit_workspace_bytes", "mr_actor_param_count",
            "mr_critic_param_count", "mr_replay_add", "mr_ou_noise_add", "mr_ddpg_update", "mr_learn_preprocess",
-           "mr_learn_workspace_bytes", "mr_ddpg_workspace_bytes", "mr_replay_sample", "mr_actor_forward_env", "mr_ddpg_gradients", "mr_ddpg_apply", "mr_host_pipeline_create", "mr_host_pipeline_destroy", "mr_env_step_host",
+           "mr_learn_workspace_bytes", "mr_ddpg_workspace_bytes", "mr_replay_sample", "mr_actor_forward_env", "mr_ddpg_gradients", "mr_ddpg_apply", "mr_gp_correct_heading_cheb", "mr_host_pipeline_create", "mr_host_pipeline_destroy", "mr_env_step_host",
            "mr_actor_forward")
 
 _lib = None
@@ -156,6 +156,9 @@ def load():
     lib.mr_actor_forward_env.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double * 2, C.c_void_p,
                                          C.c_void_p]
     lib.mr_actor_forward_env.restype = C.c_int
+    lib.mr_gp_correct_heading_cheb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                               C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mr_gp_correct_heading_cheb.restype = C.c_int
     lib.mr_ddpg_gradients.argtypes = [P(DDPGState), P(Replay), C.c_int64, C.c_int32, C.c_void_p, C.c_uint64, C.c_int64,
                                       P(DDPGHyper), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mr_ddpg_gradients.restype = C.c_int

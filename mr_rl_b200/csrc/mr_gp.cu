@@ -347,20 +347,10 @@ __device__ __forceinline__ double gp_objective_warp(double alpha, double vdx, do
     return hp.a0f * hp.a0f + ex * ex + 2 * hp.a0f * c * ex + ey * ey + 2 * hp.a0f * s * ey;
 }
 
-__global__ void __launch_bounds__(256)
-gp_correct_heading_kernel(const double* __restrict__ vd, int64_t n, HeadingProblem hp, const double* __restrict__ xsx,
-                          const double* __restrict__ ax, double lsx, const double* __restrict__ xsy,
-                          const double* __restrict__ ay, double lsy, int n_pad, int n_train, double lo, double hi,
-                          double xatol, int maxfun, double* __restrict__ alpha_out, int32_t* __restrict__ nfev_out) {
-    __shared__ double s_tab[64];
-    exp_table_init(s_tab);
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= n) return;
-    const double vdx = vd[2 * row], vdy = vd[2 * row + 1];
-    auto f = [&](double x) { return gp_objective_warp(x, vdx, vdy, hp, xsx, ax, lsx, xsy, ay, lsy, n_pad, n_train, lane, s_tab); };
-
+// scipy.optimize._minimize_scalar_bounded (golden section + parabolic interpolation) on [lo, hi]; f is evaluated in the
+// order scipy evaluates it.  Returns the minimiser, *nfev = number of objective evaluations.
+template <class F>
+__device__ __forceinline__ double bounded_minimise(F f, double lo, double hi, double xatol, int maxfun, int* nfev) {
     const double sqrt_eps = sqrt(2.2e-16);
     const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
     double a = lo, b = hi;
@@ -425,10 +415,64 @@ gp_correct_heading_kernel(const double* __restrict__ vd, int64_t n, HeadingProbl
         tol2 = 2.0 * tol1;
         if (num >= maxfun) break;
     }
+    *nfev = num;
+    return xf;
+}
+
+__global__ void __launch_bounds__(256)
+gp_correct_heading_kernel(const double* __restrict__ vd, int64_t n, HeadingProblem hp, const double* __restrict__ xsx,
+                          const double* __restrict__ ax, double lsx, const double* __restrict__ xsy,
+                          const double* __restrict__ ay, double lsy, int n_pad, int n_train, double lo, double hi,
+                          double xatol, int maxfun, double* __restrict__ alpha_out, int32_t* __restrict__ nfev_out) {
+    __shared__ double s_tab[64];
+    exp_table_init(s_tab);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const double vdx = vd[2 * row], vdy = vd[2 * row + 1];
+    auto f = [&](double x) { return gp_objective_warp(x, vdx, vdy, hp, xsx, ax, lsx, xsy, ay, lsy, n_pad, n_train, lane, s_tab); };
+    int num = 0;
+    const double xf = bounded_minimise(f, lo, hi, xatol, maxfun, &num);
     if (lane == 0) {
         alpha_out[row] = xf;
         if (nfev_out) nfev_out[row] = num;
     }
+}
+
+// The same search with the two GP means replaced by their Chebyshev interpolants on [lo, hi] (the search interval): a GP
+// mean with an RBF kernel is an entire function of the heading, ~150 coefficients reproduce it to the accuracy of the
+// direct sum, and one Clenshaw pass costs ~300 FMAs instead of 2 x 2000 exponentials.  One thread per velocity.  The
+// caller builds and VERIFIES the interpolants against mr_gp_predict before using this kernel.
+__global__ void __launch_bounds__(128)
+gp_correct_heading_cheb_kernel(const double* __restrict__ vd, int64_t n, HeadingProblem hp, const double* __restrict__ cx,
+                               const double* __restrict__ cy, int n_coef, double lo, double hi, double xatol, int maxfun,
+                               double* __restrict__ alpha_out, int32_t* __restrict__ nfev_out) {
+    extern __shared__ __align__(16) double s_c[];                // [2][n_coef] interleaved (x, y)
+    for (int k = threadIdx.x; k < n_coef; k += blockDim.x) { s_c[2 * k] = cx[k]; s_c[2 * k + 1] = cy[k]; }
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const double vdx = vd[2 * row], vdy = vd[2 * row + 1];
+    const double mid = 0.5 * (lo + hi), inv_half = 2.0 / (hi - lo);
+    auto f = [&](double alpha) {
+        const double t = (alpha - mid) * inv_half, t2 = 2.0 * t;
+        double bx1 = 0.0, bx2 = 0.0, by1 = 0.0, by2 = 0.0;       // Clenshaw: b_k = c_k + 2 t b_{k+1} - b_{k+2}
+        for (int k = n_coef - 1; k >= 1; --k) {
+            const double2 c = *reinterpret_cast<const double2*>(s_c + 2 * k);
+            const double nx = fma(t2, bx1, c.x - bx2), ny = fma(t2, by1, c.y - by2);
+            bx2 = bx1; bx1 = nx; by2 = by1; by1 = ny;
+        }
+        const double mux = fma(t, bx1, s_c[0] - bx2), muy = fma(t, by1, s_c[1] - by2);
+        const double ex = mux + hp.dx - vdx, ey = muy + hp.dy - vdy;
+        double s, c;
+        sincos(alpha, &s, &c);
+        return hp.a0f * hp.a0f + ex * ex + 2 * hp.a0f * c * ex + ey * ey + 2 * hp.a0f * s * ey;
+    };
+    int num = 0;
+    const double xf = bounded_minimise(f, lo, hi, xatol, maxfun, &num);
+    alpha_out[row] = xf;
+    if (nfev_out) nfev_out[row] = num;
 }
 
 static bool fused_spectral_disabled() {          // MR_GP_FUSED=0: keep the two-kernel path for the spectral form (A/B measurements)
@@ -582,6 +626,24 @@ int mr_gp_correct_heading(const mr_gp_model* gpx, const mr_gp_model* gpy, const 
         vd, n, hp, gpx->x_train_scaled, gpx->alpha, gpx->length_scale, gpy->x_train_scaled, gpy->alpha, gpy->length_scale,
         gpx->n_pad, gpx->n_train, -3.141592653589793, 3.141592653589793, 1e-5, 500, alpha_out, nfev_out);
     return check_launch("mr_gp_correct_heading");
+}
+
+int mr_gp_correct_heading_cheb(const double* coef_x, const double* coef_y, int32_t n_coef, const double* vd, int64_t n,
+                               double a0, double freq, double drift_x, double drift_y, double* alpha_out, int32_t* nfev_out,
+                               void* stream) {
+    using namespace mr;
+    if (!coef_x || !coef_y) return fail(MR_ERR_ARG, "mr_gp_correct_heading_cheb: null coefficients");
+    if (n_coef < 1 || n_coef > 4096) return fail(MR_ERR_ARG, "mr_gp_correct_heading_cheb: need 1 <= n_coef <= 4096");
+    if (n < 0) return fail(MR_ERR_ARG, "mr_gp_correct_heading_cheb: bad n");
+    if (n == 0) return MR_OK;
+    if (!vd || !alpha_out) return fail(MR_ERR_ARG, "mr_gp_correct_heading_cheb: null vd/alpha_out");
+    HeadingProblem hp{a0 * freq, drift_x, drift_y};
+    const size_t smem = (size_t)n_coef * 2 * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(gp_correct_heading_cheb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    gp_correct_heading_cheb_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(vd, n, hp, coef_x, coef_y, n_coef, -3.141592653589793,
+                                                                               3.141592653589793, 1e-5, 500, alpha_out, nfev_out);
+    return check_launch("mr_gp_correct_heading_cheb");
 }
 
 int32_t mr_actor_param_count(void) { return mr::kActorParams; }

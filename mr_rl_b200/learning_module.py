@@ -18,6 +18,7 @@ from .gp import DeviceGP
 
 class LearningModule:
     spectral_variance = True     # evaluate GP variances through the low-rank spectral projection when it is exact to 1e-9
+    heading_surrogate = True     # search corrected headings on verified Chebyshev interpolants of the two GP means
 
     def __init__(self, device="cuda", fit="device", preprocess=None):
         """fit: "device" | "host" (sklearn).  preprocess: "device" | "host" (numpy/scipy as in the reference); defaults to
@@ -144,6 +145,42 @@ class LearningModule:
         if self.spectral_variance:                      # verified against the triangular form before it is used
             self._dx.enable_spectral_variance()
             self._dy.enable_spectral_variance()
+        self._cheb = None
+        if self.heading_surrogate and self._dx.dim == 1:
+            self._build_heading_surrogate()
+
+    def _build_heading_surrogate(self, n_nodes=2048, n_probe=1024, tol=1e-10):
+        """Chebyshev interpolants of the two GP means on the search interval [-pi, pi] of LearningModule.predict
+        (Learning_module.py:215).  The means are entire functions of the heading (sums of Gaussians of width l), so
+        their Chebyshev coefficients fall off like exp(-(k l / pi)^2 / 2); the series is cut where they reach the
+        rounding floor of the sampled means.  Accepted only if it reproduces mr_gp_predict at ``n_probe`` random headings to ``tol`` (relative
+        to the largest mean), else the search keeps summing the kernel directly."""
+        dev = torch.device(self.device)
+        j = torch.arange(n_nodes, dtype=torch.float64, device=dev)
+        t = torch.cos(math.pi * (j + 0.5) / n_nodes)                       # Chebyshev nodes on [-1, 1]
+        mx, my = self.gp_batch(t * math.pi, False)
+        k = torch.arange(n_nodes, dtype=torch.float64, device=dev)
+        basis = torch.cos(math.pi * torch.outer(k, j + 0.5) / n_nodes)    # T_k(t_j); a 2048^2 matrix, built once per model
+        coef = torch.stack([basis @ mx, basis @ my]) * (2.0 / n_nodes)
+        coef[:, 0] *= 0.5
+        mag = coef.abs().max(dim=0).values
+        # the coefficients fall to the rounding floor of the sampled means (~1e-15 of the largest) and stay there: cut the
+        # series where they last stand clear of that floor
+        floor = float(mag[n_nodes // 2:].max())
+        keep = torch.nonzero(mag > max(1e-15 * float(mag.max()), 8.0 * floor)).flatten()
+        n_coef = int(keep.max()) + 1 if keep.numel() else 1
+        if n_coef > n_nodes // 2:                                          # not resolved: a rougher kernel than the grid
+            return
+        coef = coef[:, :n_coef].contiguous()
+        g = torch.Generator(device=dev).manual_seed(1)
+        a = (torch.rand(n_probe, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * math.pi
+        ex, ey = self.gp_batch(a, False)
+        tt = a / math.pi
+        Tk = torch.cos(torch.outer(torch.arange(n_coef, dtype=torch.float64, device=dev), torch.acos(tt.clamp(-1, 1))))
+        err = max(float((coef[0] @ Tk - ex).abs().max()), float((coef[1] @ Tk - ey).abs().max()))
+        scale = max(float(ex.abs().max()), float(ey.abs().max()), 1e-300)
+        if err <= tol * scale:
+            self._cheb = coef
 
     def set_models(self, gprX, gprY, a0, freq, Dx=0.0, Dy=0.0):
         """Install already-fitted GPRs (sklearn or DeviceGPR; e.g. fixed kernels, optimizer=None)."""
@@ -200,10 +237,17 @@ class LearningModule:
         alpha = torch.empty(n, dtype=torch.float64, device=vd.device)
         nfev = torch.empty(n, dtype=torch.int32, device=vd.device)
         stream = C.c_void_p(torch.cuda.current_stream(vd.device).cuda_stream)
-        rc = L.load().mr_gp_correct_heading(C.byref(self._dx._c), C.byref(self._dy._c), vd.data_ptr(), n, float(self.a0),
-                                            float(self.freq), float(self.Dx), float(self.Dy), alpha.data_ptr(),
-                                            nfev.data_ptr(), stream)
-        L.check(rc, "mr_gp_correct_heading")
+        cheb = getattr(self, "_cheb", None)
+        if cheb is not None:
+            rc = L.load().mr_gp_correct_heading_cheb(cheb[0].data_ptr(), cheb[1].data_ptr(), cheb.shape[1], vd.data_ptr(), n,
+                                                     float(self.a0), float(self.freq), float(self.Dx), float(self.Dy),
+                                                     alpha.data_ptr(), nfev.data_ptr(), stream)
+            L.check(rc, "mr_gp_correct_heading_cheb")
+        else:
+            rc = L.load().mr_gp_correct_heading(C.byref(self._dx._c), C.byref(self._dy._c), vd.data_ptr(), n, float(self.a0),
+                                                float(self.freq), float(self.Dx), float(self.Dy), alpha.data_ptr(),
+                                                nfev.data_ptr(), stream)
+            L.check(rc, "mr_gp_correct_heading")
         mx, my, sx, sy = self.gp_batch(alpha, True)
         return (alpha, mx, my, sx, sy, nfev) if return_nfev else (alpha, mx, my, sx, sy)
 

@@ -283,9 +283,12 @@ def test_run_sim_matches_live_reference(golden_single):
     assert np.allclose(time, np.linspace(0, (len(X) - 1) / 30.0, len(X)))
 
 
-def test_device_heading_correction_matches_reference_predict(golden_gp):
+@pytest.mark.parametrize("surrogate", [True, False])
+def test_device_heading_correction_matches_reference_predict(golden_gp, surrogate):
     """LearningModule.predict (bounded scalar minimisation with the GPs in the loop) on the device vs the
-    live reference's outputs (alpha, muX, muY, sigX, sigY) and vs scipy's minimiser on the oracle objective."""
+    live reference's outputs (alpha, muX, muY, sigX, sigY) and vs scipy's minimiser on the oracle objective.
+    surrogate=True: the search runs on the verified Chebyshev interpolants of the two GP means (the default);
+    False: on the direct kernel sums."""
     from scipy.optimize import minimize_scalar
     from sklearn.gaussian_process import GaussianProcessRegressor
     from sklearn.gaussian_process.kernels import RBF, WhiteKernel
@@ -296,7 +299,11 @@ def test_device_heading_correction_matches_reference_predict(golden_gp):
     gY = GaussianProcessRegressor(kernel=RBF(0.25) + WhiteKernel(0.008), optimizer=None).fit(X, g["yy"])
     a0, freq, Dx, Dy = g["hyper"]
     lm = LearningModule(device="cuda:0")
+    lm.heading_surrogate = surrogate
     lm.set_models(gX, gY, a0, freq, Dx, Dy)
+    assert (lm._cheb is not None) == surrogate
+    if surrogate:
+        assert 32 < lm._cheb.shape[1] < 600                   # ~exp(-(k l / pi)^2 / 2) decay at l = 0.2: a few hundred terms
     vd = g["vd"]
     alpha, mx, my, sx, sy, nfev = lm.predict_batch(vd, return_nfev=True)
     alpha = alpha.cpu().numpy()

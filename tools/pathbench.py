@@ -104,6 +104,18 @@ def heading_bench(n=262144, n_train=2000):
     e0.record(); run(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     evals = float(nfev.sum())
+    if lm._cheb is not None:
+        a2 = torch.empty_like(alpha); nf2 = torch.empty_like(nfev)
+        cheb = lm._cheb
+        def run2():
+            return L.load().mr_gp_correct_heading_cheb(cheb[0].data_ptr(), cheb[1].data_ptr(), cheb.shape[1], vd.data_ptr(), n,
+                                                       1.5, 4.0, 0.2, -0.1, a2.data_ptr(), nf2.data_ptr(), None)
+        run2(); torch.cuda.synchronize()
+        e2, e3 = ev(), ev()
+        e2.record(); run2(); e3.record(); torch.cuda.synchronize()
+        d = (a2 - alpha).abs()
+        print(f"heading correction on Chebyshev interpolants ({cheb.shape[1]} coefficients per GP): {e2.elapsed_time(e3):8.3f} ms for {n} "
+              f"velocities; vs direct sums: max |d alpha| {float(d.max()):.2e}, same nfev in {float((nf2 == nfev).double().mean()) * 100:.2f} %")
     print(f"heading correction (bounded minimiser, 2 GPs in the loop): {ms:8.2f} ms for {n} velocities "
           f"({n/ms/1e3:.2f} M/s, mean nfev {evals/n:.1f}, {evals*n_train*2/ms/1e6:.1f} G kernel evals/s)")
     # CPU reference cost for scale: sklearn + scipy on one velocity
