@@ -395,10 +395,28 @@ def run_ours(args):
                     learner.update(rb, 64)
                 ev1.record()
                 torch.cuda.synchronize()
+                t_upd = ev0.elapsed_time(ev1) / 50 * 1e3
+                # LearningModule.predict for 262144 desired velocities on the config-3 GPs
+                from mr_rl_b200 import LearningModule
+                lm = LearningModule(device=dev)
+                g1 = DeviceGPR(optimizer=None, length_scale=0.2, noise_level=0.008, device=dev).fit(Xf, yf)
+                g2 = DeviceGPR(optimizer=None, length_scale=0.25, noise_level=0.008, device=dev).fit(Xf, 0.5 * yf)
+                lm.set_models(g1, g2, 1.5, 4.0, 0.2, -0.1)
+                ang = torch.rand(262144, device=dev, dtype=torch.float64) * 6.28 - 3.14
+                vdes = 6.0 * torch.stack([torch.cos(ang), torch.sin(ang)], 1)
+                lm.predict_batch(vdes)
+                torch.cuda.synchronize()
+                ev0.record()
+                lm.predict_batch(vdes)
+                ev1.record()
+                torch.cuda.synchronize()
+                t_head = ev0.elapsed_time(ev1)
                 extras["next_rows"] = {
+                    "lm_predict_batch_262k_ms": t_head,     # heading search + posterior (mean, std of both GPs) at the minimiser
+                    "corrected_headings_path": "Chebyshev interpolants of the GP means (verified)" if lm._cheb is not None else "direct kernel sums",
                     "gpr_search_n1970_5_restarts_s": t_fit, "gpr_objective_evals": gpr.n_objective_evals,
                     "gpr_theta": [float(v) for v in gpr.kernel_.theta],
-                    "ddpg_update_batch64_us": ev0.elapsed_time(ev1) / 50 * 1e3,
+                    "ddpg_update_batch64_us": t_upd,
                     "ddpg_train_iteration_4096_envs_ms": t_it * 1e3,
                     "note": "mr_gp_fit per objective evaluation; one mr_ddpg_update launch per learner update"}
                 del env_t, learner, rb
