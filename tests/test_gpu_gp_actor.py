@@ -324,3 +324,28 @@ def test_device_heading_correction_matches_reference_predict(golden_gp, surrogat
     # the scalar facade goes through the same kernel
     A, muX, muY, sigX, sigY = lm.predict(vd[0])
     assert abs(float(A) - ref[0, 0]) < 2e-5 and muX.shape == (1,)
+
+
+def test_cheb_heading_entry_point_argument_errors_and_constant_series():
+    """mr_gp_correct_heading_cheb: argument checks, and a closed-form case — with constant GP means (one coefficient each)
+    the objective is (a0 f)^2 + ex^2 + ey^2 + 2 a0 f (ex cos a + ey sin a), minimised at a = atan2(-ey, -ex)."""
+    import ctypes as C
+    from mr_rl_b200 import _lib as L
+    lib = L.load()
+    cx = torch.tensor([0.3], dtype=torch.float64, device="cuda:0")
+    cy = torch.tensor([-0.2], dtype=torch.float64, device="cuda:0")
+    vd = torch.tensor([[2.0, 1.0], [-1.0, 0.5], [0.1, -3.0]], dtype=torch.float64, device="cuda:0")
+    out = torch.empty(3, dtype=torch.float64, device="cuda:0")
+    nf = torch.empty(3, dtype=torch.int32, device="cuda:0")
+    assert lib.mr_gp_correct_heading_cheb(None, cy.data_ptr(), 1, vd.data_ptr(), 3, 1.5, 4.0, 0.0, 0.0, out.data_ptr(), None, None) != 0
+    assert lib.mr_gp_correct_heading_cheb(cx.data_ptr(), cy.data_ptr(), 0, vd.data_ptr(), 3, 1.5, 4.0, 0.0, 0.0, out.data_ptr(), None, None) != 0
+    assert b"n_coef" in lib.mr_last_error()
+    assert lib.mr_gp_correct_heading_cheb(cx.data_ptr(), cy.data_ptr(), 1, None, 3, 1.5, 4.0, 0.0, 0.0, out.data_ptr(), None, None) != 0
+    rc = lib.mr_gp_correct_heading_cheb(cx.data_ptr(), cy.data_ptr(), 1, vd.data_ptr(), 3, 1.5, 4.0, 0.05, -0.02, out.data_ptr(),
+                                        nf.data_ptr(), None)
+    assert rc == 0
+    ex = 0.3 + 0.05 - vd[:, 0].cpu().numpy()
+    ey = -0.2 - 0.02 - vd[:, 1].cpu().numpy()
+    want = np.arctan2(-ey, -ex)
+    assert np.max(np.abs(np.angle(np.exp(1j * (out.cpu().numpy() - want))))) < 2e-5
+    assert int(nf.min()) >= 5 and int(nf.max()) < 60
