@@ -68,8 +68,10 @@ class MR_Env:
     def __init__(self, type="continuous", action_dim=2, device="cuda", noise="philox", seed=0, noise_table=None):
         self.type = type
         self.action_dim = action_dim
-        self._vec = VecMREnv(1, device=device, dtype=torch.float64, noise=noise, seed=seed, noise_table=noise_table)
+        self._vec = VecMREnv(1, device=device, dtype=torch.float64, noise=noise, seed=seed, noise_table=noise_table,
+                             host_mapped_aux=True)
         v = self._vec
+        self._a_pin = torch.zeros(1, 2, dtype=torch.float64).pin_memory()      # the action, read by the kernel in place
         self.action_space = v.action_space
         self.observation_space = v.observation_space
         self.init_space = v.init_space
@@ -103,16 +105,19 @@ class MR_Env:
         v.params.is_mismatched = 1 if sim.is_mismatched else 0
         v.params.a0 = float(sim.a0)
         v.params.noise_var = float(sim.noise_var)
-        a = torch.tensor([[float(f_t), float(alpha_t)]], dtype=torch.float64, device=v.device)
-        obs_t, rew_t, done_t, _ = v.step(a)
-        packed = torch.cat([obs_t[0], v.state_prime[0], done_t[:1].to(torch.float64)]).cpu().numpy()
-        v.check_status()
+        # one launch, one stream synchronisation: the kernel reads the action from and writes obs / reward / done /
+        # state_prime / status to page-locked host memory itself (mr_env_step_host, direct mode)
+        self._a_pin[0, 0] = float(f_t)
+        self._a_pin[0, 1] = float(alpha_t)
+        obs_h, _, done_h, _ = v.step_host(self._a_pin)
+        if v._status[0] != 0:
+            v.check_status()
         self.counter += 1
-        obs = packed[:5].copy()
-        self.state_prime = sim.state_prime = packed[5:7].copy()
+        obs = obs_h[0].copy()
+        self.state_prime = sim.state_prime = v._sp[:, 0].numpy().copy()
         sim.last_state = obs[:2].copy()
         sim.current_action = np.array([f_t, alpha_t])
-        done = bool(packed[7] != 0)
+        done = bool(done_h[0])
         rew = 10                                              # MR_env.py:89
         self.last_pos = [obs[0], obs[1]]
         self.last_action = np.array([f_t, alpha_t])

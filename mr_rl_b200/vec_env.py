@@ -44,7 +44,7 @@ class VecMREnv:
     """
 
     def __init__(self, num_envs, device="cuda", dtype=torch.float64, noise="philox", seed=0, env_base=0,
-                 auto_reset=False, reward_mode="const", noise_table=None, time_table_len=4096):
+                 auto_reset=False, reward_mode="const", noise_table=None, time_table_len=4096, host_mapped_aux=False):
         self.lib = L.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -81,11 +81,14 @@ class VecMREnv:
         self._state = torch.zeros(5, npad, dtype=dtype, device=dev)          # x, y, fx, fy, h
         self._counter = torch.zeros(npad, dtype=torch.int32, device=dev)
         self._cursor = torch.zeros(npad, dtype=torch.int32, device=dev)
-        self._status = torch.zeros(npad, dtype=torch.uint8, device=dev)
+        # host_mapped_aux (the single-env facade): status flags and state_prime live in page-locked HOST memory that the
+        # kernels address directly, so a step needs no device->host read besides the one stream synchronisation
+        aux = (lambda *s, **k: torch.zeros(*s, **k).pin_memory()) if host_mapped_aux else (lambda *s, **k: torch.zeros(*s, device=dev, **k))
+        self._status = aux(npad, dtype=torch.uint8)
         self._obs = torch.zeros(5, npad, dtype=dtype, device=dev)            # x, y, gx, gy, d
         self._rew = torch.zeros(npad, dtype=dtype, device=dev)
         self._done = torch.zeros(npad, dtype=torch.uint8, device=dev)
-        self._sp = torch.zeros(2, npad, dtype=dtype, device=dev)             # Simulator.state_prime
+        self._sp = aux(2, npad, dtype=dtype)                                 # Simulator.state_prime
         self._stats = torch.zeros(L.STATS_LEN, dtype=torch.float64, device=dev)
         tt = np.zeros(int(time_table_len), dtype=np.float64)
         self.lib.mr_fill_time_table_host(tt.ctypes.data_as(C.c_void_p), len(tt), self.params.time_span)
@@ -262,10 +265,27 @@ class VecMREnv:
         host buffers itself — the device-side obs / rew / done rows are NOT refreshed by this call (state, counters
         and state_prime are).  ``host_mode = "staged"``: copies through the device rows in pipelined chunks."""
         n = self.num_envs
+        fast = self._pinned.get("fast")            # the same pinned action tensor as last time, direct mode: everything cached
+        if fast is not None and actions is fast[0] and self.host_mode == "direct":
+            _, io_ref, ret = fast
+            if torch.cuda.current_device() != self._dev_index:
+                with torch.cuda.device(self.device):
+                    return self.step_host(actions)
+            nz = self._noise_for(self.params.noise_var)
+            rc = self.lib.mr_env_step_host(None, self._b_state, n, self._dt, self._b_params, C.byref(nz), self._b_tt, io_ref,
+                                           self._b_out if self.want_state_prime else self._b_out_lean, 0,
+                                           torch.cuda.current_stream(self.device).cuda_stream)
+            if rc:
+                L.check(rc, "mr_env_step_host")
+            self.kernel_launches += 1
+            self._step_index += 1
+            return ret
         if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() \
                 and actions.dtype == self.dtype and actions.is_contiguous() and actions.numel() == 2 * n:
             a_pin = actions.view(n, 2)
+            in_place = True
         else:
+            in_place = False
             a_np = np.asarray(actions.numpy() if torch.is_tensor(actions) else actions)
             if a_np.size != 2 * n:
                 raise ValueError(f"actions must be [{n}, 2]")
@@ -298,7 +318,11 @@ class VecMREnv:
         L.check(rc, "mr_env_step_host")
         self.kernel_launches += max(chunks, 1)
         self._step_index += 1
-        return o_pin[:, :n].numpy().T, r_pin.numpy(), d_pin.numpy().view(np.bool_), {}
+        ret = (o_pin[:, :n].numpy().T, r_pin.numpy(), d_pin.numpy().view(np.bool_), {})
+        if in_place and chunks == 0:       # a caller that reuses its pinned action tensor skips all of the above next time
+            self._pinned["fast"] = (actions, C.byref(io), ret)
+            self._pinned["fast_io"] = io           # keep the struct alive
+        return ret
 
     # Host-buffer step strategy.  Measured at 2^20 envs (fp64, sigma = 1): staged 1 / 2 / 4 / 8 chunks 1.01 / 0.91 / 0.91 /
     # 0.99 ms (each of the 5 D2H pieces per chunk costs a few us of DMA set-up); direct 0.82 ms.  Tried and dropped: a
