@@ -21,7 +21,8 @@ class Simulator:
 
     def __init__(self, device="cuda", noise="philox", seed=0, noise_table=None, _vec=None):
         self._vec = _vec or VecMREnv(1, device=device, dtype=torch.float64, noise=noise, seed=seed,
-                                     noise_table=noise_table)
+                                     noise_table=noise_table, host_mapped_aux=True)
+        self._a_pin = torch.zeros(1, 2, dtype=torch.float64).pin_memory()
         self.time_span = self._vec.time_span          # MR_simulator.py:12
         self.number_iterations = 100                  # :13
         self.a0 = 0                                   # :16
@@ -50,11 +51,13 @@ class Simulator:
         v.params.a0 = float(self.a0)
         v.params.noise_var = float(self.noise_var)
         self.current_action = np.array([f_t, alpha_t])
-        a = torch.tensor([[float(f_t), float(alpha_t)]], dtype=torch.float64, device=v.device)
-        v.step(a)
-        v.check_status()
-        self.last_state = v.last_pos[0].cpu().numpy().copy()
-        self.state_prime = v.state_prime[0].cpu().numpy().copy()
+        self._a_pin[0, 0] = float(f_t)                  # same one-launch host step as MR_Env.step
+        self._a_pin[0, 1] = float(alpha_t)
+        obs_h, _, _, _ = v.step_host(self._a_pin)
+        if v._status[0] != 0:
+            v.check_status()
+        self.last_state = obs_h[0, :2].copy()
+        self.state_prime = v._sp[:, 0].numpy().copy() if v._sp.device.type == "cpu" else v.state_prime[0].cpu().numpy().copy()
         return self.last_state
 
     def get_state(self):
