@@ -2,6 +2,8 @@
 // per-(storage dtype, noise mode) launchers.  No CPU fallback exists: every call launches CUDA.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <initializer_list>
 #include <new>
 
 #include "mr_common.cuh"
@@ -9,6 +11,13 @@
 namespace mr {
 
 thread_local char g_err[512] = "";
+
+static int step_path_from_env() {
+    const char* e = getenv("MR_STEP_PATH");
+    if (!e) return 0;
+    return e[0] == 't' ? 1 : e[0] == 'v' ? 2 : e[0] == 's' ? 3 : e[0] == 'w' ? 4 : 0;
+}
+int g_step_path = step_path_from_env();
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -150,6 +159,13 @@ extern "C" {
 int mr_abi_version(void) { return MR_ABI_VERSION; }
 const char* mr_last_error(void) { return mr::g_err; }
 
+int mr_set_step_path(int32_t path) {
+    if (path < 0 || path > 4) return mr::fail(MR_ERR_ARG, "mr_set_step_path: path must be 0..4");
+    const int old = mr::g_step_path;
+    mr::g_step_path = path;
+    return old;
+}
+
 void mr_default_params(mr_sim_params* p) {
     if (!p) return;
     memset(p, 0, sizeof(*p));
@@ -204,12 +220,17 @@ struct mr_host_pipeline {
 
 int mr_host_pipeline_create(int32_t max_chunks, mr_host_pipeline** out) {
     if (!out || max_chunks < 1 || max_chunks > 64) return mr::fail(MR_ERR_ARG, "mr_host_pipeline_create: need 1 <= max_chunks <= 64");
-    mr_host_pipeline* pl = new (std::nothrow) mr_host_pipeline();
+    *out = nullptr;
+    mr_host_pipeline* pl = new (std::nothrow) mr_host_pipeline();    // value-initialised: every handle starts null
     if (!pl) return mr::fail(MR_ERR_CUDA, "mr_host_pipeline_create: out of host memory");
     pl->max_chunks = max_chunks;
     cudaGetDevice(&pl->device);
-    pl->ev_in = new (std::nothrow) cudaEvent_t[max_chunks];
-    pl->ev_k = new (std::nothrow) cudaEvent_t[max_chunks];
+    pl->ev_in = new (std::nothrow) cudaEvent_t[max_chunks]();
+    pl->ev_k = new (std::nothrow) cudaEvent_t[max_chunks]();
+    if (!pl->ev_in || !pl->ev_k) {
+        mr_host_pipeline_destroy(pl);
+        return mr::fail(MR_ERR_CUDA, "mr_host_pipeline_create: out of host memory");
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_k, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking);
@@ -219,16 +240,25 @@ int mr_host_pipeline_create(int32_t max_chunks, mr_host_pipeline** out) {
         e = cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_k[i], cudaEventDisableTiming);
     }
-    if (e != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_host_pipeline_create: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        mr_host_pipeline_destroy(pl);                                // frees whatever was created so far
+        return mr::fail(MR_ERR_CUDA, "mr_host_pipeline_create: %s", cudaGetErrorString(e));
+    }
     *out = pl;
     return MR_OK;
 }
 
 void mr_host_pipeline_destroy(mr_host_pipeline* pl) {
     if (!pl) return;
-    cudaStreamDestroy(pl->s_in); cudaStreamDestroy(pl->s_k); cudaStreamDestroy(pl->s_out);
-    cudaEventDestroy(pl->ev_start); cudaEventDestroy(pl->ev_done);
-    for (int i = 0; i < pl->max_chunks; ++i) { cudaEventDestroy(pl->ev_in[i]); cudaEventDestroy(pl->ev_k[i]); }
+    if (pl->s_in) cudaStreamDestroy(pl->s_in);
+    if (pl->s_k) cudaStreamDestroy(pl->s_k);
+    if (pl->s_out) cudaStreamDestroy(pl->s_out);
+    if (pl->ev_start) cudaEventDestroy(pl->ev_start);
+    if (pl->ev_done) cudaEventDestroy(pl->ev_done);
+    for (int i = 0; i < pl->max_chunks; ++i) {
+        if (pl->ev_in && pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
+        if (pl->ev_k && pl->ev_k[i]) cudaEventDestroy(pl->ev_k[i]);
+    }
     delete[] pl->ev_in; delete[] pl->ev_k;
     delete pl;
 }
@@ -273,16 +303,19 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
     int64_t per = (n / chunks) / 256 * 256;
     if (per == 0) { chunks = 1; per = n; }
     cudaStream_t cur = (cudaStream_t)stream;
-    cudaEventRecord(pl->ev_start, cur);
-    cudaStreamWaitEvent(pl->s_in, pl->ev_start, 0);
-    cudaStreamWaitEvent(pl->s_k, pl->ev_start, 0);
-    cudaStreamWaitEvent(pl->s_out, pl->ev_start, 0);
-    for (int c = 0; c < chunks; ++c) {
+    // every asynchronous call is checked; after a failure nothing more is queued, but the caller's stream is still
+    // joined to the internal streams below, so no work of this call is left running behind the caller's back
+    cudaError_t ce = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (ce == cudaSuccess && r != cudaSuccess) ce = r; return ce == cudaSuccess; };
+    ok(cudaEventRecord(pl->ev_start, cur));
+    ok(cudaStreamWaitEvent(pl->s_in, pl->ev_start, 0));
+    ok(cudaStreamWaitEvent(pl->s_k, pl->ev_start, 0));
+    ok(cudaStreamWaitEvent(pl->s_out, pl->ev_start, 0));
+    for (int c = 0; c < chunks && ce == cudaSuccess && rc == MR_OK; ++c) {
         const int64_t lo = c * per, hi = c == chunks - 1 ? n : lo + per, m = hi - lo;
-        cudaMemcpyAsync((char*)io->actions_dev + 2 * lo * el, (const char*)io->actions_host + 2 * lo * el, (size_t)(2 * m * el),
-                        cudaMemcpyHostToDevice, pl->s_in);
-        cudaEventRecord(pl->ev_in[c], pl->s_in);
-        cudaStreamWaitEvent(pl->s_k, pl->ev_in[c], 0);
+        if (!ok(cudaMemcpyAsync((char*)io->actions_dev + 2 * lo * el, (const char*)io->actions_host + 2 * lo * el,
+                                (size_t)(2 * m * el), cudaMemcpyHostToDevice, pl->s_in))) break;
+        if (!ok(cudaEventRecord(pl->ev_in[c], pl->s_in)) || !ok(cudaStreamWaitEvent(pl->s_k, pl->ev_in[c], 0))) break;
         mr_env_state sc = *st;
         sc.x = (char*)st->x + lo * el; sc.y = (char*)st->y + lo * el; sc.fx = (char*)st->fx + lo * el;
         sc.fy = (char*)st->fy + lo * el; sc.h = (char*)st->h + lo * el;
@@ -296,21 +329,24 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
         const mr_noise* nzp = nz;
         if (nz) { nc = *nz; nc.env_base = nz->env_base + (uint64_t)lo; nzp = &nc; }
         rc = mr_env_step(&sc, m, dtype, p, nzp, tt, (const char*)io->actions_dev + 2 * lo * el, &oc, pl->s_k);
-        if (rc) return rc;
-        cudaEventRecord(pl->ev_k[c], pl->s_k);
-        cudaStreamWaitEvent(pl->s_out, pl->ev_k[c], 0);
+        if (rc) break;                                              // joined and reported below
+        if (!ok(cudaEventRecord(pl->ev_k[c], pl->s_k)) || !ok(cudaStreamWaitEvent(pl->s_out, pl->ev_k[c], 0))) break;
         for (int row = 0; row < 5; ++row) {
             if ((row == 2 || row == 3) && !io->copy_goal_rows) continue;     // the goal is the constant (0, 0) (MR_env.py:57)
-            cudaMemcpyAsync((char*)io->obs_host + (row * hstride + lo) * el, (const char*)out_dev->obs + (row * dstride + lo) * el,
-                            (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out);
+            ok(cudaMemcpyAsync((char*)io->obs_host + (row * hstride + lo) * el, (const char*)out_dev->obs + (row * dstride + lo) * el,
+                               (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out));
         }
-        cudaMemcpyAsync((char*)io->rew_host + lo * el, (const char*)out_dev->rew + lo * el, (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out);
-        cudaMemcpyAsync(io->done_host + lo, out_dev->done + lo, (size_t)m, cudaMemcpyDeviceToHost, pl->s_out);
+        ok(cudaMemcpyAsync((char*)io->rew_host + lo * el, (const char*)out_dev->rew + lo * el, (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out));
+        ok(cudaMemcpyAsync(io->done_host + lo, out_dev->done + lo, (size_t)m, cudaMemcpyDeviceToHost, pl->s_out));
     }
-    cudaEventRecord(pl->ev_done, pl->s_k);
-    cudaStreamWaitEvent(cur, pl->ev_done, 0);                  // later work on the caller's stream sees the new state
-    const cudaError_t e = cudaStreamSynchronize(pl->s_out);     // the host buffers are valid when this returns
-    if (e != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_env_step_host: %s", cudaGetErrorString(e));
+    // join: later work on the caller's stream sees the new state; the host buffers are valid when s_out has drained
+    const cudaError_t j0 = cudaEventRecord(pl->ev_done, pl->s_k);
+    const cudaError_t j1 = j0 == cudaSuccess ? cudaStreamWaitEvent(cur, pl->ev_done, 0) : j0;
+    const cudaError_t j2 = cudaStreamSynchronize(pl->s_in);
+    const cudaError_t j3 = cudaStreamSynchronize(pl->s_out);
+    if (rc) return rc;                                              // mr_env_step already set the message
+    for (cudaError_t e : {ce, j1, j2, j3})
+        if (e != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_env_step_host: %s", cudaGetErrorString(e));
     return mr::check_launch("mr_env_step_host");
 }
 

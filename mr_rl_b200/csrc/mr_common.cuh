@@ -12,6 +12,7 @@ namespace mr {
 
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
+extern int g_step_path;   // 0 default, 1 plain TMA, 2 vector, 3 scalar, 4 warp-specialised (mr_set_step_path)
 
 // Per-device launch configuration cache (one process may drive several GPUs): kernel attributes are
 // per device, so "done once" flags are indexed by the current device.
@@ -120,13 +121,14 @@ template <> struct NoiseOf<MR_NOISE_PHILOX> { using type = PhiloxNoise; };
 
 template <int MODE>
 __device__ __forceinline__ typename NoiseOf<MODE>::type make_noise(const NoiseView& nv, int64_t n, int64_t env,
-                                                                   int32_t cursor, uint64_t step) {
+                                                                   int32_t cursor, uint64_t step,
+                                                                   uint32_t purpose = kPurposeNoise) {
     typename NoiseOf<MODE>::type nz;
     if constexpr (MODE == MR_NOISE_TABLE) {
         nz.col = nv.table + env; nz.stride = n; nz.cursor = cursor;
         nz.len = (int32_t)nv.table_len; nz.overflow = 0;
     } else if constexpr (MODE == MR_NOISE_PHILOX) {
-        nz.seek(nv.env_base + (uint64_t)env, step);
+        nz.seek(nv.env_base + (uint64_t)env, step, purpose);
     }
     return nz;
 }
@@ -142,7 +144,7 @@ __device__ __forceinline__ void auto_reset_env(Env& e, const NoiseView& nv, int6
     const double x0 = (double)(float)(p.init_lo[0] + (p.init_hi[0] - p.init_lo[0]) * u[0]);
     const double y0 = (double)(float)(p.init_lo[1] + (p.init_hi[1] - p.init_lo[1]) * u[1]);
     const int keep = e.status;
-    auto nzr = make_noise<MODE>(nv, n, i, cur, step ^ 0x8000000000000000ull);
+    auto nzr = make_noise<MODE>(nv, n, i, cur, step, kPurposeResetNoise);
     env_reset<MISM>(e, x0, y0, p.dt, p, nzr);
     e.status |= keep;
     if constexpr (MODE == MR_NOISE_TABLE) { cur = nzr.cursor; overflow |= nzr.overflow; }

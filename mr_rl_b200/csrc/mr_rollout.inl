@@ -47,8 +47,12 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         e.h = decode_h<T>(st.h[i], (t_in + p.dt) - t_in);
         if constexpr (MODE == MR_NOISE_TABLE) cur = st.cursor[i];
     }
-    Observation o;
-    o.d = sqrt(e.x * e.x + e.y * e.y); o.rew = 0.0; o.done = false; o.why = 0;
+    Observation o = observe(e, p);
+    // an env that is stepped past its terminal step (run_sim does, utils.py:46-54; the reference never resets by
+    // itself) stays `done` on every later step: only the transition counts as an episode end in the statistics.
+    // A freshly reset env (counter 0) has not ended anything yet, wherever it starts.
+    bool was_done = o.done && e.counter > 0;
+    o.rew = 0.0; o.done = false; o.why = 0;
     bool overflow = false;
 
     for (int k = 0; k < io.k_steps; ++k) {
@@ -95,7 +99,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             acc[MR_STAT_SUM_REWARD] += o.rew;
         }
         if (o.done) {
-            if (live) {
+            if (live && !was_done) {
                 acc[MR_STAT_EPISODES] += 1.0;
                 acc[MR_STAT_SUM_LENGTH] += (double)e.counter;
                 if (o.why == 1) acc[MR_STAT_GOAL] += 1.0;
@@ -106,8 +110,10 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
                 int ov = 0;
                 auto_reset_env<MODE, MISM>(e, nv, n, live ? i : 0, cur, nv.offset + (uint64_t)k, p, ov);
                 overflow |= ov != 0;
+                o.d = sqrt(e.x * e.x + e.y * e.y);   // the policy's next input is the new episode's first observation (env.reset())
             }
         }
+        was_done = o.done && !p.auto_reset;
     }
     if constexpr (SRC == kSrcActorTc) actor_tc_teardown(*reinterpret_cast<ActorTcSmem*>(s_dyn));
 

@@ -4,6 +4,7 @@
 
 #include "mr_common.cuh"
 #include "mr_step_tma.cuh"
+#include "mr_step_ws.cuh"
 
 namespace mr {
 
@@ -123,7 +124,7 @@ env_reset_kernel(StateView<T> st, const T* __restrict__ init_xy, const uint8_t* 
     }
     int32_t cur = 0;
     if constexpr (MODE == MR_NOISE_TABLE) cur = reset_cursor ? 0 : st.cursor[i];
-    auto nz = make_noise<MODE>(nv, n, i, cur, nv.offset ^ 0x8000000000000000ull);
+    auto nz = make_noise<MODE>(nv, n, i, cur, nv.offset, kPurposeResetNoise);
     Env e;
     e.spx = e.spy = 0.0;
     if (p.mism_reset) env_reset<true>(e, x0, y0, p.dt, p, nz);
@@ -179,14 +180,32 @@ static int sm_count(int dev) {
     return cached[dev];
 }
 
-// MR_STEP_PATH=tma|vec|scalar overrides the kernel choice (tuning / A-B measurements)
-static int step_path_override() {
-    static const int v = [] {
-        const char* e = getenv("MR_STEP_PATH");
-        if (!e) return 0;
-        return e[0] == 't' ? 1 : e[0] == 'v' ? 2 : e[0] == 's' ? 3 : 0;
-    }();
-    return v;
+// kernel choice override (tuning / A-B measurements / tests): mr_set_step_path(), initialised from the environment
+// variable MR_STEP_PATH=tma|ws|vec|scalar ("tma" = the plain TMA kernel also where the warp-specialised one would be
+// picked, "ws" = the default choice)
+static int step_path_override() { return g_step_path; }
+
+template <class T, class K>
+static void launch_persistent(K kernel, int threads, size_t smem, int* ctas_per_sm, int64_t n_tiles, cudaStream_t s,
+                              const StateView<T>& sv, const T* act, const OutView<T>& ov, const NoiseView& nv,
+                              const TimeView& tv, const Params& p, int64_t n) {
+    const int dev = current_device();
+    if (!ctas_per_sm[dev]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        ctas_per_sm[dev] = occ > 0 ? occ : 1;
+    }
+    // persistent grid: exactly the CTAs that are co-resident, so there is never a second wave
+    const int64_t max_ctas = (int64_t)sm_count(dev) * ctas_per_sm[dev];
+    const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, sv, act, ov, nv, tv, p, n_tiles, n);
 }
 
 template <class T, int MODE, bool MISM>
@@ -198,30 +217,21 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
     // table-noise columns are addressed by (env, n), so that mode keeps one scalar launch
     if constexpr (MODE != MR_NOISE_TABLE) {
         constexpr int kTile = TileOf<T>::value;
-        if (vec_ok && n >= kTile && (force == 0 || force == 1)) {
+        if (vec_ok && n >= kTile && (force == 0 || force == 1 || force == 4)) {
             // Blackwell path: persistent CTAs, TMA bulk copies through shared memory
             const int64_t n_tiles = n / kTile;
-            const size_t smem = sizeof(StepSmem<T>);
             static int ctas_per_sm[kMaxDevices] = {};      // per template instantiation and device
-            const int dev = current_device();
-            if (!ctas_per_sm[dev]) {
-                cudaFuncSetAttribute(env_step_tma_kernel<T, MODE, MISM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                int occ = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_step_tma_kernel<T, MODE, MISM>, kTile, smem);
-                ctas_per_sm[dev] = occ > 0 ? occ : 1;
+            bool ws = false;
+            if constexpr (MODE == MR_NOISE_PHILOX && !MISM) ws = force != 1;
+            if constexpr (MODE == MR_NOISE_PHILOX && !MISM) {
+                static int ctas_ws[kMaxDevices] = {};
+                if (ws) launch_persistent<T>(env_step_tma_ws_kernel<T>, WsCfg<T>::kThreads, sizeof(StepSmemWs<T>), ctas_ws,
+                                             n_tiles, s, sv, act, ov, nv, tv, p, n);
             }
-            // persistent grid: exactly the CTAs that are co-resident, so there is never a second wave
-            const int64_t max_ctas = (int64_t)sm_count(dev) * ctas_per_sm[dev];
-            const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTile); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous tail
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, env_step_tma_kernel<T, MODE, MISM>, sv, act, ov, nv, tv, p, n_tiles, n);
+            if (!ws) launch_persistent<T>(env_step_tma_kernel<T, MODE, MISM>, kTile, sizeof(StepSmem<T>), ctas_per_sm, n_tiles,
+                                          s, sv, act, ov, nv, tv, p, n);
             done = n_tiles * kTile;
-        } else if (vec_ok && n >= VEC && force != 3 && force != 1) {
+        } else if (vec_ok && n >= VEC && force != 3 && force != 1 && force != 4) {
             const int64_t n_vec = (n / VEC) * VEC;
             launch_step_range<T, VEC, MODE, MISM>(sv, act, ov, nv, tv, p, n_vec, s);
             done = n_vec;

@@ -155,9 +155,7 @@ class MR_Env:
 
     def set_init_space(self, low, high):
         self.init_space = Box(low=np.array(low), high=np.array(high))
-        self._vec.init_space = self.init_space
-        self._vec.params.init_low[0], self._vec.params.init_low[1] = float(low[0]), float(low[1])
-        self._vec.params.init_high[0], self._vec.params.init_high[1] = float(high[0]), float(high[1])
+        self._vec.init_space = self.init_space                 # property: writes through to the launch parameters
 
     def set_goal(self, init):
         return self.init_goal                                  # MR_env.py:157-162 (no-op)

@@ -61,7 +61,11 @@ class VecMREnv:
         dev = self.device
 
         # --- spaces and constants, MR_env.py:34-63 -------------------------------------------
+        # (max_timesteps, min_dist2goal, init_space, action_space, observation_space are properties further down: the
+        #  kernels read them from self.params, so assigning them — as users of the reference do — writes through)
+        self.params = L.default_params()
         self.action_space = Box(low=np.array([0, 0]), high=np.array([20, np.pi * 2]))
+        self.params.action_high[1] = 2 * math.pi     # the default keeps the float64 bound (a Box stores float32)
         self.observation_space = Box(low=np.array([-5000, -5000, -5000, -5000, 0]),
                                      high=np.array([5000, 5000, 5000, 5000, 80000]))
         self.init_space = Box(low=np.array([100, 100]), high=np.array([120, 120]))
@@ -70,7 +74,6 @@ class VecMREnv:
         self.init_goal = np.zeros(2)
 
         # --- Simulator parameters, MR_simulator.py:12-19 --------------------------------------
-        self.params = L.default_params()
         self.params.a0 = 0.0
         self.params.noise_var = 0.0
         self.params.auto_reset = 1 if auto_reset else 0
@@ -120,6 +123,58 @@ class VecMREnv:
         self._views = (self._obs[:, :n].t(), self._rew[:n], self._done[:n], {})
 
     # ---- properties mirroring the reference attributes ------------------------------------
+    # MR_env.py:34-63 — plain attributes in the reference; here every assignment also updates the launch parameters
+    @property
+    def max_timesteps(self):
+        return self.params.max_timesteps
+
+    @max_timesteps.setter
+    def max_timesteps(self, v):
+        self.params.max_timesteps = int(v)
+
+    @property
+    def min_dist2goal(self):
+        return self.params.min_dist2goal
+
+    @min_dist2goal.setter
+    def min_dist2goal(self, v):
+        self.params.min_dist2goal = float(v)
+
+    @property
+    def init_space(self):
+        return self._init_space
+
+    @init_space.setter
+    def init_space(self, box):
+        self._init_space = box
+        for i in range(2):
+            self.params.init_low[i] = float(box.low[i])
+            self.params.init_high[i] = float(box.high[i])
+
+    @property
+    def action_space(self):
+        return self._action_space
+
+    @action_space.setter
+    def action_space(self, box):
+        self._action_space = box
+        for i in range(2):
+            self.params.action_high[i] = float(box.high[i])      # in-kernel random / actor policies scale by the upper bound
+
+    @property
+    def observation_space(self):
+        return self._observation_space
+
+    @observation_space.setter
+    def observation_space(self, box):
+        # the kernels test |x|, |y| <= bound_xy and 0 <= d <= bound_d (MR_env.py:37-39 is symmetric in x, y)
+        lo, hi = np.asarray(box.low, dtype=np.float64), np.asarray(box.high, dtype=np.float64)
+        if not (lo[0] == -hi[0] and lo[1] == -hi[1] and hi[0] == hi[1] and lo[4] == 0):
+            raise ValueError("observation_space must be [-b, b] in x and y and [0, bd] in the distance")
+        self._observation_space = box
+        self.params.bound_xy = float(hi[0])
+        self.params.bound_d = float(hi[4])
+
     @property
     def a0(self):
         return self.params.a0
@@ -454,7 +509,12 @@ class VecMREnv:
         return {
             "state": self._state.clone(), "counter": self._counter.clone(), "cursor": self._cursor.clone(),
             "status": self._status.clone(), "stats": self._stats.clone(), "step_index": self._step_index,
-            "params": {"a0": p.a0, "noise_var": p.noise_var, "is_mismatched": int(p.is_mismatched)},
+            "params": {"a0": p.a0, "noise_var": p.noise_var, "is_mismatched": int(p.is_mismatched),
+                       "max_timesteps": int(p.max_timesteps), "min_dist2goal": float(p.min_dist2goal),
+                       "bound_xy": float(p.bound_xy), "bound_d": float(p.bound_d),
+                       "init_low": [p.init_low[0], p.init_low[1]], "init_high": [p.init_high[0], p.init_high[1]],
+                       "action_high": [p.action_high[0], p.action_high[1]],
+                       "auto_reset": int(p.auto_reset), "reward_mode": int(p.reward_mode)},
             "seed": int(self._c_noise.seed), "env_base": int(self._c_noise.env_base),
         }
 
@@ -464,6 +524,14 @@ class VecMREnv:
         self._step_index = int(sd["step_index"])
         self.params.a0 = sd["params"]["a0"]; self.params.noise_var = sd["params"]["noise_var"]
         self.params.is_mismatched = self.params.mism_at_reset = sd["params"]["is_mismatched"]
+        q = sd["params"]
+        if "max_timesteps" in q:                      # older checkpoints carry only the three simulator parameters
+            self.max_timesteps, self.min_dist2goal = q["max_timesteps"], q["min_dist2goal"]
+            self.init_space = Box(low=np.array(q["init_low"]), high=np.array(q["init_high"]))
+            self.action_space = Box(low=np.array([0, 0]), high=np.array(q["action_high"]))
+            b, bd = q["bound_xy"], q["bound_d"]
+            self.observation_space = Box(low=np.array([-b, -b, -b, -b, 0]), high=np.array([b, b, b, b, bd]))
+            self.params.auto_reset, self.params.reward_mode = int(q["auto_reset"]), int(q["reward_mode"])
         self._c_noise.seed = sd["seed"]; self._c_noise.env_base = sd["env_base"]
 
     # ---- no-op hooks kept for drop-in compatibility (MR_env.py:203-229) --------------------------------

@@ -81,7 +81,10 @@ def test_fused_rollout_matches_live_reference(golden_single, name):
     assert int(env.counter[0]) == T
     assert rel_err(res["obs"].cpu().numpy()[0], g["obs"][-1]) < FP64_TOL
     st = env.stats_dict()
-    assert st["env_steps"] == T and st["episodes"] == int(g["done"].sum())
+    # an env stepped past its terminal step stays `done` (run_sim ignores it): only the transition ends an episode
+    d = np.asarray(g["done"]).astype(bool)
+    ends = int(d[0]) + int((d[1:] & ~d[:-1]).sum())
+    assert st["env_steps"] == T and st["episodes"] == ends
 
 
 @pytest.mark.parametrize("tag", ["sigma0", "sigma1", "mismatch"])
@@ -602,3 +605,59 @@ def test_solver_failures_are_flagged_for_the_same_envs_as_the_oracle():
     assert flagged == ref["bad"]
     with pytest.raises(Exception):
         env.check_status()
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_step_kernel_variants_are_bit_identical(dt):
+    """The generated-noise step has four kernels (scalar, 16-byte vector, TMA, warp-specialised TMA whose service warp
+    draws the normals one tile ahead).  Same counters, same blocks, same arithmetic: the results must be EQUAL, through
+    auto resets, for every env of a ragged batch (tiles + vector part + scalar tail)."""
+    from mr_rl_b200 import _lib as L
+    n, T = 128 * 37 + 19, 60
+    acts = torch.rand(T, n, 2, dtype=torch.float64, device="cuda:0")
+    acts[..., 0] *= 20; acts[..., 1] *= 2 * np.pi
+    acts = acts.to(dt)
+    ref = None
+    try:
+        for path in ("scalar", "vec", "tma", "ws"):
+            L.set_step_path(path)
+            env = make_env(n, dtype=dt, noise="philox", seed=31, env_base=5, auto_reset=True)
+            env.reset(init=None, noise_var=1.0, a0=1.0)
+            trace = []
+            for k in range(T):
+                obs, rew, done, _ = env.step(acts[k])
+                trace.append((obs.clone(), done.clone(), env.state_prime.clone(), env.counter.clone()))
+            env.check_status()
+            got = [torch.stack([t[i].double() for t in trace]).cpu().numpy() for i in range(4)]
+            assert got[1].sum() > 0                                  # episodes did end and restart inside the trace
+            if ref is None:
+                ref = got
+            else:
+                for a, b in zip(ref, got):
+                    assert np.array_equal(a, b), path
+    finally:
+        L.set_step_path("default")
+
+
+def test_reset_draws_differ_from_the_terminal_steps_draws():
+    """An auto reset happens in the same (env, env-step) as the terminal step: the integrator the reset builds must not
+    re-use that step's Philox blocks (MR_env.py:181 draws fresh noise).  With a0 = 0 the new episode's carried
+    derivative f0 and state_prime f1 are pure noise draws, and so are the terminal step's; compare them."""
+    n = 4096
+    env = make_env(n, noise="philox", seed=4, auto_reset=True)
+    env.max_timesteps = 0                                            # every step is terminal
+    env.reset(init=None, noise_var=1.0, a0=0.0)
+    env.params.auto_reset = 0
+    a = torch.zeros(n, 2, dtype=torch.float64, device="cuda:0")
+    env.step(a)
+    plain = env._state[2:4, :n].clone(), env.state_prime.clone()     # f0, f1 of the step's own rebuilt integrator
+    env2 = make_env(n, noise="philox", seed=4, auto_reset=True)
+    env2.max_timesteps = 0
+    env2.reset(init=None, noise_var=1.0, a0=0.0)
+    env2.step(a)                                                     # same draws for the step, then the auto reset
+    after = env2._state[2:4, :n], env2.state_prime
+    assert int(env2.counter.max()) == 0                              # the reset happened
+    z_step = torch.cat([plain[0].flatten(), plain[1].flatten()]).cpu().numpy()
+    z_reset = torch.cat([after[0].flatten(), after[1].flatten()]).cpu().numpy()
+    assert not np.isin(z_reset, z_step).any()                        # no value of the reset appears among the step's
+    assert abs(np.corrcoef(z_step, z_reset)[0, 1]) < 0.05
