@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MR_ABI_VERSION 1
+#define MR_ABI_VERSION 2   /* 2: per-env parameter rows, noise offset_dev, float32 I/O rows, episode recording */
 
 enum mr_status {
     MR_OK = 0,
@@ -96,8 +96,9 @@ typedef struct mr_sim_params {
     double min_dist2goal;   /* 30 */
     double bound_xy;        /* 5000  (observation_space, MR_env.py:37-39) */
     double bound_d;         /* 80000 */
-    int32_t auto_reset;     /* rollout only: re-initialise an env after done */
-    int32_t reserved;
+    int32_t auto_reset;     /* re-initialise an env from init_space right after a terminal step (gym vector-env style) */
+    int32_t action_f32;     /* != 0: the `actions` buffer of mr_env_step is float32 [n][2] although dtype is MR_F64
+                               (halves the host->device bytes of a host-buffer step; the values are widened exactly) */
     double init_low[2];     /* init_space, MR_env.py:40-42 */
     double init_high[2];
     double action_high[2];  /* action_space.high, MR_env.py:34-36 */
@@ -113,7 +114,22 @@ typedef struct mr_env_state {
     int32_t* counter;   /* MR_Env.counter == env steps since reset (t = t_table[counter]) */
     int32_t* cursor;    /* table-noise draws consumed so far (MR_NOISE_TABLE only; else may be NULL) */
     uint8_t* status;    /* sticky mr_env_flag bits */
+    /* Optional per-env simulator parameters (MR_simulator.py:16-19 are per-instance attributes, set per reset at
+     * MR_env.py:179-183).  All three NULL: every env uses the launch scalars of mr_sim_params.  All three given: the rows
+     * are the truth for step / rollout; mr_env_reset WRITES them for the envs it resets (from its per-env new-value
+     * arrays, else from the launch scalars), building the integrator with the new a0 / noise_var and the OLD flag. */
+    double* a0;             /* [n] Simulator.a0 */
+    double* noise_var;      /* [n] Simulator.noise_var */
+    uint8_t* is_mismatched; /* [n] Simulator.is_mismatched */
 } mr_env_state;
+
+/* Per-env arguments of MR_Env.reset(noise_var, a0, is_mismatched) for mr_env_reset; any member may be NULL (= the launch
+ * scalar).  Only meaningful when the state carries the per-env parameter rows. */
+typedef struct mr_reset_params {
+    const double* a0;             /* [n] */
+    const double* noise_var;      /* [n] */
+    const uint8_t* is_mismatched; /* [n] */
+} mr_reset_params;
 
 typedef struct mr_noise {
     int32_t mode;          /* mr_noise_mode */
@@ -123,7 +139,13 @@ typedef struct mr_noise {
     uint64_t seed;         /* Philox key */
     uint64_t offset;       /* Philox: global env-step index of this launch (caller increments) */
     uint64_t env_base;     /* global index of local env 0 (multi-GPU sharding) */
+    const uint64_t* offset_dev; /* optional DEVICE counter added to `offset` when the kernel runs: launches captured in
+                                   a CUDA graph keep drawing fresh noise on every replay (set it with mr_counter_set
+                                   before a replay); NULL = none */
 } mr_noise;
+
+/* *counter = value, stream-ordered (one tiny kernel): the base env-step index of the next graph replay. */
+int mr_counter_set(uint64_t* counter_dev, uint64_t value, void* stream);
 
 /* t_k after k env steps since reset, t_k = fl(t_{k-1} + time_span) (MR_simulator.py:46-50). */
 typedef struct mr_time_table {
@@ -140,7 +162,9 @@ typedef struct mr_step_out {
     int64_t row_stride; /* elements between rows of obs / state_prime (0 = n) */
     int32_t skip_goal_rows; /* != 0: leave obs rows 2, 3 (the constant goal (0, 0), MR_env.py:57) untouched — the caller
                              * zeroed them once; saves 2 of the 5 obs rows when obs points at host memory */
-    int32_t reserved;
+    int32_t out_f32;        /* != 0: obs / rew / state_prime rows are float32 although dtype is MR_F64 (row_stride then
+                             * counts floats): the 1e-4 tier of the outputs at half the device->host bytes, while the state
+                             * and every decision stay fp64 */
 } mr_step_out;
 
 int mr_abi_version(void);
@@ -164,6 +188,10 @@ void mr_fill_time_table_host(double* t_host, int32_t len, double time_span);
 int mr_env_reset(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
                  const mr_noise* nz, const void* init_xy, const uint8_t* mask, int32_t reset_cursor,
                  const mr_step_out* out, void* stream);
+/* The same with per-env reset arguments (rp may be NULL = mr_env_reset). */
+int mr_env_reset_ex(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
+                    const mr_noise* nz, const void* init_xy, const uint8_t* mask, int32_t reset_cursor,
+                    const mr_reset_params* rp, const mr_step_out* out, void* stream);
 
 /* MR_Env.step for n envs.  actions is [n][2] (f_t, alpha_t), storage dtype. */
 /* (device buffers; the host-buffer form is mr_env_step_host below) */
@@ -281,10 +309,13 @@ typedef struct mr_host_step_io {
     void* actions_dev;         /* device staging [n][2]                                                       */
     void* obs_host;            /* HOST  [5][host_row_stride]; rows 2, 3 (the constant goal) are copied only if  */
     void* rew_host;            /* HOST  [n]                                     copy_goal_rows != 0           */
+                               /*       (direct mode: may be NULL — with the constant reward of MR_env.py:89  */
+                               /*        there is nothing to send)                                            */
     uint8_t* done_host;        /* HOST  [n]                                                                   */
     int64_t host_row_stride;   /* elements between obs_host rows (0 = n)                                      */
     int32_t copy_goal_rows;
-    int32_t reserved;
+    int32_t io_f32;            /* direct mode, MR_F64 storage: actions_host / obs_host / rew_host are float32 */
+                               /* (the 1e-4 tier on the wire; the state and all decisions stay fp64)          */
 } mr_host_step_io;
 
 /* out_dev: the device rows the kernel writes (obs, rew, done required).  `stream`: the caller's stream; the pipeline

@@ -11,6 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MR_LIB_PATH") or os.path.join(HERE, "_lib", "libmr_rl_b200.so")   # MR_LIB_PATH: tuning variants
 
+ABI_VERSION = 2
 MR_F64, MR_F32 = 0, 1
 NOISE_NONE, NOISE_TABLE, NOISE_PHILOX = 0, 1, 2
 ACTIONS_TENSOR, ACTIONS_PHILOX, ACTIONS_ACTOR, ACTIONS_BROADCAST = 0, 1, 2, 3
@@ -27,19 +28,24 @@ class SimParams(C.Structure):
         ("time_span", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
         ("max_timesteps", C.c_int32), ("reward_mode", C.c_int32),
         ("min_dist2goal", C.c_double), ("bound_xy", C.c_double), ("bound_d", C.c_double),
-        ("auto_reset", C.c_int32), ("reserved", C.c_int32),
+        ("auto_reset", C.c_int32), ("action_f32", C.c_int32),
         ("init_low", C.c_double * 2), ("init_high", C.c_double * 2), ("action_high", C.c_double * 2),
     ]
 
 
 class EnvState(C.Structure):
     _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("fx", C.c_void_p), ("fy", C.c_void_p), ("h", C.c_void_p),
-                ("counter", C.c_void_p), ("cursor", C.c_void_p), ("status", C.c_void_p)]
+                ("counter", C.c_void_p), ("cursor", C.c_void_p), ("status", C.c_void_p),
+                ("a0", C.c_void_p), ("noise_var", C.c_void_p), ("is_mismatched", C.c_void_p)]
+
+
+class ResetParams(C.Structure):
+    _fields_ = [("a0", C.c_void_p), ("noise_var", C.c_void_p), ("is_mismatched", C.c_void_p)]
 
 
 class Noise(C.Structure):
     _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("table", C.c_void_p), ("table_len", C.c_int64),
-                ("seed", C.c_uint64), ("offset", C.c_uint64), ("env_base", C.c_uint64)]
+                ("seed", C.c_uint64), ("offset", C.c_uint64), ("env_base", C.c_uint64), ("offset_dev", C.c_void_p)]
 
 
 class TimeTable(C.Structure):
@@ -48,7 +54,7 @@ class TimeTable(C.Structure):
 
 class StepOut(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p), ("state_prime", C.c_void_p),
-                ("row_stride", C.c_int64), ("skip_goal_rows", C.c_int32), ("reserved", C.c_int32)]
+                ("row_stride", C.c_int64), ("skip_goal_rows", C.c_int32), ("out_f32", C.c_int32)]
 
 
 class RolloutIO(C.Structure):
@@ -65,7 +71,7 @@ class GPModel(C.Structure):
 
 class HostStepIO(C.Structure):
     _fields_ = [("actions_host", C.c_void_p), ("actions_dev", C.c_void_p), ("obs_host", C.c_void_p), ("rew_host", C.c_void_p),
-                ("done_host", C.c_void_p), ("host_row_stride", C.c_int64), ("copy_goal_rows", C.c_int32), ("reserved", C.c_int32)]
+                ("done_host", C.c_void_p), ("host_row_stride", C.c_int64), ("copy_goal_rows", C.c_int32), ("io_f32", C.c_int32)]
 
 
 class DDPGState(C.Structure):
@@ -90,7 +96,7 @@ EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time
            "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_gp_fit", "mr_gp_fit_workspace_bytes", "mr_actor_param_count",
            "mr_critic_param_count", "mr_replay_add", "mr_ou_noise_add", "mr_ddpg_update", "mr_learn_preprocess",
            "mr_learn_workspace_bytes", "mr_ddpg_workspace_bytes", "mr_replay_sample", "mr_actor_forward_env", "mr_ddpg_gradients", "mr_ddpg_apply", "mr_gp_correct_heading_cheb", "mr_host_pipeline_create", "mr_host_pipeline_destroy", "mr_env_step_host",
-           "mr_actor_forward", "mr_set_step_path")
+           "mr_actor_forward", "mr_set_step_path", "mr_env_reset_ex", "mr_counter_set")
 
 _lib = None
 
@@ -118,6 +124,11 @@ def load():
     lib.mr_fill_time_table_host.restype = None
     lib.mr_env_reset.argtypes = [P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), C.c_void_p, C.c_void_p,
                                  C.c_int32, P(StepOut), C.c_void_p]
+    lib.mr_env_reset_ex.argtypes = [P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), C.c_void_p, C.c_void_p,
+                                    C.c_int32, P(ResetParams), P(StepOut), C.c_void_p]
+    lib.mr_env_reset_ex.restype = C.c_int
+    lib.mr_counter_set.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.mr_counter_set.restype = C.c_int
     lib.mr_env_step.argtypes = [P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), P(TimeTable), C.c_void_p,
                                 P(StepOut), C.c_void_p]
     lib.mr_env_rollout.argtypes = [P(EnvState), C.c_int64, C.c_int32, P(SimParams), P(Noise), P(TimeTable),
@@ -180,8 +191,8 @@ def load():
                                      C.c_void_p]
     for f in ("mr_env_reset", "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_actor_forward"):
         getattr(lib, f).restype = C.c_int
-    if lib.mr_abi_version() != 1:
-        raise MRLibraryError(f"ABI version mismatch: library {lib.mr_abi_version()}, binding 1")
+    if lib.mr_abi_version() != ABI_VERSION:
+        raise MRLibraryError(f"ABI version mismatch: library {lib.mr_abi_version()}, binding {ABI_VERSION}")
     _lib = lib
     return lib
 

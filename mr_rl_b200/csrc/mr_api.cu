@@ -42,6 +42,7 @@ static Params to_params(const mr_sim_params& s, const mr_noise* nz) {
     for (int i = 0; i < 2; ++i) { p.init_lo[i] = s.init_low[i]; p.init_hi[i] = s.init_high[i]; p.act_hi[i] = s.action_high[i]; }
     p.mism = s.is_mismatched; p.mism_reset = s.mism_at_reset; p.max_steps = s.max_timesteps;
     p.reward_mode = s.reward_mode; p.auto_reset = s.auto_reset;
+    p.act_f32 = s.action_f32;
     finalize_params(p);
     return p;
 }
@@ -51,23 +52,30 @@ static StateView<T> state_view(const mr_env_state& s) {
     StateView<T> v;
     v.x = (T*)s.x; v.y = (T*)s.y; v.fx = (T*)s.fx; v.fy = (T*)s.fy; v.h = (T*)s.h;
     v.counter = s.counter; v.cursor = s.cursor; v.status = s.status;
+    v.a0 = s.a0; v.sigma = s.noise_var; v.mism = s.is_mismatched;
     return v;
 }
 
 template <class T>
 static OutView<T> out_view(const mr_step_out* o, int64_t n) {
     OutView<T> v;
+    v.f32 = false;
     if (!o) { v.obs = nullptr; v.rew = nullptr; v.done = nullptr; v.sp = nullptr; v.stride = n; v.goal = true; return v; }
     v.obs = (T*)o->obs; v.rew = (T*)o->rew; v.done = o->done; v.sp = (T*)o->state_prime;
     v.goal = o->skip_goal_rows == 0;
+    v.f32 = sizeof(T) == 8 && o->out_f32 != 0;
     v.stride = o->row_stride ? o->row_stride : n;
     return v;
 }
 
-static NoiseView noise_view(const mr_noise* nz) {
+static NoiseView noise_view(const mr_noise* nz, int64_t n) {
     NoiseView v;
     memset(&v, 0, sizeof(v));
-    if (nz) { v.table = nz->table; v.table_len = nz->table_len; v.seed = nz->seed; v.offset = nz->offset; v.env_base = nz->env_base; }
+    if (nz) {
+        v.table = nz->table; v.table_len = nz->table_len; v.seed = nz->seed; v.offset = nz->offset; v.env_base = nz->env_base;
+        v.offset_dev = nz->offset_dev;
+    }
+    v.table_stride = n;        // the table is [table_len][n] for the n envs of this call
     return v;
 }
 
@@ -80,7 +88,8 @@ static bool rows_aligned(const mr_env_state& s, const mr_step_out* o, const void
               aligned16(s.counter) && aligned16(actions);
     if (o) {
         const int64_t stride = o->row_stride ? o->row_stride : n;
-        const bool stride_ok = (stride * (int64_t)sizeof(T)) % 16 == 0;
+        const int64_t el_out = o->out_f32 ? 4 : (int64_t)sizeof(T);
+        const bool stride_ok = (stride * el_out) % 16 == 0;
         if (o->obs) ok = ok && aligned16(o->obs) && stride_ok;
         if (o->state_prime) ok = ok && aligned16(o->state_prime) && stride_ok;
         if (o->rew) ok = ok && aligned16(o->rew);
@@ -102,8 +111,10 @@ static int check_common(const char* fn, const mr_env_state* st, int64_t n, int d
         if (!nz->table || nz->table_len <= 0) return fail(MR_ERR_ARG, "%s: table noise without a table", fn);
         if (!st->cursor) return fail(MR_ERR_ARG, "%s: table noise needs state.cursor", fn);
     }
-    if (mode == MR_NOISE_NONE && p->noise_var != 0.0)
+    if (mode == MR_NOISE_NONE && p->noise_var != 0.0 && !st->noise_var)
         return fail(MR_ERR_ARG, "%s: noise_var=%g needs a noise source (table or philox)", fn, p->noise_var);
+    const int rows = (st->a0 != nullptr) + (st->noise_var != nullptr) + (st->is_mismatched != nullptr);
+    if (rows != 0 && rows != 3) return fail(MR_ERR_ARG, "%s: give all three per-env parameter rows (a0, noise_var, is_mismatched) or none", fn);
     if (!(p->time_span > 0.0)) return fail(MR_ERR_ARG, "%s: time_span must be positive", fn);
     return MR_OK;
 }
@@ -113,8 +124,10 @@ static int do_step(const mr_env_state& st, int64_t n, const Params& p, const mr_
                    const void* actions, const mr_step_out* out, cudaStream_t s) {
     const StateView<T> sv = state_view<T>(st);
     const OutView<T> ov = out_view<T>(out, n);
-    const NoiseView nv = noise_view(nz);
-    const bool vec_ok = rows_aligned<T>(st, out, actions, n);
+    const NoiseView nv = noise_view(nz, n);
+    bool vec_ok = rows_aligned<T>(st, out, actions, n);
+    if (nz && nz->mode == MR_NOISE_TABLE)      // bulk copies of table rows: every row of the tile must be 16-byte aligned
+        vec_ok = vec_ok && aligned16(nz->table) && n % 2 == 0 && aligned16(st.cursor);
     switch (nz ? nz->mode : MR_NOISE_NONE) {
         case MR_NOISE_TABLE: return launch_step<T, MR_NOISE_TABLE>(sv, (const T*)actions, ov, nv, tv, p, n, vec_ok, s);
         case MR_NOISE_PHILOX: return launch_step<T, MR_NOISE_PHILOX>(sv, (const T*)actions, ov, nv, tv, p, n, vec_ok, s);
@@ -124,16 +137,20 @@ static int do_step(const mr_env_state& st, int64_t n, const Params& p, const mr_
 
 template <class T>
 static int do_reset(const mr_env_state& st, int64_t n, const Params& p, const mr_noise* nz, const void* init_xy,
-                    const uint8_t* mask, int reset_cursor, const mr_step_out* out, cudaStream_t s) {
+                    const uint8_t* mask, int reset_cursor, const mr_reset_params* rp, const mr_step_out* out, cudaStream_t s) {
     const StateView<T> sv = state_view<T>(st);
     const OutView<T> ov = out_view<T>(out, n);
-    const NoiseView nv = noise_view(nz);
+    const NoiseView nv = noise_view(nz, n);
+    ResetRows rr{nullptr, nullptr, nullptr};
+    if (rp) { rr.a0 = rp->a0; rr.sigma = rp->noise_var; rr.mism = rp->is_mismatched; }
     switch (nz ? nz->mode : MR_NOISE_NONE) {
-        case MR_NOISE_TABLE: return launch_reset<T, MR_NOISE_TABLE>(sv, (const T*)init_xy, mask, reset_cursor, ov, nv, p, n, s);
-        case MR_NOISE_PHILOX: return launch_reset<T, MR_NOISE_PHILOX>(sv, (const T*)init_xy, mask, reset_cursor, ov, nv, p, n, s);
-        default: return launch_reset<T, MR_NOISE_NONE>(sv, (const T*)init_xy, mask, reset_cursor, ov, nv, p, n, s);
+        case MR_NOISE_TABLE: return launch_reset<T, MR_NOISE_TABLE>(sv, (const T*)init_xy, mask, reset_cursor, rr, ov, nv, p, n, s);
+        case MR_NOISE_PHILOX: return launch_reset<T, MR_NOISE_PHILOX>(sv, (const T*)init_xy, mask, reset_cursor, rr, ov, nv, p, n, s);
+        default: return launch_reset<T, MR_NOISE_NONE>(sv, (const T*)init_xy, mask, reset_cursor, rr, ov, nv, p, n, s);
     }
 }
+
+__global__ void counter_set_kernel(uint64_t* c, uint64_t v) { *c = v; }
 
 template <class T>
 static int do_rollout(const mr_env_state& st, int64_t n, const Params& p, const mr_noise* nz, const TimeView& tv,
@@ -144,7 +161,7 @@ static int do_rollout(const mr_env_state& st, int64_t n, const Params& p, const 
     rv.k_steps = io.k_steps; rv.action_source = io.action_source;
     const StateView<T> sv = state_view<T>(st);
     const OutView<T> ov = out_view<T>(out, n);
-    const NoiseView nv = noise_view(nz);
+    const NoiseView nv = noise_view(nz, n);
     switch (nz ? nz->mode : MR_NOISE_NONE) {
         case MR_NOISE_TABLE: return launch_rollout<T, MR_NOISE_TABLE>(sv, rv, ov, nv, tv, p, n, s);
         case MR_NOISE_PHILOX: return launch_rollout<T, MR_NOISE_PHILOX>(sv, rv, ov, nv, tv, p, n, s);
@@ -183,15 +200,30 @@ void mr_fill_time_table_host(double* t, int32_t len, double time_span) {
     for (int32_t k = 1; k < len; ++k) t[k] = t[k - 1] + time_span;
 }
 
-int mr_env_reset(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
-                 const void* init_xy, const uint8_t* mask, int32_t reset_cursor, const mr_step_out* out, void* stream) {
+int mr_env_reset_ex(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
+                    const void* init_xy, const uint8_t* mask, int32_t reset_cursor, const mr_reset_params* rp,
+                    const mr_step_out* out, void* stream) {
     int rc = mr::check_common("mr_env_reset", st, n, dtype, p, nz);
     if (rc) return rc;
+    if (rp && (rp->a0 || rp->noise_var || rp->is_mismatched) && !st->a0)
+        return mr::fail(MR_ERR_ARG, "mr_env_reset: per-env reset arguments need the per-env parameter rows in the state");
+    if (out && out->out_f32) return mr::fail(MR_ERR_UNSUPPORTED, "mr_env_reset: float32 output rows are a step option");
     if (n == 0) return MR_OK;
     const mr::Params pp = mr::to_params(*p, nz);
     cudaStream_t s = (cudaStream_t)stream;
-    return dtype == MR_F64 ? mr::do_reset<double>(*st, n, pp, nz, init_xy, mask, reset_cursor, out, s)
-                           : mr::do_reset<float>(*st, n, pp, nz, init_xy, mask, reset_cursor, out, s);
+    return dtype == MR_F64 ? mr::do_reset<double>(*st, n, pp, nz, init_xy, mask, reset_cursor, rp, out, s)
+                           : mr::do_reset<float>(*st, n, pp, nz, init_xy, mask, reset_cursor, rp, out, s);
+}
+
+int mr_env_reset(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
+                 const void* init_xy, const uint8_t* mask, int32_t reset_cursor, const mr_step_out* out, void* stream) {
+    return mr_env_reset_ex(st, n, dtype, p, nz, init_xy, mask, reset_cursor, nullptr, out, stream);
+}
+
+int mr_counter_set(uint64_t* counter_dev, uint64_t value, void* stream) {
+    if (!counter_dev) return mr::fail(MR_ERR_ARG, "mr_counter_set: null counter");
+    mr::counter_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, value);
+    return mr::check_launch("mr_counter_set");
 }
 
 int mr_env_step(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
@@ -269,8 +301,10 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
     int rc = mr::check_common("mr_env_step_host", st, n, dtype, p, nz);
     if (rc) return rc;
     if (!io) return mr::fail(MR_ERR_ARG, "mr_env_step_host: null io");
-    if (!io->actions_host || !io->obs_host || !io->rew_host || !io->done_host)
+    if (!io->actions_host || !io->obs_host || !io->done_host || (!io->rew_host && n_chunks != 0))
         return mr::fail(MR_ERR_ARG, "mr_env_step_host: null host buffer");
+    if (io->io_f32 && (n_chunks != 0 || dtype != MR_F64))
+        return mr::fail(MR_ERR_ARG, "mr_env_step_host: io_f32 is the direct mode (n_chunks = 0) with MR_F64 storage");
     if (n == 0) return MR_OK;
     const int64_t el = dtype == MR_F64 ? 8 : 4;
     const int64_t hstride = io->host_row_stride ? io->host_row_stride : n;
@@ -285,8 +319,10 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
         if (oh.state_prime && (out_dev->row_stride ? out_dev->row_stride : n) != hstride)
             return mr::fail(MR_ERR_ARG, "mr_env_step_host: direct mode shares one row stride between obs_host and state_prime");
         oh.skip_goal_rows = io->copy_goal_rows ? 0 : 1;
-        oh.reserved = 0;
-        rc = mr_env_step(st, n, dtype, p, nz, tt, io->actions_host, &oh, stream);
+        oh.out_f32 = io->io_f32 ? 1 : 0;
+        mr_sim_params ph = *p;
+        if (io->io_f32) { ph.action_f32 = 1; oh.state_prime = nullptr; }   // float32 host rows; state_prime stays on the device side
+        rc = mr_env_step(st, n, dtype, &ph, nz, tt, io->actions_host, &oh, stream);
         if (rc) return rc;
         const cudaError_t e0 = cudaStreamSynchronize((cudaStream_t)stream);
         if (e0 != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_env_step_host: %s", cudaGetErrorString(e0));
@@ -366,6 +402,9 @@ int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_si
         return mr::fail(MR_ERR_ARG, "mr_env_rollout: actions must be 16-byte aligned");
     if (p->auto_reset && nz == nullptr)
         return mr::fail(MR_ERR_ARG, "mr_env_rollout: auto_reset needs mr_noise (seed) for the init sampler");
+    if (out && out->out_f32) return mr::fail(MR_ERR_UNSUPPORTED, "mr_env_rollout: float32 output rows are a step option");
+    if (p->action_f32 && dtype == MR_F64 && io->action_source == MR_ACTIONS_TENSOR)
+        return mr::fail(MR_ERR_UNSUPPORTED, "mr_env_rollout: float32 actions with fp64 storage are a step option");
     const mr::Params pp = mr::to_params(*p, nz);
     mr::TimeView tv{tt->t, tt->len};
     cudaStream_t s = (cudaStream_t)stream;

@@ -30,6 +30,8 @@ struct StateView {
     int32_t* counter;
     int32_t* cursor;
     uint8_t* status;
+    double *a0, *sigma;   // optional per-env Simulator.a0 / noise_var rows (all three or none)
+    uint8_t* mism;        // optional per-env Simulator.is_mismatched
 };
 
 template <class T>
@@ -40,13 +42,32 @@ struct OutView {
     T* sp;            // [2][stride]
     int64_t stride;
     bool goal;        // write the constant goal rows obs[2], obs[3] (off when the caller keeps them pre-zeroed)
+    bool f32;         // T = double only: obs / rew / sp are float rows (mr_step_out.out_f32), stride counts floats
 };
 
+// one output element: the row is T, or float when the float32-output option is on (step kernels only)
+template <class T>
+__device__ __forceinline__ void put_out(T* row, bool f32, int64_t i, double v) {
+    if constexpr (sizeof(T) == 8) { if (f32) { reinterpret_cast<float*>(row)[i] = (float)v; return; } }
+    row[i] = (T)v;
+}
+template <class T>
+__device__ __forceinline__ T* out_row(T* base, bool f32, int64_t elems) {   // base + elems in units of the row type
+    if constexpr (sizeof(T) == 8) { if (f32) return reinterpret_cast<T*>(reinterpret_cast<float*>(base) + elems); }
+    return base + elems;
+}
+
 struct NoiseView {
-    const double* table;
-    int64_t table_len;
+    const double* table;       // [table_len][table_stride]; local env i reads column table_col0 + i
+    int64_t table_len, table_stride, table_col0;
     uint64_t seed, offset, env_base;
+    const uint64_t* offset_dev;   // optional device counter added to offset (CUDA-graph replays)
 };
+
+// env-step index of this launch; read after griddepcontrol.wait (an earlier kernel of the stream may have set it)
+__device__ __forceinline__ uint64_t step_offset(const NoiseView& nv) {
+    return nv.offset + (nv.offset_dev ? *reinterpret_cast<const volatile uint64_t*>(nv.offset_dev) : 0ull);
+}
 
 struct TimeView { const double* t; int len; };
 
@@ -125,7 +146,7 @@ __device__ __forceinline__ typename NoiseOf<MODE>::type make_noise(const NoiseVi
                                                                    uint32_t purpose = kPurposeNoise) {
     typename NoiseOf<MODE>::type nz;
     if constexpr (MODE == MR_NOISE_TABLE) {
-        nz.col = nv.table + env; nz.stride = n; nz.cursor = cursor;
+        nz.col = nv.table + nv.table_col0 + env; nz.stride = nv.table_stride; nz.cursor = cursor;
         nz.len = (int32_t)nv.table_len; nz.overflow = 0;
     } else if constexpr (MODE == MR_NOISE_PHILOX) {
         nz.seek(nv.env_base + (uint64_t)env, step, purpose);
@@ -155,9 +176,10 @@ __device__ __forceinline__ void auto_reset_env(Env& e, const NoiseView& nv, int6
 template <class T, int MODE>
 int launch_step(const StateView<T>& sv, const T* actions, const OutView<T>& ov, const NoiseView& nv, const TimeView& tv,
                 const Params& p, int64_t n, bool vec_ok, cudaStream_t s);
+struct ResetRows { const double* a0; const double* sigma; const uint8_t* mism; };   // per-env MR_Env.reset arguments (or NULL)
 template <class T, int MODE>
-int launch_reset(const StateView<T>& sv, const T* init_xy, const uint8_t* mask, int reset_cursor, const OutView<T>& ov,
-                 const NoiseView& nv, const Params& p, int64_t n, cudaStream_t s);
+int launch_reset(const StateView<T>& sv, const T* init_xy, const uint8_t* mask, int reset_cursor, const ResetRows& rr,
+                 const OutView<T>& ov, const NoiseView& nv, const Params& p, int64_t n, cudaStream_t s);
 
 template <class T>
 struct RolloutView {

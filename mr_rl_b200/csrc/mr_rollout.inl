@@ -17,8 +17,10 @@ constexpr int kSrcActorTc = 100;   // internal: MR_ACTIONS_ACTOR evaluated on th
 #ifndef MR_ROLLOUT_MINB
 #define MR_ROLLOUT_MINB 6   // measured: 85 registers, 24 warps/SM -> 56 vs 46 Genv-steps/s (sigma = 0) than unconstrained (143 registers)
 #endif
-template <class T, int MODE, bool MISM, int SRC>
-__global__ void __launch_bounds__(128, (SRC == MR_ACTIONS_ACTOR || SRC == kSrcActorTc) ? 1 : MR_ROLLOUT_MINB)
+// PERENV: a0 / noise_var / is_mismatched come from the per-env rows of the state (the model flag is then a run-time
+// branch and MISM is ignored).
+template <class T, int MODE, bool MISM, int SRC, bool PERENV = false>
+__global__ void __launch_bounds__(128, (SRC == MR_ACTIONS_ACTOR || SRC == kSrcActorTc || PERENV) ? 1 : MR_ROLLOUT_MINB)
 env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView nv, TimeView tv, Params p, int64_t n) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ double s_stats[MR_STATS_LEN];
@@ -36,10 +38,15 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
 #pragma unroll
     for (int k = 0; k < MR_STATS_LEN; ++k) acc[k] = 0.0;
 
+    const uint64_t off = step_offset(nv);
     Env e;
     e.x = 110.0; e.y = 110.0; e.fx = 0.0; e.fy = 0.0; e.h = p.dt; e.counter = 0;   // harmless state for padding lanes
     e.status = 0; e.spx = e.spy = 0.0;
     int32_t cur = 0;
+    bool mism_i = MISM;
+    if constexpr (PERENV) {
+        if (live) { p.a0 = st.a0[i]; p.sigma = st.sigma[i]; mism_i = st.mism[i] != 0; }
+    }
     if (live) {
         e.x = (double)st.x[i]; e.y = (double)st.y[i]; e.fx = (double)st.fx[i]; e.fy = (double)st.fy[i];
         e.counter = st.counter[i];
@@ -67,7 +74,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             f_t = (double)io.actions[2 * k]; al = (double)io.actions[2 * k + 1];
         } else if constexpr (SRC == MR_ACTIONS_PHILOX) {
             double u[4];
-            philox_uniform4(p, nv.env_base + (uint64_t)i, nv.offset + (uint64_t)k, kPurposeAction, u);
+            philox_uniform4(p, nv.env_base + (uint64_t)i, off + (uint64_t)k, kPurposeAction, u);
             f_t = p.act_hi[0] * u[0]; al = p.act_hi[1] * u[1];   // U[0,20) x U[0,2pi)
         } else {
             const float obs5[5] = {(float)e.x, (float)e.y, 0.f, 0.f, (float)o.d};
@@ -78,11 +85,16 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
                 actor_forward_smem(s_actor, obs5, (float)p.act_hi[0], (float)p.act_hi[1], a2);
             f_t = (double)a2[0]; al = (double)a2[1];
         }
-        auto nz = make_noise<MODE>(nv, n, live ? i : 0, cur, nv.offset + (uint64_t)k);
+        auto nz = make_noise<MODE>(nv, n, live ? i : 0, cur, off + (uint64_t)k);
         const double t = time_at(tv, e.counter, p.dt);
         const double tb = t + p.dt, tb2 = tb + p.dt;
         e.counter += 1;
-        sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
+        if constexpr (PERENV) {
+            if (mism_i) sim_step<true>(e, t, tb, tb2, f_t, al, p, nz);
+            else sim_step<false>(e, t, tb, tb2, f_t, al, p, nz);
+        } else {
+            sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
+        }
         o = observe(e, p);
         if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; overflow |= nz.overflow != 0; }
         if (live) {
@@ -108,7 +120,12 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             }
             if (p.auto_reset) {
                 int ov = 0;
-                auto_reset_env<MODE, MISM>(e, nv, n, live ? i : 0, cur, nv.offset + (uint64_t)k, p, ov);
+                if constexpr (PERENV) {
+                    if (mism_i) auto_reset_env<MODE, true>(e, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
+                    else auto_reset_env<MODE, false>(e, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
+                } else {
+                    auto_reset_env<MODE, MISM>(e, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
+                }
                 overflow |= ov != 0;
                 o.d = sqrt(e.x * e.x + e.y * e.y);   // the policy's next input is the new episode's first observation (env.reset())
             }
@@ -156,6 +173,21 @@ static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const O
                        const TimeView& tv, const Params& p, int64_t n, cudaStream_t s) {
     const int threads = 128;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    if (sv.a0) {                                            // per-env parameter rows (instantiated once, under MISM = false)
+        if constexpr (!MISM) {
+            switch (rv.action_source) {
+                case MR_ACTIONS_TENSOR:
+                    env_rollout_kernel<T, MODE, false, MR_ACTIONS_TENSOR, true><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+                case MR_ACTIONS_BROADCAST:
+                    env_rollout_kernel<T, MODE, false, MR_ACTIONS_BROADCAST, true><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+                case MR_ACTIONS_PHILOX:
+                    env_rollout_kernel<T, MODE, false, MR_ACTIONS_PHILOX, true><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+                default:
+                    return fail(MR_ERR_UNSUPPORTED, "mr_env_rollout: the in-kernel actor policy does not take per-env parameter rows");
+            }
+            return check_launch("mr_env_rollout");
+        }
+    }
     switch (rv.action_source) {
         case MR_ACTIONS_TENSOR:
             env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_TENSOR><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
@@ -188,8 +220,8 @@ static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const O
 template <>
 int launch_rollout<MR_T, MR_MODE>(const StateView<MR_T>& sv, const RolloutView<MR_T>& rv, const OutView<MR_T>& ov,
                                   const NoiseView& nv, const TimeView& tv, const Params& p, int64_t n, cudaStream_t s) {
-    return p.mism ? rollout_src<MR_T, MR_MODE, true>(sv, rv, ov, nv, tv, p, n, s)
-                  : rollout_src<MR_T, MR_MODE, false>(sv, rv, ov, nv, tv, p, n, s);
+    return (p.mism && !sv.a0) ? rollout_src<MR_T, MR_MODE, true>(sv, rv, ov, nv, tv, p, n, s)
+                              : rollout_src<MR_T, MR_MODE, false>(sv, rv, ov, nv, tv, p, n, s);
 }
 
 }  // namespace mr

@@ -97,12 +97,56 @@ struct alignas(128) TileOut {
     uint8_t done[kTile];
 };
 
-template <class T, int kTile = TileOf<T>::value>
+// Table-noise (parity) mode: the draws an env consumes in one step are table rows cursor .. cursor+15 (+23 when
+// mismatched: 3 draws per RHS evaluation, MR_simulator.py:78-80) of its column.  Envs of a tile normally share the
+// cursor (every step of the common regime takes 16 draws), so those rows of the tile are kNoiseRows contiguous
+// kTile*8-byte lines of the [L][n] table: they are bulk-copied with the state rows.  An env whose cursor is elsewhere
+// (more RK45 attempts, an auto reset) reads the table from global memory for the rows the stage does not hold.
+template <int MODE, bool MISM> struct NoiseRows { static constexpr int value = 0; };
+template <bool MISM> struct NoiseRows<MR_NOISE_TABLE, MISM> { static constexpr int value = MISM ? 24 : 16; };
+// input stages: the noise rows are read during the integration, so their stage is re-filled only after the tile is
+// done (2 stages: one being consumed, one in flight); the other modes copy their inputs to registers first (3 stages)
+template <int MODE> struct StagesIn { static constexpr int value = MODE == MR_NOISE_TABLE ? 2 : kStagesIn; };
+
+template <int kTile, int ROWS>
+struct alignas(128) TileNoiseIn {
+    double z[ROWS][kTile];
+    int32_t cursor[kTile];
+    int32_t base, rows;                 // the stage holds table rows [base, base + rows) of the tile's columns
+};
+template <int kTile> struct TileNoiseIn<kTile, 0> {};
+template <int kTile, int ROWS> struct alignas(128) TileNoiseOut { int32_t cursor[kTile]; };
+template <int kTile> struct TileNoiseOut<kTile, 0> {};
+
+struct TileTableNoise {                 // TableNoise with the common rows served from shared memory
+    static constexpr bool kActive = true;
+    static constexpr bool kCompress = false;
+    const double* stage;                // &z[0][tid] of the tile's stage, row stride = stage_stride
+    const double* col;                  // &table[0][env]
+    int64_t stride;
+    int32_t stage_stride, base, rows;
+    int32_t cursor, len;
+    int overflow;
+    template <class P> __device__ __forceinline__ double next(const P&) {
+        double z = 0.0;
+        const uint32_t k = (uint32_t)(cursor - base);
+        if (k < (uint32_t)rows) z = stage[k * stage_stride];
+        else if (cursor < len) z = col[(int64_t)cursor * stride];
+        else overflow = 1;
+        ++cursor;
+        return z;
+    }
+};
+
+template <class T, int MODE = MR_NOISE_NONE, bool MISM = false, int kTile = TileOf<T>::value>
 struct StepSmem {
-    TileIn<T, kTile> in[kStagesIn];
+    static constexpr int kIn = StagesIn<MODE>::value;
+    TileIn<T, kTile> in[kIn];
     TileOut<T, kTile> out[kStagesOut];
+    TileNoiseIn<kTile, NoiseRows<MODE, MISM>::value> nin[kIn];
+    TileNoiseOut<kTile, NoiseRows<MODE, MISM>::value> nout[kStagesOut];
     alignas(128) T zero[kTile];
-    alignas(8) uint64_t full[kStagesIn];
+    alignas(8) uint64_t full[kIn];
 };
 
 // at least 16 warps per SM (<= 128 registers): the generated-noise variant would otherwise take 136.
@@ -116,18 +160,27 @@ struct StepSmem {
 #define MR_TMA_WARPS_F32 24
 #endif
 template <class T> struct TmaWarps { static constexpr int value = sizeof(T) == 4 ? MR_TMA_WARPS_F32 : MR_TMA_WARPS; };
+// resident CTAs per SM the launch bound asks for: the table mode is limited by its shared-memory stages instead
+template <class T, int MODE> struct TmaMinCtas {
+    static constexpr int value = MODE == MR_NOISE_TABLE ? 1 : TmaWarps<T>::value * 32 / TileOf<T>::value;
+};
+
 template <class T, int MODE, bool MISM>
-__global__ void __launch_bounds__(TileOf<T>::value, TmaWarps<T>::value * 32 / TileOf<T>::value)
+__global__ void __launch_bounds__(TileOf<T>::value, TmaMinCtas<T, MODE>::value)
 env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
                     Params p, int64_t n_tiles, int64_t n_total) {
     constexpr int kTile = TileOf<T>::value;
+    constexpr int kSI = StagesIn<MODE>::value;
+    constexpr int kNR = NoiseRows<MODE, MISM>::value;
+    constexpr bool kTable = MODE == MR_NOISE_TABLE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    StepSmem<T>& sm = *reinterpret_cast<StepSmem<T>*>(smem_raw);
+    using Smem = StepSmem<T, MODE, MISM>;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
     const int64_t first = blockIdx.x, stride = gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < kStagesIn; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < kSI; ++s) mbar_init(&sm.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     sm.zero[tid] = (T)0;   // kTile threads
@@ -139,7 +192,11 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     constexpr uint32_t kRow = kTile * sizeof(T);
-    constexpr uint32_t kInBytes = 5 * kRow + 2 * kRow + kTile * 4;
+    const bool act32 = sizeof(T) == 8 && p.act_f32;         // float32 actions with fp64 storage (mr_sim_params.action_f32)
+    const bool out32 = sizeof(T) == 8 && out.f32;           // float32 output rows with fp64 storage (mr_step_out.out_f32)
+    const uint32_t act_bytes = act32 ? kTile * 8u : 2u * kRow;
+    const uint32_t kInBytes = 5 * kRow + act_bytes + kTile * 4;
+    const uint64_t off = step_offset(nv);                   // env-step index of this launch (after griddepcontrol.wait)
 
     // Tried and rejected (measured, 2^20 envs fp64): a dedicated producer warp with mbarrier-only
     // hand-offs (no CTA barrier) — the extra warp costs a resident CTA at ~120 registers/thread:
@@ -153,31 +210,53 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
     constexpr int kWarps = MR_ISSUE_WARPS;                  // 1: a single issuing thread
     const int warp = tid >> 5;
     const bool elect = (tid & 31) == 0 && warp < kWarps;
-    auto issue_loads = [&](int s, int64_t tile) {     // called by the elected lane of every warp
+    // cbase (table mode): the noise cursor of the tile's first env = first table row to stage
+    auto issue_loads = [&](int s, int64_t tile, int32_t cbase) {     // called by the elected lane of every warp
         const int64_t i0 = tile * kTile;
         uint64_t* bar = &sm.full[s];
         TileIn<T, kTile>& b = sm.in[s];
-        if (warp == 0) mbar_expect_tx(bar, kInBytes);
+        if constexpr (kTable) {
+            int64_t rows = nv.table_len - (int64_t)cbase;
+            rows = rows < 0 ? 0 : (rows > kNR ? kNR : rows);
+            if (cbase < 0) rows = 0;
+            sm.nin[s].base = cbase; sm.nin[s].rows = (int32_t)rows;
+            mbar_expect_tx(bar, kInBytes + kTile * 4 + (uint32_t)rows * kTile * 8);
+            bulk_load(sm.nin[s].cursor, st.cursor + i0, kTile * 4, bar);
+            const double* src = nv.table + (int64_t)cbase * nv.table_stride + nv.table_col0 + i0;
+            for (int k = 0; k < (int)rows; ++k) bulk_load(sm.nin[s].z[k], src + (int64_t)k * nv.table_stride, kTile * 8, bar);
+        } else {
+            if (warp == 0) mbar_expect_tx(bar, kInBytes);
+        }
         if (warp == 0 % kWarps) bulk_load(b.x, st.x + i0, kRow, bar);
         if (warp == 1 % kWarps) bulk_load(b.y, st.y + i0, kRow, bar);
         if (warp == 2 % kWarps) bulk_load(b.fx, st.fx + i0, kRow, bar);
         if (warp == 3 % kWarps) bulk_load(b.fy, st.fy + i0, kRow, bar);
         if (warp == 4 % kWarps) bulk_load(b.h, st.h + i0, kRow, bar);
-        if (warp == 5 % kWarps) bulk_load(b.act, actions + 2 * i0, 2 * kRow, bar);
+        if (warp == 5 % kWarps)
+            bulk_load(b.act, act32 ? (const void*)(reinterpret_cast<const float*>(actions) + 2 * i0) : (const void*)(actions + 2 * i0),
+                      act_bytes, bar);
         if (warp == 6 % kWarps) bulk_load(b.counter, st.counter + i0, kTile * 4, bar);
     };
+    // this launch changes a tile's cursors only when it processes the tile, so the elected thread may read the first
+    // cursor of a tile it will load later with a plain load, one issue ahead (its latency hides behind a tile)
+    auto tile_cursor = [&](int64_t tile) -> int32_t {
+        if constexpr (kTable) { if (tile < n_tiles) return st.cursor[tile * kTile]; }
+        return 0;
+    };
 
+    int32_t cb_next = 0;
     if (elect) {
-        for (int s = 0; s < kStagesIn; ++s) {
+        for (int s = 0; s < kSI; ++s) {
             const int64_t tile = first + (int64_t)s * stride;
-            if (tile < n_tiles) issue_loads(s, tile);
+            if (tile < n_tiles) issue_loads(s, tile, tile_cursor(tile));
         }
+        cb_next = tile_cursor(first + (int64_t)kSI * stride);
     }
 
     int it = 0;
     for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
-        const int s = it % kStagesIn;
-        const uint32_t parity = (uint32_t)(it / kStagesIn) & 1u;
+        const int s = it % kSI;
+        const uint32_t parity = (uint32_t)(it / kSI) & 1u;
         const int so = it % kStagesOut;
         const int64_t i0 = tile * kTile;
 
@@ -188,27 +267,42 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
         const T h_raw = bi.h[tid];
         e.counter = bi.counter[tid]; e.status = 0; e.spx = e.spy = 0.0;
         double f_t, al;
-        if constexpr (sizeof(T) == 8) { const double2 a2 = reinterpret_cast<const double2*>(bi.act)[tid]; f_t = a2.x; al = a2.y; }
+        if (sizeof(T) == 8 && !act32) { const double2 a2 = reinterpret_cast<const double2*>(bi.act)[tid]; f_t = a2.x; al = a2.y; }
         else { const float2 a2 = reinterpret_cast<const float2*>(bi.act)[tid]; f_t = a2.x; al = a2.y; }
 
         if (elect) bulk_wait_read<kStagesOut - 1>();        // out[so] (used kStagesOut tiles ago) has been read out
         __syncthreads();                                    // [A] in[s] fully consumed, out[so] free
-        if (elect) {
-            const int64_t nxt = tile + (int64_t)kStagesIn * stride;
-            if (nxt < n_tiles) issue_loads(s, nxt);
+        if constexpr (!kTable) {
+            if (elect) {
+                const int64_t nxt = tile + (int64_t)kSI * stride;
+                if (nxt < n_tiles) issue_loads(s, nxt, 0);
+            }
         }
 
         const double t = time_at(tv, e.counter, p.dt);
         const double tb = t + p.dt, tb2 = tb + p.dt;
         e.h = decode_h<T>(h_raw, tb - t);
-        auto nz = make_noise<MODE>(nv, n_total, i0 + tid, 0, nv.offset);
+        int32_t cur = 0;
         e.counter += 1;                                     // MR_env.py:80
-        sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
+        if constexpr (kTable) {
+            TileTableNoise nz;
+            nz.stage = &sm.nin[s].z[0][tid]; nz.stage_stride = kTile;
+            nz.base = sm.nin[s].base; nz.rows = sm.nin[s].rows;
+            nz.col = nv.table + nv.table_col0 + i0 + tid; nz.stride = nv.table_stride;
+            nz.cursor = sm.nin[s].cursor[tid]; nz.len = (int32_t)nv.table_len; nz.overflow = 0;
+            sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
+            cur = nz.cursor;
+            if (nz.overflow) e.status |= kNoiseOverflow;
+        } else {
+            auto nz = make_noise<MODE>(nv, n_total, i0 + tid, 0, off);
+            sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
+        }
         const Observation o = observe(e, p);
         double d_out = o.d, il_next = tb2 - tb;
         if (p.auto_reset && o.done) {                       // reported obs = first obs of the new episode
-            int32_t cur = 0; int ov = 0;
-            auto_reset_env<MODE, MISM>(e, nv, n_total, i0 + tid, cur, nv.offset, p, ov);
+            int ov = 0;
+            auto_reset_env<MODE, MISM>(e, nv, n_total, i0 + tid, cur, off, p, ov);
+            if (ov) e.status |= kNoiseOverflow;
             d_out = sqrt(e.x * e.x + e.y * e.y);
             il_next = p.dt;
         }
@@ -217,31 +311,69 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
         bo.x[tid] = (T)e.x; bo.y[tid] = (T)e.y; bo.fx[tid] = (T)e.fx; bo.fy[tid] = (T)e.fy;
         bo.h[tid] = encode_h<T>(e.h, il_next);
         bo.counter[tid] = e.counter;
-        bo.d[tid] = (T)d_out; bo.rew[tid] = (T)o.rew; bo.done[tid] = o.done ? 1 : 0;
-        if (out.sp) { bo.spx[tid] = (T)e.spx; bo.spy[tid] = (T)e.spy; }
+        bo.done[tid] = o.done ? 1 : 0;
+        if (out32) {
+            // the output-only rows of the stage (d, rew, spx: kTile doubles each) are re-used as 2 * kTile floats:
+            // rew <- x | y,  d <- d | rew,  spx <- spx | spy
+            float* fxy = reinterpret_cast<float*>(bo.rew); fxy[tid] = (float)e.x; fxy[kTile + tid] = (float)e.y;
+            float* fdr = reinterpret_cast<float*>(bo.d); fdr[tid] = (float)d_out; fdr[kTile + tid] = (float)o.rew;
+            if (out.sp) { float* fsp = reinterpret_cast<float*>(bo.spx); fsp[tid] = (float)e.spx; fsp[kTile + tid] = (float)e.spy; }
+        } else {
+            bo.d[tid] = (T)d_out; bo.rew[tid] = (T)o.rew;
+            if (out.sp) { bo.spx[tid] = (T)e.spx; bo.spy[tid] = (T)e.spy; }
+        }
+        if constexpr (kTable) sm.nout[so].cursor[tid] = cur;
         if (e.status) st.status[i0 + tid] |= (uint8_t)e.status;   // rare: sticky flags, plain store
         fence_async_smem();
         __syncthreads();                                    // [B] tile results complete in out[so]
         if (elect) {
+            if constexpr (kTable) {                         // the stage's noise rows are free only now
+                const int64_t nxt = tile + (int64_t)kSI * stride;
+                if (nxt < n_tiles) issue_loads(s, nxt, cb_next);
+                cb_next = tile_cursor(nxt + stride);
+                bulk_store(st.cursor + i0, sm.nout[so].cursor, kTile * 4);
+            }
             if (warp == 0 % kWarps) bulk_store(st.x + i0, bo.x, kRow);
             if (warp == 1 % kWarps) bulk_store(st.y + i0, bo.y, kRow);
             if (warp == 2 % kWarps) bulk_store(st.fx + i0, bo.fx, kRow);
             if (warp == 3 % kWarps) bulk_store(st.fy + i0, bo.fy, kRow);
             if (warp == 4 % kWarps) bulk_store(st.h + i0, bo.h, kRow);
             if (warp == 5 % kWarps) bulk_store(st.counter + i0, bo.counter, kTile * 4);
-            if (out.obs) {
-                if (warp == 6 % kWarps) bulk_store(out.obs + i0, bo.x, kRow);
-                if (warp == 7 % kWarps) bulk_store(out.obs + out.stride + i0, bo.y, kRow);
-                if (out.goal && warp == 8 % kWarps) bulk_store(out.obs + 2 * out.stride + i0, sm.zero, kRow);   // goal = (0,0), MR_env.py:57
-                if (out.goal && warp == 9 % kWarps) bulk_store(out.obs + 3 * out.stride + i0, sm.zero, kRow);
-                if (warp == 10 % kWarps) bulk_store(out.obs + 4 * out.stride + i0, bo.d, kRow);
+            if (out32) {
+                constexpr uint32_t kRow32 = kTile * 4;
+                float* obs = reinterpret_cast<float*>(out.obs);
+                const float* fxy = reinterpret_cast<const float*>(bo.rew);
+                const float* fdr = reinterpret_cast<const float*>(bo.d);
+                if (obs) {
+                    bulk_store(obs + i0, fxy, kRow32);
+                    bulk_store(obs + out.stride + i0, fxy + kTile, kRow32);
+                    if (out.goal) {
+                        bulk_store(obs + 2 * out.stride + i0, sm.zero, kRow32);
+                        bulk_store(obs + 3 * out.stride + i0, sm.zero, kRow32);
+                    }
+                    bulk_store(obs + 4 * out.stride + i0, fdr, kRow32);
+                }
+                if (out.rew) bulk_store(reinterpret_cast<float*>(out.rew) + i0, fdr + kTile, kRow32);
+                if (out.sp) {
+                    const float* fsp = reinterpret_cast<const float*>(bo.spx);
+                    bulk_store(reinterpret_cast<float*>(out.sp) + i0, fsp, kRow32);
+                    bulk_store(reinterpret_cast<float*>(out.sp) + out.stride + i0, fsp + kTile, kRow32);
+                }
+            } else {
+                if (out.obs) {
+                    if (warp == 6 % kWarps) bulk_store(out.obs + i0, bo.x, kRow);
+                    if (warp == 7 % kWarps) bulk_store(out.obs + out.stride + i0, bo.y, kRow);
+                    if (out.goal && warp == 8 % kWarps) bulk_store(out.obs + 2 * out.stride + i0, sm.zero, kRow);   // goal = (0,0), MR_env.py:57
+                    if (out.goal && warp == 9 % kWarps) bulk_store(out.obs + 3 * out.stride + i0, sm.zero, kRow);
+                    if (warp == 10 % kWarps) bulk_store(out.obs + 4 * out.stride + i0, bo.d, kRow);
+                }
+                if (out.rew && warp == 11 % kWarps) bulk_store(out.rew + i0, bo.rew, kRow);
+                if (out.sp) {
+                    if (warp == 13 % kWarps) bulk_store(out.sp + i0, bo.spx, kRow);
+                    if (warp == 14 % kWarps) bulk_store(out.sp + out.stride + i0, bo.spy, kRow);
+                }
             }
-            if (out.rew && warp == 11 % kWarps) bulk_store(out.rew + i0, bo.rew, kRow);
             if (out.done && warp == 12 % kWarps) bulk_store(out.done + i0, bo.done, kTile);
-            if (out.sp) {
-                if (warp == 13 % kWarps) bulk_store(out.sp + i0, bo.spx, kRow);
-                if (warp == 14 % kWarps) bulk_store(out.sp + out.stride + i0, bo.spy, kRow);
-            }
             bulk_commit();                                  // bulk groups are per thread: every issuing lane commits
         }
     }

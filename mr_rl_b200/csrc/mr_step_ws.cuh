@@ -10,6 +10,14 @@
 // time.  The draws depend only on (seed, global env index, env-step index) — not on loaded data — so another warp can
 // produce them ahead of time; its instruction stream is independent of the fp64 chains and fills the idle issue slots,
 // and the integrators shrink to the noise-free kernel's register footprint.
+// MEASURED AND REJECTED as the default (B200, 2^20 envs, fp64, profiles/r02_ncu_step_ws.txt): 45.0 us per launch against
+// 32.0 us for env_step_tma_kernel (fp32 storage 35.2 against 29.3).  The draws of a tile are ~600 warp-instructions and
+// the service warp also issues the tile's 20 bulk copies, while each integrator warp has ~420: the ONE service warp per
+// CTA is the critical path (the integrators' top stall is the CTA barrier that waits for it), and at 96 registers the
+// integrators spill (LDL/STL 0.85 M warp-instructions per launch).  Two service warps per CTA would need 80 registers
+// per thread at 4 CTAs/SM, or cost a quarter of the integrator warps at 3 CTAs/SM; the register file, not the issue
+// slots, is what the step is short of.  Kept, selectable with mr_set_step_path(4) / MR_STEP_PATH=ws, so the measurement
+// can be repeated; results are bit-identical to the plain kernel (tests/test_gpu_env.py).
 // Noise semantics are identical to PhiloxNoise::draw8 (same counters, same blocks, same Box-Muller), so this kernel and
 // env_step_tma_kernel<T, MR_NOISE_PHILOX, false> produce bit-identical results (tested).
 #pragma once
@@ -62,6 +70,7 @@ env_step_tma_ws_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T
 
     constexpr uint32_t kRow = kTile * sizeof(T);
     constexpr uint32_t kInBytes = 5 * kRow + 2 * kRow + kTile * 4;
+    const uint64_t off = step_offset(nv);
 
     auto issue_loads = [&](int s, int64_t tile) {
         const int64_t i0 = tile * kTile;
@@ -83,7 +92,7 @@ env_step_tma_ws_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T
         for (int q = 0; q < kTile / kSvc; ++q) {
             const int j = lane_s + q * kSvc;
             PhiloxNoise nz;
-            nz.seek(nv.env_base + (uint64_t)(i0 + j), nv.offset);
+            nz.seek(nv.env_base + (uint64_t)(i0 + j), off);
             float z8[8];
             nz.draw8(p, z8);
             sm.z[buf][0][j] = make_float4(z8[0], z8[1], z8[2], z8[3]);
@@ -136,7 +145,7 @@ env_step_tma_ws_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T
             const float4 za = sm.z[it & 1][0][tid], zb = sm.z[it & 1][1][tid];
             const float z8[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
             PhiloxNoise nz;                                       // only the rare multi-attempt path draws from it
-            nz.seek(nv.env_base + (uint64_t)(i0 + tid), nv.offset);
+            nz.seek(nv.env_base + (uint64_t)(i0 + tid), off);
             nz.blk += 2;
             e.counter += 1;                                       // MR_env.py:80
             sim_step_drawn(e, t, tb, tb2, f_t, al, p, nz, z8);
@@ -144,7 +153,7 @@ env_step_tma_ws_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T
             double d_out = o.d, il_next = tb2 - tb;
             if (p.auto_reset && o.done) {                         // reported obs = first obs of the new episode
                 int32_t cur = 0; int ov = 0;
-                auto_reset_env<MR_NOISE_PHILOX, false>(e, nv, n_total, i0 + tid, cur, nv.offset, p, ov);
+                auto_reset_env<MR_NOISE_PHILOX, false>(e, nv, n_total, i0 + tid, cur, off, p, ov);
                 d_out = sqrt(e.x * e.x + e.y * e.y);
                 il_next = p.dt;
             }

@@ -41,10 +41,14 @@ class VecMREnv:
         keeps trajectories independent of the number of ranks)
     auto_reset : restart an env from ``init_space`` right after a terminal step
     reward_mode : "const" (rew = 10, MR_env.py:89) or "shaped" (calculate_reward, MR_env.py:118-134)
+    per_env_params : keep Simulator.a0 / noise_var / is_mismatched (MR_simulator.py:16-19, per-instance attributes set
+        by every reset, MR_env.py:179-183) as per-env rows instead of launch scalars: ``reset`` then takes scalars or
+        [N] arrays for them, a masked reset may change them, and one launch steps envs with different models
     """
 
     def __init__(self, num_envs, device="cuda", dtype=torch.float64, noise="philox", seed=0, env_base=0,
-                 auto_reset=False, reward_mode="const", noise_table=None, time_table_len=4096, host_mapped_aux=False):
+                 auto_reset=False, reward_mode="const", noise_table=None, time_table_len=4096, host_mapped_aux=False,
+                 per_env_params=False):
         self.lib = L.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -97,8 +101,15 @@ class VecMREnv:
         self.lib.mr_fill_time_table_host(tt.ctypes.data_as(C.c_void_p), len(tt), self.params.time_span)
         self._tt = torch.from_numpy(tt).to(dev)
 
+        self.per_env_params = bool(per_env_params)
+        self._a0_row = self._sigma_row = self._mism_row = None
+        if self.per_env_params:
+            self._a0_row = torch.zeros(npad, dtype=torch.float64, device=dev)
+            self._sigma_row = torch.zeros(npad, dtype=torch.float64, device=dev)
+            self._mism_row = torch.zeros(npad, dtype=torch.uint8, device=dev)
         self._c_state = L.EnvState(*[_ptr(self._state[i]) for i in range(5)], _ptr(self._counter),
-                                   _ptr(self._cursor), _ptr(self._status))
+                                   _ptr(self._cursor), _ptr(self._status), _ptr(self._a0_row), _ptr(self._sigma_row),
+                                   _ptr(self._mism_row))
         self._c_tt = L.TimeTable(_ptr(self._tt), len(tt), 0)
         self._c_out = L.StepOut(_ptr(self._obs), _ptr(self._rew), _ptr(self._done), _ptr(self._sp), npad)
         self._c_out_lean = L.StepOut(_ptr(self._obs), _ptr(self._rew), _ptr(self._done), C.c_void_p(0), npad)
@@ -106,7 +117,7 @@ class VecMREnv:
         # --- noise -----------------------------------------------------------------------------
         self.noise_kind = noise
         self._noise_table = None
-        self._c_noise = L.Noise(_NOISE[noise], 0, C.c_void_p(0), 0, int(seed) & (2**64 - 1), 0, int(env_base))
+        self._c_noise = L.Noise(_NOISE[noise], 0, C.c_void_p(0), 0, int(seed) & (2**64 - 1), 0, int(env_base), C.c_void_p(0))
         if noise == "table":
             if noise_table is None:
                 raise ValueError("noise='table' needs noise_table[L, num_envs] (standard normals, float64)")
@@ -177,15 +188,16 @@ class VecMREnv:
 
     @property
     def a0(self):
-        return self.params.a0
+        """Simulator.a0: the launch scalar, or the [N] device row with ``per_env_params``."""
+        return self._a0_row[:self.num_envs] if self.per_env_params else self.params.a0
 
     @property
     def noise_var(self):
-        return self.params.noise_var
+        return self._sigma_row[:self.num_envs] if self.per_env_params else self.params.noise_var
 
     @property
     def is_mismatched(self):
-        return bool(self.params.is_mismatched)
+        return self._mism_row[:self.num_envs].bool() if self.per_env_params else bool(self.params.is_mismatched)
 
     @property
     def time_span(self):
@@ -234,6 +246,8 @@ class VecMREnv:
         nz = self._c_noise
         if self.noise_kind == "table":
             nz.mode = L.NOISE_TABLE
+        elif self.per_env_params and self.noise_kind == "philox":
+            nz.mode = L.NOISE_PHILOX              # the noise levels live in the per-env row
         elif sigma == 0.0:
             nz.mode = L.NOISE_NONE
         elif self.noise_kind == "philox":
@@ -246,18 +260,40 @@ class VecMREnv:
     # ---- MR_Env.reset, MR_env.py:164-201 -----------------------------------------------------
     def reset(self, init=None, noise_var=1, a0=1, is_mismatched=False, mask=None, reset_cursor=True):
         """Reset all envs (or those with ``mask[i] != 0``).  ``init``: None (sample init_space on
-        device), a (2,) position for every env, or an [N, 2] tensor.  Returns obs [N, 5]."""
+        device), a (2,) position for every env, or an [N, 2] tensor.  With ``per_env_params`` the three simulator
+        arguments may be scalars or [N] arrays (only the masked envs take the new values).  Returns obs [N, 5]."""
         if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
                 return self.reset(init, noise_var, a0, is_mismatched, mask, reset_cursor)
         n = self.num_envs
         p = self.params
-        if mask is not None and (float(noise_var) != p.noise_var or float(a0) != p.a0
-                                 or bool(is_mismatched) != bool(p.is_mismatched)):
-            raise ValueError("a masked reset cannot change noise_var / a0 / is_mismatched (launch scalars)")
+        rp, keep = None, []
+        if self.per_env_params:
+            def row(v, dt):
+                if np.ndim(v) == 0 and not torch.is_tensor(v):
+                    return None
+                t = torch.as_tensor(v).to(device=self.device, dtype=dt).contiguous()
+                if t.numel() != n:
+                    raise ValueError(f"per-env reset arguments must have {n} entries")
+                keep.append(t)
+                return t
+            ra, rs, rm = row(a0, torch.float64), row(noise_var, torch.float64), row(is_mismatched, torch.uint8)
+            rp = L.ResetParams(_ptr(ra), _ptr(rs), _ptr(rm))
+            # scalars go through the launch parameters (the kernel writes them into the rows of the envs it resets)
+            a0 = 0.0 if ra is not None else a0
+            noise_var = 0.0 if rs is not None else noise_var
+            is_mismatched = False if rm is not None else is_mismatched
+            if self.noise_kind == "none" and (rs is not None and float(rs.abs().max()) != 0.0 or float(noise_var) != 0.0):
+                raise ValueError("noise_var != 0 needs noise='philox' or noise='table'")
+        elif mask is not None and (float(noise_var) != p.noise_var or float(a0) != p.a0
+                                   or bool(is_mismatched) != bool(p.is_mismatched)):
+            raise ValueError("a masked reset cannot change noise_var / a0 / is_mismatched when they are launch scalars "
+                             "(construct the env with per_env_params=True)")
         p.mism_at_reset = p.is_mismatched          # the integrator is built before the flag changes (:181 vs :183)
         p.noise_var = float(noise_var)
         p.a0 = float(a0)
+        if self.per_env_params:
+            p.is_mismatched = 1 if is_mismatched else 0       # the NEW flag for the envs being reset (old one: their row)
         init_t = None
         if init is not None:
             init_t = torch.as_tensor(np.asarray(init) if not torch.is_tensor(init) else init)
@@ -271,8 +307,9 @@ class VecMREnv:
         if mask is not None:
             mask_t = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
         nz = self._noise_for(p.noise_var)
-        rc = self.lib.mr_env_reset(C.byref(self._c_state), n, self._dt, C.byref(p), C.byref(nz), _ptr(init_t),
-                                   _ptr(mask_t), 1 if reset_cursor else 0, C.byref(self._c_out), self._stream())
+        rc = self.lib.mr_env_reset_ex(C.byref(self._c_state), n, self._dt, C.byref(p), C.byref(nz), _ptr(init_t),
+                                      _ptr(mask_t), 1 if reset_cursor else 0, C.byref(rp) if rp is not None else None,
+                                      C.byref(self._c_out), self._stream())
         L.check(rc, "mr_env_reset")
         self.kernel_launches += 1
         self._step_index += 1
@@ -305,6 +342,16 @@ class VecMREnv:
         self._step_index += 1
         return self._views
 
+    # ---- K single-step launches as ONE CUDA graph ---------------------------------------------------------------
+    def capture_steps(self, action_buffers, k_steps=None):
+        """Capture ``k_steps`` launches of the single-step kernel into a CUDA graph (step k reads
+        ``action_buffers[k % len(action_buffers)]``, each an [N, 2] device tensor whose CONTENTS may change between
+        replays) and return a ``StepGraph``; ``graph.replay()`` then costs one graph launch instead of K kernel launches —
+        what a rank of a sharded population needs once a launch is only a few microseconds of work.
+        The Philox env-step index is read from a device counter (mr_noise.offset_dev) that every replay advances, so
+        replays keep drawing fresh noise; results are identical to K ``step`` calls (tested)."""
+        return StepGraph(self, action_buffers, k_steps)
+
     def _pinned_buf(self, key, shape, dtype):
         b = self._pinned.get(key)
         if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
@@ -321,7 +368,8 @@ class VecMREnv:
         and state_prime are).  ``host_mode = "staged"``: copies through the device rows in pipelined chunks."""
         n = self.num_envs
         fast = self._pinned.get("fast")            # the same pinned action tensor as last time, direct mode: everything cached
-        if fast is not None and actions is fast[0] and self.host_mode == "direct":
+        if fast is not None and actions is fast[0] and self.host_mode == "direct" \
+                and actions.dtype == (self.host_io_dtype or self.dtype):
             _, io_ref, ret = fast
             if torch.cuda.current_device() != self._dev_index:
                 with torch.cuda.device(self.device):
@@ -335,8 +383,11 @@ class VecMREnv:
             self.kernel_launches += 1
             self._step_index += 1
             return ret
+        direct = self.host_mode == "direct"
+        io32 = direct and self.dtype is torch.float64 and self.host_io_dtype is torch.float32
+        hdt = torch.float32 if io32 else self.dtype          # dtype of the host action / observation buffers
         if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() \
-                and actions.dtype == self.dtype and actions.is_contiguous() and actions.numel() == 2 * n:
+                and actions.dtype == hdt and actions.is_contiguous() and actions.numel() == 2 * n:
             a_pin = actions.view(n, 2)
             in_place = True
         else:
@@ -344,28 +395,37 @@ class VecMREnv:
             a_np = np.asarray(actions.numpy() if torch.is_tensor(actions) else actions)
             if a_np.size != 2 * n:
                 raise ValueError(f"actions must be [{n}, 2]")
-            a_pin = self._pinned_buf("act", (n, 2), self.dtype)
+            a_pin = self._pinned_buf("act", (n, 2), hdt)
             np.copyto(a_pin.numpy(), a_np.reshape(n, 2), casting="same_kind")
         a_dev = self._pinned.get("act_dev")
-        if a_dev is None:
+        if a_dev is None and not direct:
             a_dev = self._pinned["act_dev"] = torch.empty(n, 2, dtype=self.dtype, device=self.device)
-        fresh = "obs" not in self._pinned
-        o_pin = self._pinned_buf("obs", (5, self._np), self.dtype)    # same row stride as the device rows
-        r_pin = self._pinned_buf("rew", (n,), self.dtype)
+        fresh = "obs" not in self._pinned or self._pinned["obs"].dtype != hdt
+        o_pin = self._pinned_buf("obs", (5, self._np), hdt)           # same row stride as the device rows
         d_pin = self._pinned_buf("done", (n,), torch.uint8)
+        # the constant reward of MR_env.py:89 is not sent at all in direct mode: one cached array of 10s
+        const_rew = direct and self.params.reward_mode == L.REWARD_CONST10
+        if const_rew:
+            r_np = self._pinned.get("rew_const")
+            if r_np is None or r_np.dtype != o_pin.numpy().dtype:
+                r_np = self._pinned["rew_const"] = np.full(n, 10.0, dtype=o_pin.numpy().dtype)
+            r_ptr = 0
+        else:
+            r_pin = self._pinned_buf("rew", (n,), hdt)
+            r_np, r_ptr = r_pin.numpy(), r_pin.data_ptr()
         if fresh:
             o_pin.zero_()          # goal rows 2, 3 are always 0 (MR_env.py:57): written once, never re-copied
         # one C call.  "direct": the step kernel reads / writes the pinned host buffers itself (zero-copy over PCIe);
         # "staged": H2D, kernel(s) and D2H pipelined over env chunks on the library's own streams
-        chunks = 0 if self.host_mode == "direct" else self._host_chunks(n)
+        chunks = 0 if direct else self._host_chunks(n)
         with torch.cuda.device(self.device):
             pl = self._pinned.get("pipeline")
             if pl is None and chunks:
                 h = C.c_void_p()
                 L.check(self.lib.mr_host_pipeline_create(8, C.byref(h)), "mr_host_pipeline_create")
                 pl = self._pinned["pipeline"] = h
-            io = L.HostStepIO(a_pin.data_ptr(), a_dev.data_ptr(), o_pin.data_ptr(), r_pin.data_ptr(), d_pin.data_ptr(),
-                              self._np, 0, 0)
+            io = L.HostStepIO(a_pin.data_ptr(), a_dev.data_ptr() if a_dev is not None else 0, o_pin.data_ptr(), r_ptr,
+                              d_pin.data_ptr(), self._np, 0, 1 if io32 else 0)
             nz = self._noise_for(self.params.noise_var)
             rc = self.lib.mr_env_step_host(pl, self._b_state, n, self._dt, self._b_params, C.byref(nz), self._b_tt, C.byref(io),
                                            self._b_out if self.want_state_prime else self._b_out_lean, chunks,
@@ -373,7 +433,7 @@ class VecMREnv:
         L.check(rc, "mr_env_step_host")
         self.kernel_launches += max(chunks, 1)
         self._step_index += 1
-        ret = (o_pin[:, :n].numpy().T, r_pin.numpy(), d_pin.numpy().view(np.bool_), {})
+        ret = (o_pin[:, :n].numpy().T, r_np, d_pin.numpy().view(np.bool_), {})
         if in_place and chunks == 0:       # a caller that reuses its pinned action tensor skips all of the above next time
             self._pinned["fast"] = (actions, C.byref(io), ret)
             self._pinned["fast_io"] = io           # keep the struct alive
@@ -387,6 +447,10 @@ class VecMREnv:
     # 4 / 8 / 16 chunks: correct, but DMA reads + SM writes to the host interfere more than SM reads + SM writes do.
     host_mode = "direct"
     host_chunks = 2
+    # dtype of the HOST action / observation buffers of step_host in direct mode: None = the storage dtype;
+    # torch.float32 with float64 storage = float32 on the wire (north_star's 1e-4 tier for the transferred values, half
+    # the bytes over PCIe), state and all decisions stay float64 on the device
+    host_io_dtype = None
 
     def _host_chunks(self, n, min_chunk=1 << 16):
         """Number of env ranges for the staged host step; small batches and table noise stay in one piece."""
@@ -540,6 +604,55 @@ class VecMREnv:
 
     def close(self):
         return None
+
+
+class StepGraph:
+    """K MR_Env.step launches of a VecMREnv captured in one CUDA graph (see VecMREnv.capture_steps)."""
+
+    def __init__(self, env, action_buffers, k_steps=None):
+        bufs = list(action_buffers)
+        n = env.num_envs
+        for a in bufs:
+            if not (torch.is_tensor(a) and a.device == env.device and a.dtype is env.dtype and a.is_contiguous()
+                    and a.numel() == 2 * n):
+                raise ValueError(f"action buffers must be contiguous [{n}, 2] {env.dtype} tensors on {env.device}")
+        self.env, self.buffers = env, bufs
+        self.k_steps = int(k_steps if k_steps is not None else len(bufs))
+        self._ctr = torch.zeros(1, dtype=torch.int64, device=env.device)      # mr_noise.offset_dev
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(env.device):
+            env.step(bufs[0])                       # first-launch set-up (function attributes) must not be captured
+            torch.cuda.synchronize(env.device)
+            nz = env._noise_for(env.params.noise_var)
+            out = env._b_out if env.want_state_prime else env._b_out_lean
+            with torch.cuda.graph(self.graph):
+                stream = torch.cuda.current_stream(env.device).cuda_stream
+                nz.offset_dev = self._ctr.data_ptr()
+                try:
+                    for k in range(self.k_steps):
+                        nz.offset = k
+                        rc = env._call_step(env._b_state, n, env._dt, env._b_params, C.byref(nz), env._b_tt,
+                                            bufs[k % len(bufs)].data_ptr(), out, stream)
+                        if rc:
+                            L.check(rc, "mr_env_step (graph capture)")
+                finally:
+                    nz.offset_dev = None
+        # the simulator parameters are baked into the captured launches
+        self._baked = (env.params.a0, env.params.noise_var, env.params.is_mismatched, env.params.auto_reset)
+
+    def replay(self):
+        """Run the K captured steps; returns the views (obs, rew, done, info) after the last one."""
+        env = self.env
+        if self._baked != (env.params.a0, env.params.noise_var, env.params.is_mismatched, env.params.auto_reset):
+            raise RuntimeError("simulator parameters changed since the graph was captured: capture again")
+        with torch.cuda.device(env.device):
+            rc = env.lib.mr_counter_set(self._ctr.data_ptr(), env._step_index, env._stream())
+            if rc:
+                L.check(rc, "mr_counter_set")
+            self.graph.replay()
+        env._step_index += self.k_steps
+        env.kernel_launches += self.k_steps + 1
+        return env._views
 
 
 from .dist import shard_range  # noqa: E402,F401  (re-exported)

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(_lib.EXPORTS) == set(names)
-    assert lib.mr_abi_version() == 1
+    assert lib.mr_abi_version() == _lib.ABI_VERSION == 2
     assert lib.mr_actor_param_count() == 5 * 64 + 5 * 64 + 64 * 64 + 5 * 64 + 64 * 2 + 2
 
 
@@ -44,7 +44,7 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     from mr_rl_b200 import _lib
     prog = tmp_path / "sizes.c"
     structs = ["mr_sim_params", "mr_env_state", "mr_noise", "mr_time_table", "mr_step_out", "mr_rollout_io", "mr_gp_model",
-               "mr_host_step_io", "mr_ddpg_state", "mr_replay", "mr_ddpg_hyper"]
+               "mr_host_step_io", "mr_ddpg_state", "mr_replay", "mr_ddpg_hyper", "mr_reset_params"]
     body = "\n".join(f'printf("{s} %zu\\n", sizeof({s}));' for s in structs)
     prog.write_text(f'#include <stdio.h>\n#include <stddef.h>\n#include "{HEADER}"\nint main(void){{{body}\n'
                     'printf("off_action_high %zu\\n", offsetof(mr_sim_params, action_high));\n'
@@ -59,7 +59,7 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     py = {"mr_sim_params": _lib.SimParams, "mr_env_state": _lib.EnvState, "mr_noise": _lib.Noise, "mr_time_table": _lib.TimeTable,
           "mr_step_out": _lib.StepOut, "mr_rollout_io": _lib.RolloutIO, "mr_gp_model": _lib.GPModel,
           "mr_host_step_io": _lib.HostStepIO, "mr_ddpg_state": _lib.DDPGState, "mr_replay": _lib.Replay,
-          "mr_ddpg_hyper": _lib.DDPGHyper}
+          "mr_ddpg_hyper": _lib.DDPGHyper, "mr_reset_params": _lib.ResetParams}
     for name, cls in py.items():
         assert C.sizeof(cls) == int(out[name]), name
     assert _lib.SimParams.action_high.offset == int(out["off_action_high"])

@@ -546,7 +546,8 @@ def test_pipelined_host_step_equals_single_launch_step():
 
 @pytest.mark.parametrize("seed", range(12))
 def test_random_regimes_against_c_oracle(seed):
-    """Randomised sweep of simulator regimes (noise level, a0, model mismatch, start positions from inside the goal
+    """(n = 256 is two tiles: the single-step launches take the tiled TMA kernel with staged table rows; the scalar
+    kernel gets the same sweep in test_random_regimes_scalar_kernel.)  Randomised sweep of simulator regimes (noise level, a0, model mismatch, start positions from inside the goal
     radius to beyond the observation bounds, actions outside the action space) — single-step kernel and fused rollout
     against the plain-C oracle on the same noise streams: done flags and draw counts exact, positions 1e-9."""
     from oracle import c_oracle
@@ -582,6 +583,132 @@ def test_random_regimes_against_c_oracle(seed):
         assert np.array_equal(env._cursor[:n].cpu().numpy().astype(np.int64), ref["cursor"])
         assert rel_err(xy, ref["pos"]) < FP64_TOL
         env.check_status()
+
+
+def _random_regime(seed, n, T, sigmas=None):
+    rng = np.random.default_rng(1000 + seed)
+    scale = float(rng.choice([20.0, 150.0, 4000.0, 7000.0]))
+    sigma = float(rng.choice(sigmas if sigmas is not None else ([0.0, 0.02, 0.05] if scale < 100 else [0.0, 0.05, 0.5, 1.0])))
+    a0 = float(rng.choice([0.5, 1.0, 1.5, 4.0]))
+    mism = bool(rng.integers(0, 2))
+    init = rng.uniform(-scale, scale, (n, 2))
+    acts = np.stack([rng.uniform(-5, 30, (T, n)), rng.uniform(-7, 7, (T, n))], -1)
+    acts[rng.random((T, n)) < 0.05] = 0.0
+    return rng, scale, sigma, a0, mism, init, acts
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("path", ["scalar", "tma"])
+def test_random_regimes_table_noise_both_step_kernels(seed, path):
+    """The same sweep, single-step path only, with the kernel forced: the scalar kernel and the tiled TMA kernel (table rows
+    bulk-copied per tile, global loads where an env's cursor has left the staged rows) against the C oracle — every env,
+    done flags and draw counts exact, positions 1e-9.  n = 3 * 128 + 34: three tiles and a scalar tail whose table columns
+    are offset."""
+    from mr_rl_b200 import _lib as L
+    from oracle import c_oracle
+    n, T = 3 * 128 + 34, 40
+    rng, scale, sigma, a0, mism, init, acts = _random_regime(seed, n, T)
+    z = rng.standard_normal((n, 200 * T + 64))
+    ref = c_oracle.rollout(init, acts, sigma, a0, mism=mism, mism_at_reset=False, z=z)
+    assert ref["bad"] == 0
+    try:
+        L.set_step_path(path)
+        env = make_env(n, noise="table", noise_table=np.ascontiguousarray(z.T))
+        env.reset(init=init, noise_var=sigma, a0=a0, is_mismatched=mism)
+        a_dev = torch.as_tensor(acts, device="cuda:0")
+        xy, dn = [], []
+        for k in range(T):
+            _, _, d, _ = env.step(a_dev[k])
+            xy.append(env.last_pos.cpu().numpy().copy()); dn.append(d.cpu().numpy().copy())
+        xy, dn = np.stack(xy), np.stack(dn)
+    finally:
+        L.set_step_path("default")
+    assert np.array_equal(dn.astype(bool), ref["done"].astype(bool)), (sigma, a0, mism, scale, path)
+    assert np.array_equal(env._cursor[:n].cpu().numpy().astype(np.int64), ref["cursor"])
+    assert rel_err(xy, ref["pos"]) < FP64_TOL
+    env.check_status()
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_noise_free_tma_kernel_random_regimes_all_envs(seed, dt):
+    """The noise-free instantiations of the benchmarked TMA kernel (matched AND mismatched model) over the random
+    regimes — starts from inside the goal radius to beyond the bounds, actions outside the action space, idle steps,
+    multi-attempt first steps (h_abs starts at 1e-6 with sigma = 0) — EVERY env against the C oracle."""
+    from mr_rl_b200 import _lib as L
+    from oracle import c_oracle
+    n, T = 8 * 256, 30
+    rng, scale, _, a0, mism, init, acts = _random_regime(seed, n, T, sigmas=[0.0])
+    if dt is torch.float32:
+        init = init.astype(np.float32).astype(np.float64)
+        acts = acts.astype(np.float32).astype(np.float64)
+    ref = c_oracle.rollout(init, acts, 0.0, a0, mism=mism, mism_at_reset=False, z=None, want_attempts=True)
+    assert ref["bad"] == 0
+    try:
+        L.set_step_path("tma")
+        env = make_env(n, dtype=dt, noise="none")
+        env.reset(init=init, noise_var=0.0, a0=a0, is_mismatched=mism)
+        a_dev = torch.as_tensor(acts, device="cuda:0", dtype=dt)
+        xy, dn = [], []
+        for k in range(T):
+            _, _, d, _ = env.step(a_dev[k])
+            xy.append(env.last_pos.double().cpu().numpy().copy()); dn.append(d.cpu().numpy().copy())
+        xy, dn = np.stack(xy), np.stack(dn)
+    finally:
+        L.set_step_path("default")
+    if dt is torch.float64:
+        assert np.array_equal(dn.astype(bool), ref["done"].astype(bool)), (a0, mism, scale)
+        assert rel_err(xy, ref["pos"]) < FP64_TOL
+    else:
+        # fp32 storage: positions 1e-4; a done flag may legitimately differ only where the fp64 distance sits within
+        # fp32 rounding of a threshold, which these regimes do not produce more than a handful of times
+        assert rel_err(xy, ref["pos"]) < FP32_TOL
+        assert (dn.astype(bool) != ref["done"].astype(bool)).mean() < 1e-3
+    env.check_status()
+
+
+def test_table_noise_tma_kernel_common_regime_at_scale():
+    """The parity mode as it is benchmarked: 16 384 envs in the RL regime, every env's cursor advancing by 16 per step so
+    all draws come from the bulk-copied rows; every env against the C oracle, plus auto resets (cursors diverge by the
+    reset's 4 draws, those envs fall back to global table reads) compared with the scalar kernel bit for bit."""
+    from mr_rl_b200 import _lib as L
+    from oracle import c_oracle
+    n, T = 16384, 20
+    rng = np.random.default_rng(8)
+    init = rng.uniform(100, 120, (n, 2)).astype(np.float32).astype(np.float64)
+    acts = np.stack([rng.uniform(0, 20, (T, n)), rng.uniform(0, 2 * np.pi, (T, n))], -1)
+    z = rng.standard_normal((n, 16 * T + 8))
+    ref = c_oracle.rollout(init, acts, 1.0, 1.0, mism=False, mism_at_reset=False, z=z)
+    assert ref["bad"] == 0
+    zt = np.ascontiguousarray(z.T)
+    env = make_env(n, noise="table", noise_table=zt)
+    env.reset(init=init, noise_var=1.0, a0=1.0)
+    a_dev = torch.as_tensor(acts, device="cuda:0")
+    for k in range(T):
+        env.step(a_dev[k])
+    assert np.array_equal(env._cursor[:n].cpu().numpy().astype(np.int64), ref["cursor"])
+    assert int(env._cursor[:n].min()) == int(env._cursor[:n].max()) == 4 + 16 * T
+    assert rel_err(env._state[:, :n].t().cpu().numpy(), ref["final"]) < FP64_TOL
+    env.check_status()
+    # auto reset on (max_timesteps = 6: three resets inside the trace), tiled kernel == scalar kernel
+    outs = []
+    z2 = np.ascontiguousarray(rng.standard_normal((24 * T + 64, n)))
+    try:
+        for path in ("scalar", "tma"):
+            L.set_step_path(path)
+            e = make_env(n, noise="table", noise_table=z2, auto_reset=True, seed=5)
+            e.max_timesteps = 6
+            e.reset(init=init, noise_var=1.0, a0=1.0)
+            tr = []
+            for k in range(T):
+                o, _, d, _ = e.step(a_dev[k])
+                tr.append(torch.cat([o.flatten(), d.double(), e._cursor[:n].double()]).clone())
+            e.check_status()
+            outs.append(torch.stack(tr).cpu().numpy())
+    finally:
+        L.set_step_path("default")
+    assert np.array_equal(outs[0], outs[1])
+    assert outs[0][:, 5 * n:6 * n].sum() > 0
 
 
 def test_solver_failures_are_flagged_for_the_same_envs_as_the_oracle():
@@ -661,3 +788,128 @@ def test_reset_draws_differ_from_the_terminal_steps_draws():
     z_reset = torch.cat([after[0].flatten(), after[1].flatten()]).cpu().numpy()
     assert not np.isin(z_reset, z_step).any()                        # no value of the reset appears among the step's
     assert abs(np.corrcoef(z_step, z_reset)[0, 1]) < 0.05
+
+
+def _golden_batch_of_cases(golden_single, T):
+    names = list(SINGLE_CASES)
+    cases = [golden_single.case(nm) for nm in names]
+    n = len(cases)
+    L = max(len(c["z"]) for c in cases)
+    z = np.zeros((L, n))
+    acts = np.zeros((T, n, 2))
+    init = np.zeros((n, 2))
+    for j, c in enumerate(cases):
+        z[:len(c["z"]), j] = c["z"]
+        t = min(T, len(c["actions"]))
+        acts[:t, j] = c["actions"][:t, :2]
+        init[j] = np.asarray(c["init"], dtype=np.float64)
+    par = np.array([c["params"] for c in cases])           # sigma, a0, mism, prior flag
+    return names, cases, z, acts, init, par
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_per_env_parameters_every_env_against_its_golden(golden_single, fused):
+    """Simulator.a0 / noise_var / is_mismatched are per-instance attributes in the reference (MR_simulator.py:16-19, set per
+    reset at MR_env.py:179-183).  ONE batch whose envs carry the parameter sets of all the single-env goldens (noise-free,
+    sigma 1, mismatched from the origin with up to 29 RK attempts, stale-flag resets ...): every env must reproduce its own
+    golden from the live reference — done flags, counters and draw counts exact, positions 1e-9 — through the per-env
+    single-step kernel and through the fused rollout."""
+    T = 60
+    names, cases, z, acts, init, par = _golden_batch_of_cases(golden_single, T)
+    n = len(cases)
+    env = make_env(n, noise="table", noise_table=z, per_env_params=True)
+    # the stale flag of a previous episode (MR_env.py:181 vs :183): put it in the rows with a first reset, rewind the cursor
+    env.reset(init=init, noise_var=par[:, 0], a0=par[:, 1], is_mismatched=par[:, 3].astype(np.uint8))
+    obs0 = env.reset(init=init, noise_var=par[:, 0], a0=par[:, 1], is_mismatched=par[:, 2].astype(np.uint8), reset_cursor=True)
+    for j, c in enumerate(cases):
+        assert rel_err(obs0.cpu().numpy()[j], c["reset_obs"]) < FP64_TOL, names[j]
+        assert int(env._cursor[j]) == int(c["reset_cursor"]), names[j]
+        assert rel_err(env.state_prime.cpu().numpy()[j], c["reset_state_prime"]) < FP64_TOL, names[j]
+    assert np.array_equal(env.is_mismatched.cpu().numpy(), par[:, 2].astype(bool))
+    if fused:
+        res = env.rollout(actions=torch.as_tensor(acts, device="cuda:0"), record=True, record_done=True)
+        pos = res["xy"].cpu().numpy().transpose(0, 2, 1)
+        done = res["done_traj"].cpu().numpy()
+        cursor_end = env._cursor[:n].cpu().numpy()
+    else:
+        r = step_through(env, acts)
+        pos, done, cursor_end = r["pos"], r["done"], r["cursor"][-1]
+    for j, c in enumerate(cases):
+        t = min(T, len(c["actions"]))
+        assert np.array_equal(done[:t, j], c["done"][:t]), names[j]
+        assert rel_err(pos[:t, j], c["pos"][:t]) < FP64_TOL, names[j]
+        if t == T:
+            assert int(cursor_end[j]) == int(c["cursor"][T - 1]), names[j]
+    env.check_status()
+
+
+def test_masked_reset_can_change_per_env_parameters():
+    """With per-env rows a masked reset may give the reset envs a new model (the launch-scalar env refuses that)."""
+    n = 64
+    rng = np.random.default_rng(3)
+    init = rng.uniform(100, 120, (n, 2))
+    env = make_env(n, noise="none", per_env_params=True)
+    env.reset(init=init, noise_var=0.0, a0=1.0)
+    mask = np.zeros(n, np.uint8); mask[::2] = 1
+    env.reset(init=init, noise_var=0.0, a0=2.0, is_mismatched=True, mask=mask)
+    assert np.array_equal(env.a0.cpu().numpy(), np.where(mask, 2.0, 1.0))
+    assert np.array_equal(env.is_mismatched.cpu().numpy(), mask.astype(bool))
+    a = np.tile(np.array([[5.0, 0.3]]), (n, 1))
+    acts = np.repeat(a[None], 5, 0)
+    r = step_through(env, acts)
+    for j in (0, 1, 2, 3):
+        ref = mo.rollout(acts[:, j], init[j], 0.0, 2.0 if mask[j] else 1.0, bool(mask[j]), None)
+        assert rel_err(r["pos"][:, j], ref["pos"]) < FP64_TOL
+    plain = make_env(n, noise="none")
+    plain.reset(init=init, noise_var=0.0, a0=1.0)
+    with pytest.raises(ValueError):
+        plain.reset(init=init, noise_var=0.0, a0=2.0, mask=mask)
+
+
+@pytest.mark.parametrize("n", [8192, 8192 + 200])
+def test_cuda_graph_of_k_steps_equals_k_step_calls(n):
+    """K single-step launches captured in a CUDA graph (the Philox env-step index comes from a device counter that every
+    replay advances) == the same K steps launched one by one, bit for bit, over several replays with auto resets."""
+    K, reps = 12, 3
+    acts = torch.rand(4, n, 2, dtype=torch.float64, device="cuda:0")
+    acts[..., 0] *= 20; acts[..., 1] *= 2 * np.pi
+    bufs = [acts[k] for k in range(4)]
+    e1 = make_env(n, noise="philox", seed=9, auto_reset=True); e1.max_timesteps = 10
+    e2 = make_env(n, noise="philox", seed=9, auto_reset=True); e2.max_timesteps = 10
+    e1.reset(init=None, noise_var=1.0, a0=1.0); e2.reset(init=None, noise_var=1.0, a0=1.0)
+    g = e1.capture_steps(bufs, K)                           # captures after one real step
+    e2.step(bufs[0])
+    for r in range(reps):
+        o1, _, d1, _ = g.replay()
+        for k in range(K):
+            o2, _, d2, _ = e2.step(bufs[k % 4])
+        assert torch.equal(o1, o2) and torch.equal(d1, d2), r
+        assert torch.equal(e1._state, e2._state) and torch.equal(e1.counter, e2.counter)
+    assert e1._step_index == e2._step_index
+    e1.check_status()
+
+
+def test_host_step_float32_wire_format():
+    """step_host with float32 host buffers over fp64 device state (north_star's 1e-4 tier for the transferred values):
+    actions are widened exactly, the state evolves in fp64 (equal to the fp64 path fed the same float32-valued actions),
+    observations arrive rounded to float32, the constant reward is not transferred at all."""
+    n = 4096 + 70
+    rng = np.random.default_rng(0)
+    init = rng.uniform(100, 120, (n, 2))
+    a32 = np.stack([rng.uniform(0, 20, n), rng.uniform(0, 6.28, n)], -1).astype(np.float32)
+    e64 = make_env(n, noise="philox", seed=2); e32 = make_env(n, noise="philox", seed=2)
+    e64.reset(init=init, noise_var=1.0, a0=1.0); e32.reset(init=init, noise_var=1.0, a0=1.0)
+    e32.host_io_dtype = torch.float32
+    for k in range(4):
+        o64, r64, d64, _ = e64.step_host(a32.astype(np.float64))
+        o32, r32, d32, _ = e32.step_host(a32)
+        assert o32.dtype == np.float32 and r32.dtype == np.float32
+        assert np.array_equal(d64, d32)
+        assert np.all(r32 == 10.0) and np.all(r64 == 10.0)
+        assert np.array_equal(o32, o64.astype(np.float32))
+        assert torch.equal(e64._state, e32._state)
+    pin = torch.from_numpy(a32).pin_memory()                # the cached fast path with a pinned float32 tensor
+    for k in range(3):
+        o64, _, d64, _ = e64.step_host(a32.astype(np.float64))
+        o32, _, d32, _ = e32.step_host(pin)
+        assert np.array_equal(o32, o64.astype(np.float32)) and np.array_equal(d64, d32)
