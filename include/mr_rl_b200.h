@@ -208,6 +208,20 @@ typedef struct mr_rollout_io {
     void* traj_state_prime;  /* optional [K][2][n] */
     uint8_t* traj_done;      /* optional [K][n] */
     double* stats;           /* optional [MR_STATS_LEN] device accumulators (atomically added) */
+    /* Per-episode recording on the device — what MRExperiment.new_iter / new_transition log (MR_data.py:27-57,
+     * MR_env.py:94-95,190-198) — all optional, storage dtype unless noted: */
+    void* traj_actions;      /* [K][n][2] the action applied at step k (also for the in-kernel policies) */
+    void* traj_rew;          /* [K][n] reward of step k */
+    void* traj_reset_xy;     /* [K][2][n] written where traj_done[k][i] != 0 and auto_reset is on: the start position of
+                                the episode that follows (row 0 of the next iteration's log) */
+    int32_t* traj_episode;   /* [K][n] ordinal of the episode of env i the transition belongs to */
+    int32_t* traj_step;      /* [K][n] step inside that episode (MR_Env.counter after the step) */
+    int32_t* episode_counter;/* [n] in/out: episodes env i has finished so far (carries the ordinals across launches) */
+    const void* reset_init;  /* [reset_init_len][n][2] start positions of the auto resets: the e-th finished episode of
+                                env i is followed by reset_init[(e - 1) % reset_init_len][i]; NULL: sample init_space
+                                (gym Box.sample, MR_env.py:172-173) */
+    int32_t reset_init_len;
+    int32_t reserved;
 } mr_rollout_io;
 
 enum { MR_STAT_EPISODES = 0, MR_STAT_SUM_LENGTH = 1, MR_STAT_SUM_REWARD = 2, MR_STAT_GOAL = 3,

@@ -20,7 +20,7 @@ from .gpr import DeviceGPR  # noqa: F401
 from .learning_module import LearningModule  # noqa: F401
 from .learning_module_2d import LearningModule2D  # noqa: F401
 from .mr_env import MR_Env, Simulator  # noqa: F401
-from .recording import MRExperiment, experiment_dict, load_experiment, save_experiment  # noqa: F401
+from .recording import MRExperiment, experiment_dict, experiment_from_rollout, load_experiment, save_experiment  # noqa: F401
 from .spaces import Box  # noqa: F401
 from .utils import run_sim  # noqa: F401
 from .vec_env import VecMREnv, shard_range  # noqa: F401

@@ -60,7 +60,9 @@ class StepOut(C.Structure):
 class RolloutIO(C.Structure):
     _fields_ = [("action_source", C.c_int32), ("k_steps", C.c_int32), ("actions", C.c_void_p), ("actor", C.c_void_p),
                 ("traj_xy", C.c_void_p), ("traj_state_prime", C.c_void_p), ("traj_done", C.c_void_p),
-                ("stats", C.c_void_p)]
+                ("stats", C.c_void_p), ("traj_actions", C.c_void_p), ("traj_rew", C.c_void_p), ("traj_reset_xy", C.c_void_p),
+                ("traj_episode", C.c_void_p), ("traj_step", C.c_void_p), ("episode_counter", C.c_void_p),
+                ("reset_init", C.c_void_p), ("reset_init_len", C.c_int32), ("reserved", C.c_int32)]
 
 
 class GPModel(C.Structure):

@@ -158,6 +158,9 @@ static int do_rollout(const mr_env_state& st, int64_t n, const Params& p, const 
     RolloutView<T> rv;
     rv.actions = (const T*)io.actions; rv.actor = io.actor; rv.traj_xy = (T*)io.traj_xy;
     rv.traj_sp = (T*)io.traj_state_prime; rv.traj_done = io.traj_done; rv.stats = io.stats;
+    rv.traj_actions = (T*)io.traj_actions; rv.traj_rew = (T*)io.traj_rew; rv.traj_reset_xy = (T*)io.traj_reset_xy;
+    rv.traj_episode = io.traj_episode; rv.traj_step = io.traj_step; rv.episode_counter = io.episode_counter;
+    rv.reset_init = (const T*)io.reset_init; rv.reset_init_len = io.reset_init_len;
     rv.k_steps = io.k_steps; rv.action_source = io.action_source;
     const StateView<T> sv = state_view<T>(st);
     const OutView<T> ov = out_view<T>(out, n);
@@ -403,6 +406,7 @@ int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_si
     if (p->auto_reset && nz == nullptr)
         return mr::fail(MR_ERR_ARG, "mr_env_rollout: auto_reset needs mr_noise (seed) for the init sampler");
     if (out && out->out_f32) return mr::fail(MR_ERR_UNSUPPORTED, "mr_env_rollout: float32 output rows are a step option");
+    if (io->reset_init && io->reset_init_len <= 0) return mr::fail(MR_ERR_ARG, "mr_env_rollout: reset_init needs reset_init_len > 0");
     if (p->action_f32 && dtype == MR_F64 && io->action_source == MR_ACTIONS_TENSOR)
         return mr::fail(MR_ERR_UNSUPPORTED, "mr_env_rollout: float32 actions with fp64 storage are a step option");
     const mr::Params pp = mr::to_params(*p, nz);

@@ -52,7 +52,7 @@ __device__ __forceinline__ void put_out(T* row, bool f32, int64_t i, double v) {
     row[i] = (T)v;
 }
 template <class T>
-__device__ __forceinline__ T* out_row(T* base, bool f32, int64_t elems) {   // base + elems in units of the row type
+__host__ __device__ __forceinline__ T* out_row(T* base, bool f32, int64_t elems) {   // base + elems in units of the row type
     if constexpr (sizeof(T) == 8) { if (f32) return reinterpret_cast<T*>(reinterpret_cast<float*>(base) + elems); }
     return base + elems;
 }
@@ -157,18 +157,31 @@ __device__ __forceinline__ typename NoiseOf<MODE>::type make_noise(const NoiseVi
 
 // gym-style auto reset after a terminal step: the env restarts from a Philox-sampled
 // init_space position (float32-rounded like gym.spaces.Box.sample, MR_env.py:172-173).
-template <int MODE, bool MISM>
-__device__ __forceinline__ void auto_reset_env(Env& e, const NoiseView& nv, int64_t n, int64_t i, int32_t& cur,
-                                               uint64_t step, const Params& p, int& overflow) {
+__device__ __forceinline__ void sample_init(const NoiseView& nv, int64_t i, uint64_t step, const Params& p, double& x0, double& y0) {
     double u[4];
     philox_uniform4(p, nv.env_base + (uint64_t)i, step, kPurposeInit, u);
-    const double x0 = (double)(float)(p.init_lo[0] + (p.init_hi[0] - p.init_lo[0]) * u[0]);
-    const double y0 = (double)(float)(p.init_lo[1] + (p.init_hi[1] - p.init_lo[1]) * u[1]);
+    x0 = (double)(float)(p.init_lo[0] + (p.init_hi[0] - p.init_lo[0]) * u[0]);
+    y0 = (double)(float)(p.init_lo[1] + (p.init_hi[1] - p.init_lo[1]) * u[1]);
+}
+
+// MR_Env.reset(init = (x0, y0)) in the middle of a kernel: new integrator (two RHS evaluations with action 0 and
+// fresh draws), counter 0, sticky status kept.
+template <int MODE, bool MISM>
+__device__ __forceinline__ void auto_reset_at(Env& e, double x0, double y0, const NoiseView& nv, int64_t n, int64_t i,
+                                              int32_t& cur, uint64_t step, const Params& p, int& overflow) {
     const int keep = e.status;
     auto nzr = make_noise<MODE>(nv, n, i, cur, step, kPurposeResetNoise);
     env_reset<MISM>(e, x0, y0, p.dt, p, nzr);
     e.status |= keep;
     if constexpr (MODE == MR_NOISE_TABLE) { cur = nzr.cursor; overflow |= nzr.overflow; }
+}
+
+template <int MODE, bool MISM>
+__device__ __forceinline__ void auto_reset_env(Env& e, const NoiseView& nv, int64_t n, int64_t i, int32_t& cur,
+                                               uint64_t step, const Params& p, int& overflow) {
+    double x0, y0;
+    sample_init(nv, i, step, p, x0, y0);
+    auto_reset_at<MODE, MISM>(e, x0, y0, nv, n, i, cur, step, p, overflow);
 }
 
 
@@ -189,6 +202,15 @@ struct RolloutView {
     T* traj_sp;                // [K][2][n]
     uint8_t* traj_done;        // [K][n]
     double* stats;             // [MR_STATS_LEN]
+    // per-episode recording (MR_data.py:27-57): what new_iter / new_transition log, keyed on the device
+    T* traj_actions;           // [K][n][2] the action applied at step k (also for in-kernel policies)
+    T* traj_rew;               // [K][n]
+    T* traj_reset_xy;          // [K][2][n] start position of the episode that begins after a terminal step k (auto reset)
+    int32_t* traj_episode;     // [K][n] episode ordinal of env i the transition belongs to
+    int32_t* traj_step;        // [K][n] step inside that episode (MR_Env.counter after the step)
+    int32_t* episode_counter;  // [n] in/out: episodes env i has finished so far
+    const T* reset_init;       // [reset_init_len][n][2] start positions for the auto resets (NULL: sample init_space)
+    int reset_init_len;
     int k_steps;
     int action_source;
 };

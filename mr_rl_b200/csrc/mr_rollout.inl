@@ -54,6 +54,8 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         e.h = decode_h<T>(st.h[i], (t_in + p.dt) - t_in);
         if constexpr (MODE == MR_NOISE_TABLE) cur = st.cursor[i];
     }
+    int32_t ep = 0;                                  // episodes this env has finished (recording key)
+    if (live && io.episode_counter) ep = io.episode_counter[i];
     Observation o = observe(e, p);
     // an env that is stepped past its terminal step (run_sim does, utils.py:46-54; the reference never resets by
     // itself) stays `done` on every later step: only the transition counts as an episode end in the statistics.
@@ -107,6 +109,10 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
                 io.traj_sp[((int64_t)k * 2 + 1) * n + i] = (T)e.spy;
             }
             if (io.traj_done) io.traj_done[(int64_t)k * n + i] = o.done ? 1 : 0;
+            if (io.traj_actions) { io.traj_actions[((int64_t)k * n + i) * 2] = (T)f_t; io.traj_actions[((int64_t)k * n + i) * 2 + 1] = (T)al; }
+            if (io.traj_rew) io.traj_rew[(int64_t)k * n + i] = (T)o.rew;
+            if (io.traj_episode) io.traj_episode[(int64_t)k * n + i] = ep;
+            if (io.traj_step) io.traj_step[(int64_t)k * n + i] = e.counter;
             acc[MR_STAT_ENV_STEPS] += 1.0;
             acc[MR_STAT_SUM_REWARD] += o.rew;
         }
@@ -118,16 +124,28 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
                 else if (o.why == 2) acc[MR_STAT_OUT_OF_BOUNDS] += 1.0;
                 else acc[MR_STAT_TIMEOUT] += 1.0;
             }
+            if (!was_done) ++ep;
             if (p.auto_reset) {
                 int ov = 0;
-                if constexpr (PERENV) {
-                    if (mism_i) auto_reset_env<MODE, true>(e, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
-                    else auto_reset_env<MODE, false>(e, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
+                double x0, y0;
+                if (io.reset_init) {                        // the caller's start positions, one per finished episode
+                    const T* r = io.reset_init + ((int64_t)((ep - 1) % io.reset_init_len) * n + (live ? i : 0)) * 2;
+                    x0 = (double)r[0]; y0 = (double)r[1];
                 } else {
-                    auto_reset_env<MODE, MISM>(e, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
+                    sample_init(nv, live ? i : 0, off + (uint64_t)k, p, x0, y0);
+                }
+                if constexpr (PERENV) {
+                    if (mism_i) auto_reset_at<MODE, true>(e, x0, y0, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
+                    else auto_reset_at<MODE, false>(e, x0, y0, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
+                } else {
+                    auto_reset_at<MODE, MISM>(e, x0, y0, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
                 }
                 overflow |= ov != 0;
                 o.d = sqrt(e.x * e.x + e.y * e.y);   // the policy's next input is the new episode's first observation (env.reset())
+                if (live && io.traj_reset_xy) {
+                    io.traj_reset_xy[((int64_t)k * 2) * n + i] = (T)e.x;
+                    io.traj_reset_xy[((int64_t)k * 2 + 1) * n + i] = (T)e.y;
+                }
             }
         }
         was_done = o.done && !p.auto_reset;
@@ -143,6 +161,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         st.counter[i] = e.counter;
         if constexpr (MODE == MR_NOISE_TABLE) st.cursor[i] = cur;
         if (e.status) st.status[i] |= (uint8_t)e.status;
+        if (io.episode_counter) io.episode_counter[i] = ep;
         // outputs of the LAST step (after an auto reset: the first observation of the new episode)
         if (out.obs) {
             out.obs[i] = (T)e.x; out.obs[out.stride + i] = (T)e.y;

@@ -47,6 +47,48 @@ def experiment_dict(init_xy, actions, xy, done=None, reward=10, info=None, until
     return exp
 
 
+def experiment_from_rollout(res, info=None):
+    """The reference's MRExperiment dict from a device-recorded rollout (``VecMREnv.rollout(..., record_episodes=True)``),
+    episodes split at the terminal steps the kernel flagged — any number of episodes per env, auto resets included.
+    Episodes ("iterations") are numbered env-major: all episodes of env 0 in time order, then env 1, ...  Row 0 of an
+    episode is what ``new_iter`` logs at reset (start state, its observation, a zero action, reward [0],
+    MR_env.py:190-198), the following rows what ``new_transition`` logs per step (MR_env.py:94-95).
+    Vectorised: the per-row arrays are assembled with numpy index arithmetic over all N x K transitions at once and cut
+    into per-episode views with one ``np.split`` (no Python loop over envs or steps)."""
+    xy = _to_np(res["xy"]).astype(np.float64)                       # [K, 2, N] position after step k
+    K, _, N = xy.shape
+    done = _to_np(res["done_traj"]).astype(bool)                    # [K, N]
+    acts = _to_np(res["actions_traj"]).astype(np.float64)           # [K, N, 2]
+    rew = _to_np(res["rew_traj"]).astype(np.float64)                # [K, N]
+    start = _to_np(res["start_xy"]).astype(np.float64)              # [N, 2]
+    reset_xy = _to_np(res["reset_xy"]).astype(np.float64)           # [K, 2, N]
+    # slot layout per env: for every step k an optional "new_iter" row (present when an episode starts at k) followed
+    # by the transition row -> [N, K, 2 slots]; flattening env-major puts every episode's rows in order
+    starts = np.zeros((K, N), bool)
+    starts[0] = True
+    starts[1:] = done[:-1]                                          # an episode starts after every terminal step
+    begin_xy = np.empty((K, 2, N))
+    begin_xy[0] = start.T
+    begin_xy[1:] = reset_xy[:-1]                                    # only read where starts is set
+    pos = np.stack([begin_xy, xy], axis=1)                          # [K, slot, 2, N]
+    pos = pos.transpose(3, 0, 1, 2).reshape(N * K * 2, 2)           # env-major rows
+    act = np.stack([np.zeros_like(acts), acts], axis=1).transpose(2, 0, 1, 3).reshape(N * K * 2, 2)
+    rw = np.stack([np.zeros_like(rew), rew], axis=1).transpose(2, 0, 1).reshape(N * K * 2, 1)
+    present = np.stack([starts, np.ones_like(starts)], axis=1).transpose(2, 0, 1).reshape(N * K * 2)
+    is_start = np.stack([starts, np.zeros_like(starts)], axis=1).transpose(2, 0, 1).reshape(N * K * 2)
+    pos, act, rw, is_start = pos[present], act[present], rw[present], is_start[present]
+    obs = np.column_stack([pos, np.zeros((len(pos), 2)), np.hypot(pos[:, 0], pos[:, 1])])     # MR_env.py:100-116, goal (0, 0)
+    cuts = np.flatnonzero(is_start)
+    n_ep = len(cuts)
+    lengths = np.diff(np.append(cuts, len(pos))) - 1
+    ids = range(n_ep)
+    return {"iterations": n_ep - 1,
+            "states": dict(zip(ids, np.split(pos, cuts[1:]))), "observations": dict(zip(ids, np.split(obs, cuts[1:]))),
+            "actions": dict(zip(ids, np.split(act, cuts[1:]))), "rewards": dict(zip(ids, np.split(rw, cuts[1:]))),
+            "steps": dict(zip(ids, lengths.tolist())),
+            "info": info, "viewer": None, "scream": None, "obs_states_str": {}, "time_step": 10}
+
+
 def save_experiment(exp, path):
     """MRExperiment.save_experiment's pickle (protocol 2, MR_data.py:67-75) at an explicit path."""
     with open(path, "wb") as f:

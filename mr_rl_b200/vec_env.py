@@ -474,18 +474,26 @@ class VecMREnv:
 
     # ---- fused K-step rollout: utils.run_sim (utils.py:43-61) / the DDPG acting loop --------------
     def rollout(self, actions=None, k_steps=None, policy=None, record=False, record_state_prime=False,
-                record_done=False, accumulate_stats=True):
+                record_done=False, accumulate_stats=True, record_episodes=False, reset_init=None):
         """K env steps in ONE launch with the state held in registers.
 
         actions : [K, N, 2] per-env actions, or [K, 2] / [K, >=2] one action row for every env
                   (what utils.run_sim does), or None with ``policy``:
         policy  : "random" -> U[0,20) x U[0,2pi) generated in-kernel (Philox);
                   a packed float32 actor tensor (see actor.pack_actor) -> DDPG actor in the loop.
+        record_episodes : per-episode logging on the device (what MRExperiment.new_iter / new_transition record,
+                  MR_data.py:27-57): adds ``actions_traj`` [K,N,2], ``rew_traj`` [K,N], ``reset_xy`` [K,2,N] (start of the
+                  episode that follows a terminal step, with auto_reset), ``episode`` / ``step`` [K,N] int32 keys and
+                  ``start_xy`` [N,2] (positions before the first step); ``recording.experiment_from_rollout`` turns them into
+                  the reference's pickle layout.  Episode ordinals continue across launches (``self._episode_counter``).
+        reset_init : [E, N, 2] start positions for the auto resets (episode e of env i restarts at reset_init[(e-1) % E, i])
+                  instead of sampling init_space.
         Returns dict(obs, rew, done[, xy [K,2,N], state_prime [K,2,N], done_traj [K,N]]).
         """
         if torch.cuda.current_device() != self._dev_index:
             with torch.cuda.device(self.device):
-                return self.rollout(actions, k_steps, policy, record, record_state_prime, record_done, accumulate_stats)
+                return self.rollout(actions, k_steps, policy, record, record_state_prime, record_done, accumulate_stats,
+                                    record_episodes, reset_init)
         n = self.num_envs
         io = L.RolloutIO()
         keep = []
@@ -518,6 +526,29 @@ class VecMREnv:
             raise ValueError("give actions or policy")
         io.k_steps = k
         res = {}
+        if record_episodes:
+            record = record_done = True
+            res["start_xy"] = self.last_pos.clone()
+            res["actions_traj"] = torch.empty(k, n, 2, dtype=self.dtype, device=self.device)
+            res["rew_traj"] = torch.empty(k, n, dtype=self.dtype, device=self.device)
+            res["reset_xy"] = torch.zeros(k, 2, n, dtype=self.dtype, device=self.device)
+            res["episode"] = torch.empty(k, n, dtype=torch.int32, device=self.device)
+            res["step"] = torch.empty(k, n, dtype=torch.int32, device=self.device)
+            if getattr(self, "_episode_counter", None) is None:
+                self._episode_counter = torch.zeros(n, dtype=torch.int32, device=self.device)
+            io.traj_actions, io.traj_rew = res["actions_traj"].data_ptr(), res["rew_traj"].data_ptr()
+            io.traj_reset_xy = res["reset_xy"].data_ptr()
+            io.traj_episode, io.traj_step = res["episode"].data_ptr(), res["step"].data_ptr()
+            io.episode_counter = self._episode_counter.data_ptr()
+        if reset_init is not None:
+            ri = torch.as_tensor(reset_init).to(device=self.device, dtype=self.dtype).contiguous()
+            if ri.dim() != 3 or ri.shape[1] != n or ri.shape[2] != 2:
+                raise ValueError(f"reset_init must be [E, {n}, 2]")
+            if getattr(self, "_episode_counter", None) is None:
+                self._episode_counter = torch.zeros(n, dtype=torch.int32, device=self.device)
+            io.episode_counter = self._episode_counter.data_ptr()
+            io.reset_init, io.reset_init_len = ri.data_ptr(), ri.shape[0]
+            keep.append(ri)
         if record:
             res["xy"] = torch.empty(k, 2, n, dtype=self.dtype, device=self.device)
             io.traj_xy = res["xy"].data_ptr()

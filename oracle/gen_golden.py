@@ -275,8 +275,66 @@ def gen_ddpg_host():
     print("ddpg_host: OU last", xs[-1], "kept", kept, "batch", r_b - 10.0)
 
 
+def gen_recording(n_env=3, K=60, max_steps=12):
+    """The reference's own transition logger (MR_data.MRExperiment) attached to the live MR_Env (MR_env.py:94-95,
+    190-198) while a caller loop in the style of RL/MR_ddpg.py:268-311 resets on `done`: several episodes per env
+    (time-outs at a shortened max_timesteps, one env that starts next to the goal).  Stored per env: the logger's
+    per-episode arrays concatenated, the episode lengths, and every input (start positions per episode, actions,
+    noise stream) so the device path can be fed the same run."""
+    import contextlib
+    import importlib
+    import io
+    import tempfile
+    mods = lr.load()
+    MRExperiment = importlib.import_module("MR_data").MRExperiment
+    rng = np.random.default_rng(17)
+    acts = np.stack([rng.uniform(0, 20, (K, n_env)), rng.uniform(0, 2 * np.pi, (K, n_env))], -1)
+    E = K                                                     # more start positions than episodes can occur
+    inits = rng.uniform(100, 120, (E, n_env, 2)).astype(np.float32).astype(np.float64)
+    inits[1, 2] = [31.0, 5.0]                                 # env 2's second episode starts next to the goal radius
+    acts[:, 2, 0] = 20.0; acts[:, 2, 1] = np.pi               # ... and drives towards it (x decreasing)
+    zlen = 40 * K
+    z = rng.standard_normal((zlen, n_env))
+    out = {"actions": acts, "inits": inits, "z": z, "max_steps": max_steps, "versions": versions()}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "_experiments"))
+        os.chdir(tmp)
+        try:
+            for j in range(n_env):
+                env = lr.new_env()
+                env.max_timesteps = max_steps
+                env.MR_data = MRExperiment()
+                env.name_experiment = "golden"
+                with lr.patched_noise(z[:, j]) as ns, contextlib.redirect_stdout(io.StringIO()):
+                    ep = 0
+                    # first episode starts at inits[-1] (the device run's explicit reset); later ones at inits[e - 1]
+                    env.reset(init=inits[E - 1, j].copy(), noise_var=1, a0=1)
+                    for k in range(K):
+                        _, _, done, _ = env.step(acts[k, j])
+                        if done and k < K - 1:
+                            ep += 1
+                            env.reset(init=inits[ep - 1, j].copy(), noise_var=1, a0=1)
+                    out[f"env{j}/cursor"] = ns.cursor
+                d = env.MR_data.__dict__
+                n_ep = d["iterations"] + 1
+                out[f"env{j}/steps"] = np.array([d["steps"][e] for e in range(n_ep)])
+                for key in ("states", "observations", "actions", "rewards"):
+                    out[f"env{j}/{key}"] = np.concatenate([np.asarray(d[key][e], dtype=np.float64).reshape(d["steps"][e] + 1, -1)
+                                                           for e in range(n_ep)])
+                print(f"recording: env {j}: {n_ep} episodes, lengths {out[f'env{j}/steps'].tolist()}, draws {ns.cursor}")
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "recording.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    import sys
+    if len(sys.argv) > 1:                                     # python -m oracle.gen_golden recording [...]
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        raise SystemExit(0)
     gen_single()
     gen_batch()
     gen_gp()
@@ -284,3 +342,4 @@ if __name__ == "__main__":
     gen_learn_fit()
     gen_learn_2d()
     gen_ddpg_host()
+    gen_recording()

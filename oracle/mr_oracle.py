@@ -206,10 +206,12 @@ def convert_state(x, y):
     return (x, y, 0.0, 0.0, math.sqrt(x * x + y * y))
 
 
-def is_done(obs, counter):
-    """MR_Env.end, MR_env.py:136-152 with a bounds-only Box.contains (NaN -> not contained)."""
+def is_done(obs, counter, max_steps=None):
+    """MR_Env.end, MR_env.py:136-152 with a bounds-only Box.contains (NaN -> not contained).
+    max_steps: MR_Env.max_timesteps when a caller changed the attribute (default 50, MR_env.py:62)."""
     inside = all(OBS_LOW[i] <= obs[i] <= OBS_HIGH[i] for i in range(5))
-    return (not inside or counter > MAX_TIMESTEPS) or (obs[4] < MIN_DIST2GOAL)
+    limit = MAX_TIMESTEPS if max_steps is None else max_steps
+    return (not inside or counter > limit) or (obs[4] < MIN_DIST2GOAL)
 
 
 def shaped_reward(obs, counter):
@@ -232,12 +234,12 @@ def env_reset(s: SimState, init, noise_var=1, a0=1, is_mismatched=False):
     return convert_state(s.x, s.y)
 
 
-def env_step(s: SimState, act):
+def env_step(s: SimState, act, max_steps=None):
     """MR_Env.step, MR_env.py:70-98."""
     s.counter += 1
     sim_step(s, act)
     obs = convert_state(s.x, s.y)
-    return obs, 10, is_done(obs, s.counter), {}
+    return obs, 10, is_done(obs, s.counter, max_steps), {}
 
 
 def rollout(actions, init, noise_var, a0, is_mismatched, z, mism_before_reset=False):

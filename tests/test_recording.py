@@ -109,3 +109,87 @@ def test_mr_env_facade_logging_hook(tmp_path, monkeypatch):
         env.step(np.array([10.0, 0.5]))
     d = env.MR_data
     assert d.iterations == 0 and d.steps[0] == 5 and d.observations[0].shape == (6, 5) and d.actions[0].shape == (6, 2)
+
+
+def _golden_recording():
+    import os
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "recording.npz"))
+
+
+def _check_against_reference_logger(exp, g, n_env):
+    """exp: dict in the MRExperiment layout with env-major episode numbering; g: the golden of the reference's own logger."""
+    it = 0
+    for j in range(n_env):
+        steps = g[f"env{j}/steps"]
+        offs = np.concatenate([[0], np.cumsum(steps + 1)])
+        for e, m in enumerate(steps):
+            assert exp["steps"][it] == int(m), (j, e)
+            for key in ("states", "observations", "actions", "rewards"):
+                ref = g[f"env{j}/{key}"][offs[e]:offs[e + 1]]
+                got = np.asarray(exp[key][it], dtype=np.float64)
+                assert got.shape == ref.shape, (key, j, e, got.shape, ref.shape)
+                assert np.allclose(got, ref, rtol=1e-9, atol=1e-12), (key, j, e)
+            it += 1
+    assert exp["iterations"] == it - 1
+
+
+def test_vectorised_episode_flush_reproduces_the_reference_logger_on_oracle_data():
+    """experiment_from_rollout (numpy index arithmetic, no loop over envs) fed with the per-step arrays the rollout kernel
+    records — produced here by the scalar oracle with the same reset-on-done loop — must give exactly what the reference's
+    MRExperiment logged in the live run (golden recording.npz: several episodes per env, a goal episode)."""
+    from mr_rl_b200.recording import experiment_from_rollout
+    g = _golden_recording()
+    acts, inits, z, max_steps = g["actions"], g["inits"], g["z"], int(g["max_steps"])
+    K, n_env = acts.shape[:2]
+    E = inits.shape[0]
+    res = {k: np.zeros(s) for k, s in (("xy", (K, 2, n_env)), ("done_traj", (K, n_env)), ("actions_traj", (K, n_env, 2)),
+                                       ("rew_traj", (K, n_env)), ("reset_xy", (K, 2, n_env)), ("start_xy", (n_env, 2)))}
+    for j in range(n_env):
+        s = mo.SimState(noise=mo.NoiseCursor(z[:, j]))
+        mo.env_reset(s, inits[E - 1, j], 1.0, 1.0, False)
+        res["start_xy"][j] = inits[E - 1, j]
+        ep = 0
+        for k in range(K):
+            obs, rew, done = mo.env_step(s, acts[k, j], max_steps=max_steps)[:3]
+            res["xy"][k, :, j] = obs[:2]; res["done_traj"][k, j] = done; res["rew_traj"][k, j] = rew
+            res["actions_traj"][k, j] = acts[k, j]
+            if done and k < K - 1:
+                ep += 1
+                mo.env_reset(s, inits[ep - 1, j], 1.0, 1.0, False)
+                res["reset_xy"][k, :, j] = inits[ep - 1, j]
+        assert s.noise.cursor == int(g[f"env{j}/cursor"])
+    _check_against_reference_logger(experiment_from_rollout(res), g, n_env)
+
+
+@pytest.mark.gpu
+def test_device_recorded_episodes_equal_the_reference_logger(tmp_path):
+    """The same run on the device: ONE fused rollout launch with auto reset (start positions from the golden's list,
+    table noise), per-episode keys written by the kernel, flushed to the MRExperiment layout — compared with what the
+    reference's logger recorded in the live run, and round-tripped through the pickle."""
+    import torch
+
+    from mr_rl_b200 import VecMREnv, experiment_from_rollout
+    g = _golden_recording()
+    acts, inits, z, max_steps = g["actions"], g["inits"], g["z"], int(g["max_steps"])
+    K, n_env = acts.shape[:2]
+    E = inits.shape[0]
+    env = VecMREnv(n_env, device="cuda:0", noise="table", noise_table=z, auto_reset=True)
+    env.max_timesteps = max_steps
+    env.reset(init=inits[E - 1], noise_var=1.0, a0=1.0)
+    res = env.rollout(actions=torch.as_tensor(acts, device="cuda:0"), record_episodes=True, reset_init=inits)
+    env.check_status()
+    for j in range(n_env):
+        assert int(env._cursor[j]) == int(g[f"env{j}/cursor"])
+    exp = experiment_from_rollout(res)
+    _check_against_reference_logger(exp, g, n_env)
+    # the kernel's own keys agree with the split
+    ep, st, dn = res["episode"].cpu().numpy(), res["step"].cpu().numpy(), res["done_traj"].cpu().numpy().astype(bool)
+    for j in range(n_env):
+        steps = g[f"env{j}/steps"]
+        assert np.array_equal(ep[:, j], np.repeat(np.arange(len(steps)), steps))
+        assert np.array_equal(st[:, j], np.concatenate([np.arange(1, m + 1) for m in steps]))
+    assert np.array_equal(env._episode_counter.cpu().numpy(), dn.sum(0))
+    save_experiment(exp, tmp_path / "rec")
+    back = load_experiment(tmp_path / "rec")
+    assert back["iterations"] == exp["iterations"] and np.array_equal(back["states"][2], exp["states"][2])
