@@ -177,6 +177,11 @@ void mr_default_params(mr_sim_params* p);
  * (tma | vec | scalar | ws).  Process-wide, not thread-safe against concurrent launches. */
 int mr_set_step_path(int32_t path);
 
+/* The same for the actor evaluated inside mr_env_rollout (MR_ACTIONS_ACTOR): 0 = default (both dense layers on the
+ * tensor cores, 3xFP16 passes, four CTAs per SM), 1 = CUDA-core MLP, 2 = hidden layer on the tensor cores with 3xTF32
+ * passes (fp32 operand range).  Initial value: environment variable MR_ACTOR_PATH (simt | tf32).  Returns the previous one. */
+int mr_set_actor_path(int32_t path);
+
 /* Fill t[0..len) on the HOST with the accumulated step times. */
 void mr_fill_time_table_host(double* t_host, int32_t len, double time_span);
 

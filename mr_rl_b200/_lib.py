@@ -98,7 +98,7 @@ EXPORTS = ("mr_abi_version", "mr_last_error", "mr_default_params", "mr_fill_time
            "mr_env_step", "mr_env_rollout", "mr_gp_predict", "mr_gp_workspace_bytes", "mr_gp_correct_heading", "mr_gp_fit", "mr_gp_fit_workspace_bytes", "mr_actor_param_count",
            "mr_critic_param_count", "mr_replay_add", "mr_ou_noise_add", "mr_ddpg_update", "mr_learn_preprocess",
            "mr_learn_workspace_bytes", "mr_ddpg_workspace_bytes", "mr_replay_sample", "mr_actor_forward_env", "mr_ddpg_gradients", "mr_ddpg_apply", "mr_gp_correct_heading_cheb", "mr_host_pipeline_create", "mr_host_pipeline_destroy", "mr_env_step_host",
-           "mr_actor_forward", "mr_set_step_path", "mr_env_reset_ex", "mr_counter_set")
+           "mr_actor_forward", "mr_set_step_path", "mr_env_reset_ex", "mr_counter_set", "mr_set_actor_path")
 
 _lib = None
 
@@ -187,6 +187,8 @@ def load():
     lib.mr_gp_workspace_bytes.argtypes = [P(GPModel), C.c_int64, C.c_int32]
     lib.mr_gp_workspace_bytes.restype = C.c_int64
     lib.mr_actor_param_count.restype = C.c_int32
+    lib.mr_set_actor_path.argtypes = [C.c_int32]
+    lib.mr_set_actor_path.restype = C.c_int
     lib.mr_set_step_path.argtypes = [C.c_int32]
     lib.mr_set_step_path.restype = C.c_int
     lib.mr_actor_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double * 2, C.c_void_p,
@@ -208,6 +210,17 @@ def set_step_path(name):
     if old < 0:
         check(old, "mr_set_step_path")
     return {v: k for k, v in STEP_PATHS.items()}[old]
+
+
+ACTOR_PATHS = {"default": 0, "simt": 1, "tf32": 2}
+
+
+def set_actor_path(name):
+    """Force the in-rollout actor implementation (tests / A-B timing); returns the previous name."""
+    old = load().mr_set_actor_path(ACTOR_PATHS[name])
+    if old < 0:
+        check(old, "mr_set_actor_path")
+    return {v: k for k, v in ACTOR_PATHS.items()}[old]
 
 
 def check(rc, what=""):

@@ -18,6 +18,11 @@ static int step_path_from_env() {
     return e[0] == 't' ? 1 : e[0] == 'v' ? 2 : e[0] == 's' ? 3 : e[0] == 'w' ? 4 : 0;
 }
 int g_step_path = step_path_from_env();
+static int actor_path_from_env() {
+    const char* e = getenv("MR_ACTOR_PATH");
+    return !e ? 0 : e[0] == 's' ? 1 : e[0] == 't' ? 2 : 0;
+}
+int g_actor_path = actor_path_from_env();
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -183,6 +188,13 @@ int mr_set_step_path(int32_t path) {
     if (path < 0 || path > 4) return mr::fail(MR_ERR_ARG, "mr_set_step_path: path must be 0..4");
     const int old = mr::g_step_path;
     mr::g_step_path = path;
+    return old;
+}
+
+int mr_set_actor_path(int32_t path) {
+    if (path < 0 || path > 2) return mr::fail(MR_ERR_ARG, "mr_set_actor_path: path must be 0..2");
+    const int old = mr::g_actor_path;
+    mr::g_actor_path = path;
     return old;
 }
 

@@ -4,6 +4,7 @@
 
 #include "mr_actor.cuh"
 #include "mr_actor_tc.cuh"
+#include "mr_actor_tc16.cuh"
 #include "mr_common.cuh"
 
 namespace mr {
@@ -12,15 +13,19 @@ namespace mr {
 // Fused rollout: K env steps per launch, state in registers, one env per thread.
 // FP64-pipe bound (no HBM traffic for state between steps).
 // =============================================================================================
-constexpr int kSrcActorTc = 100;   // internal: MR_ACTIONS_ACTOR evaluated on the tensor cores (mr_actor_tc.cuh)
+constexpr int kSrcActorTc = 100;     // internal: MR_ACTIONS_ACTOR with the hidden layer on the tensor cores, 3xTF32 (mr_actor_tc.cuh)
+constexpr int kSrcActorTc16 = 101;   // internal: both dense layers on the tensor cores, 3xFP16, 4 CTAs per SM (mr_actor_tc16.cuh)
 
 #ifndef MR_ROLLOUT_MINB
 #define MR_ROLLOUT_MINB 6   // measured: 85 registers, 24 warps/SM -> 56 vs 46 Genv-steps/s (sigma = 0) than unconstrained (143 registers)
 #endif
+template <int SRC, bool PERENV> struct RolloutMinCtas {
+    static constexpr int value = SRC == kSrcActorTc16 ? 4 : (SRC == MR_ACTIONS_ACTOR || SRC == kSrcActorTc || PERENV) ? 1 : MR_ROLLOUT_MINB;
+};
 // PERENV: a0 / noise_var / is_mismatched come from the per-env rows of the state (the model flag is then a run-time
 // branch and MISM is ignored).
 template <class T, int MODE, bool MISM, int SRC, bool PERENV = false>
-__global__ void __launch_bounds__(128, (SRC == MR_ACTIONS_ACTOR || SRC == kSrcActorTc || PERENV) ? 1 : MR_ROLLOUT_MINB)
+__global__ void __launch_bounds__(128, RolloutMinCtas<SRC, PERENV>::value)
 env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView nv, TimeView tv, Params p, int64_t n) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ double s_stats[MR_STATS_LEN];
@@ -29,6 +34,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         for (int k = threadIdx.x; k < kActorParams; k += blockDim.x) s_actor[k] = io.actor[k];
     }
     if constexpr (SRC == kSrcActorTc) actor_tc_setup(*reinterpret_cast<ActorTcSmem*>(s_dyn), io.actor);
+    if constexpr (SRC == kSrcActorTc16) actor_tc16_setup(*reinterpret_cast<ActorTc16Smem*>(s_dyn), io.actor);
     if (threadIdx.x < MR_STATS_LEN) s_stats[threadIdx.x] = 0.0;
     __syncthreads();
 
@@ -83,6 +89,8 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             float a2[2];
             if constexpr (SRC == kSrcActorTc)
                 actor_tc_forward(*reinterpret_cast<ActorTcSmem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], k, a2);
+            else if constexpr (SRC == kSrcActorTc16)
+                actor_tc16_forward(*reinterpret_cast<ActorTc16Smem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], k, a2);
             else
                 actor_forward_smem(s_actor, obs5, (float)p.act_hi[0], (float)p.act_hi[1], a2);
             f_t = (double)a2[0]; al = (double)a2[1];
@@ -151,6 +159,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         was_done = o.done && !p.auto_reset;
     }
     if constexpr (SRC == kSrcActorTc) actor_tc_teardown(*reinterpret_cast<ActorTcSmem*>(s_dyn));
+    if constexpr (SRC == kSrcActorTc16) actor_tc16_teardown(*reinterpret_cast<ActorTc16Smem*>(s_dyn));
 
     if (live) {
         if (overflow) e.status |= kNoiseOverflow;
@@ -215,20 +224,24 @@ static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const O
         case MR_ACTIONS_PHILOX:
             env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_PHILOX><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
         case MR_ACTIONS_ACTOR: {
-            // default: hidden layer on the tensor cores (tcgen05); MR_ACTOR_PATH=simt selects the CUDA-core MLP
-            static const bool simt = [] { const char* e = getenv("MR_ACTOR_PATH"); return e && e[0] == 's'; }();
-            if (simt) {
-                env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_ACTOR><<<blocks, threads, kActorParams * sizeof(float), s>>>(sv, rv, ov, nv, tv, p, n);
-            } else {
-                static bool attr[kMaxDevices] = {};
-                const int dev = current_device();
-                if (!attr[dev]) {
-                    cudaFuncSetAttribute(env_rollout_kernel<T, MODE, MISM, kSrcActorTc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(ActorTcSmem));
-                    attr[dev] = true;
-                }
-                env_rollout_kernel<T, MODE, MISM, kSrcActorTc><<<blocks, kTcRows, sizeof(ActorTcSmem), s>>>(sv, rv, ov, nv, tv, p, n);
+            // default: both dense layers on the tensor cores (tcgen05, 3xFP16, 4 CTAs/SM); MR_ACTOR_PATH=tf32 selects the
+            // 3xTF32 hidden-layer kernel (fp32 operand range), MR_ACTOR_PATH=simt the CUDA-core MLP
+            const int path = g_actor_path;              // mr_set_actor_path(), initialised from MR_ACTOR_PATH
+            static bool attr[kMaxDevices] = {};
+            const int dev = current_device();
+            if (!attr[dev]) {
+                cudaFuncSetAttribute(env_rollout_kernel<T, MODE, MISM, kSrcActorTc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(ActorTcSmem));
+                cudaFuncSetAttribute(env_rollout_kernel<T, MODE, MISM, kSrcActorTc16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(ActorTc16Smem));
+                attr[dev] = true;
             }
+            if (path == 1)
+                env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_ACTOR><<<blocks, threads, kActorParams * sizeof(float), s>>>(sv, rv, ov, nv, tv, p, n);
+            else if (path == 2)
+                env_rollout_kernel<T, MODE, MISM, kSrcActorTc><<<blocks, kTcRows, sizeof(ActorTcSmem), s>>>(sv, rv, ov, nv, tv, p, n);
+            else
+                env_rollout_kernel<T, MODE, MISM, kSrcActorTc16><<<blocks, kT16Rows, sizeof(ActorTc16Smem), s>>>(sv, rv, ov, nv, tv, p, n);
             break;
         }
         default: return fail(MR_ERR_ARG, "mr_env_rollout: unknown action source %d", rv.action_source);

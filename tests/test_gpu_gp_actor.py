@@ -242,6 +242,50 @@ def test_actor_in_the_rollout_loop_matches_stepwise_composition():
     assert rel_err(e1.last_pos.cpu().numpy(), e2.last_pos.cpu().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize("path", ["default", "tf32", "simt"])
+def test_in_rollout_actor_paths_cross_an_episode_boundary(path):
+    """Every in-kernel actor implementation (3xFP16 tensor cores with both dense layers, 3xTF32 hidden layer, CUDA cores),
+    with non-trivial batch-norm statistics, through AUTO RESETS: the fused rollout must equal actor_forward + single step
+    composed on the host — in particular the first action of a new episode sees the new episode's observation (x, y AND
+    distance), as a caller that does `s = env.reset()` would feed it (RL/MR_ddpg.py:270-278)."""
+    from mr_rl_b200 import VecMREnv, _lib as L, actor_forward, init_actor, pack_actor
+    params = init_actor(7)
+    g = torch.Generator().manual_seed(8)
+    params["w3"] = 0.5 * torch.randn(64, 2, generator=g)
+    for k in ("m1", "m2"):
+        params[k] = 0.05 * torch.randn(64, generator=g)
+    for k in ("v1", "v2"):
+        params[k] = 0.5 + torch.rand(64, generator=g)
+    for k in ("be1", "be2", "b1", "b2"):
+        params[k] = 0.02 * torch.randn(64, generator=g)
+    packed = pack_actor(params, "cuda:0")
+    n, K = 300, 14
+    try:
+        L.set_actor_path(path)
+        e1 = VecMREnv(n, device="cuda:0", noise="philox", seed=3, auto_reset=True)
+        e2 = VecMREnv(n, device="cuda:0", noise="philox", seed=3, auto_reset=True)
+        for e in (e1, e2):
+            e.max_timesteps = 5                                    # two episode boundaries inside K steps
+            e.reset(init=None, noise_var=0.0, a0=1.0)
+        res = e1.rollout(policy=packed, k_steps=K, record=True, record_done=True)
+        xy, dn = [], []
+        for _ in range(K):
+            a = actor_forward(packed, e2._obs, n)
+            _, _, d, _ = e2.step(a)
+            # (with auto reset last_pos is already the new episode's start: compare the states after the whole run and the
+            # done flags per step; positions per step only where no reset happened)
+            xy.append(e2.last_pos.cpu().numpy().copy()); dn.append(d.cpu().numpy().copy())
+    finally:
+        L.set_actor_path("default")
+    xy, dn = np.stack(xy), np.stack(dn).astype(bool)
+    got = res["xy"].cpu().numpy().transpose(0, 2, 1)
+    assert np.array_equal(res["done_traj"].cpu().numpy().astype(bool), dn) and dn.sum() >= 2 * n
+    keep = ~dn
+    assert rel_err(got[keep], xy[keep]) < 2e-6
+    assert rel_err(e1.last_pos.cpu().numpy(), e2.last_pos.cpu().numpy()) < 2e-6
+    assert np.array_equal(e1.counter.cpu().numpy(), e2.counter.cpu().numpy())
+
+
 def test_mr_env_facade_matches_live_reference(golden_single):
     """The N = 1 drop-in class: numpy in / numpy out, python int reward, python bool done, dict info."""
     from mr_rl_b200 import MR_Env
