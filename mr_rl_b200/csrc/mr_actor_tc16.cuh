@@ -15,8 +15,9 @@
 //     layer (layer 2): 16 live registers instead of 64;
 //   -> 53 KB shared memory, 128 TMEM columns and <= 128 registers per CTA: 4 CTAs = 16 warps per SM, so one CTA's MMA
 //   round trips overlap the CUDA-core work (operand split, epilogue, the fp64 env step) of the three others.
-// Range: fp16 operands saturate at 6e4 (activations are clamped there); the TF32 path keeps fp32 range and stays
-// selectable (MR_ACTOR_PATH=tf32).  Descriptors are hand-built (SM100 UMMA, K-major, no swizzle), no CUTLASS.
+// Range: fp16 operands overflow beyond 65504 — an observation or hidden activation that large turns the action into
+// NaN, which the env flags as MR_ENV_NONFINITE (a loud failure; MR_Env's observation bounds are 5000 / 80000 and
+// batch-normalised activations are O(1-10)).  The TF32 path keeps fp32 range and stays selectable (MR_ACTOR_PATH=tf32).  Descriptors are hand-built (SM100 UMMA, K-major, no swizzle), no CUTLASS.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -32,7 +33,6 @@ constexpr int kT16LBO = 128;                   // bytes between adjacent 16-byte
 constexpr int kT16SBO2 = 8 * 128;              // layer 2: K = 64 halfs = 8 chunks per 8-row group
 constexpr int kT16SBO1 = 2 * 128;              // layer 1: K = 16 halfs = 2 chunks per 8-row group
 constexpr int kT16Cols = 128;                  // TMEM columns: D1 [0, 64), D2 [64, 128)
-constexpr float kT16Max = 6.0e4f;              // fp16 operand range
 
 struct alignas(128) ActorTc16Smem {
     __half a_hi[kT16Rows * kActorHidden];      // 16 KB each; bytes [0, 4096) double as the layer-1 A tile [128 x 16]
@@ -81,13 +81,23 @@ __device__ __forceinline__ void t16_split2(float a, float b, uint32_t& hi, uint3
 }
 
 __device__ __forceinline__ void t16_wait(uint64_t* mbar, uint32_t parity) {
-    // bounded spin: a descriptor mistake must trap, not hang the GPU
-    const uint32_t bar = t16_smem_u32(mbar);
-    uint32_t ok = 0;
-    for (int spin = 0; spin < (1 << 28) && !ok; ++spin)
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok) __trap();
+    // try_wait suspends the thread in hardware until the phase completes or the hinted time passes, so the loop body
+    // normally runs once or twice (the first version polled from C: 14 polls of 6 instructions per wait, 9 % of the
+    // kernel's issue slots).  Bounded: a descriptor mistake must trap, not hang the GPU.
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 c;\n"
+        "mov.u32 c, 0;\n"
+        "T16_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n"
+        "@p bra T16_DONE_%=;\n"
+        "add.u32 c, c, 1;\n"
+        "setp.lt.u32 q, c, 0x4000000;\n"
+        "@q bra T16_WAIT_%=;\n"
+        "trap;\n"
+        "T16_DONE_%=:\n"
+        "}\n" ::"r"(t16_smem_u32(mbar)), "r"(parity) : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
@@ -172,11 +182,9 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
 
     // ---- layer-1 A tile: [x, y, d, 1, 0, 0, 0, 0 | 0 x 8] as fp16 hi / lo -----------------------------------
     {
-        const float ox = fminf(fmaxf(obs[0], -kT16Max), kT16Max), oy = fminf(fmaxf(obs[1], -kT16Max), kT16Max);
-        const float od = fminf(obs[4], kT16Max);
         uint32_t h0, l0, h1, l1;
-        t16_split2(ox, oy, h0, l0);
-        t16_split2(od, 1.0f, h1, l1);
+        t16_split2(obs[0], obs[1], h0, l0);
+        t16_split2(obs[4], 1.0f, h1, l1);
         const int off = (tid >> 3) * kT16SBO1 + (tid & 7) * 16;
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h0, h1, 0u, 0u);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l0, l1, 0u, 0u);
@@ -208,8 +216,7 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
             uint32_t h[8], l[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                t16_split2(fminf(fmaxf(__uint_as_float(r[2 * j]), 0.f), kT16Max),
-                           fminf(fmaxf(__uint_as_float(r[2 * j + 1]), 0.f), kT16Max), h[j], l[j]);
+                t16_split2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f), h[j], l[j]);
             *reinterpret_cast<uint4*>(a_hi + row_off + (2 * q) * kT16LBO) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(a_hi + row_off + (2 * q + 1) * kT16LBO) = make_uint4(h[4], h[5], h[6], h[7]);
             *reinterpret_cast<uint4*>(a_lo + row_off + (2 * q) * kT16LBO) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -235,7 +242,7 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
     t16_wait(&sm.mbar[1], parity);
 
     // ---- BN + ReLU, 64 x 2 output layer, tanh, action bound ---------------------------------------------------------
-    float o0 = sm.b3[0], o1 = sm.b3[1];
+    float o0[2] = {sm.b3[0], 0.f}, o1[2] = {sm.b3[1], 0.f};           // two partial sums each: shorter FMA chains
 #pragma unroll
     for (int q = 0; q < kActorHidden / 16; ++q) {
         uint32_t r[16];
@@ -244,11 +251,11 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
         for (int j = 0; j < 16; ++j) {
             const float4 c = sm.ep[q * 16 + j];                        // one broadcast 16-byte read per hidden unit
             const float y = fmaxf(fmaf(c.x, __uint_as_float(r[j]), c.y), 0.f);
-            o0 = fmaf(y, c.z, o0); o1 = fmaf(y, c.w, o1);
+            o0[j & 1] = fmaf(y, c.z, o0[j & 1]); o1[j & 1] = fmaf(y, c.w, o1[j & 1]);
         }
     }
-    act[0] = tanhf(o0) * hi0;
-    act[1] = tanhf(o1) * hi1;
+    act[0] = tanhf(o0[0] + o0[1]) * hi0;
+    act[1] = tanhf(o1[0] + o1[1]) * hi1;
 }
 
 }  // namespace mr

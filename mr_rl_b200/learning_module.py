@@ -154,7 +154,9 @@ class LearningModule:
         (Learning_module.py:215).  The means are entire functions of the heading (sums of Gaussians of width l), so
         their Chebyshev coefficients fall off like exp(-(k l / pi)^2 / 2); the series is cut where they reach the
         rounding floor of the sampled means.  Accepted only if it reproduces mr_gp_predict at ``n_probe`` random headings to ``tol`` (relative
-        to the largest mean), else the search keeps summing the kernel directly."""
+        to the largest mean), else the search keeps summing the kernel directly.
+        LIBRARY CODE, SET-UP ONLY: the discrete cosine transform below is a 2048^2 torch matmul (cuBLAS), once per
+        fitted model; the means it transforms and the search that uses the coefficients are the hand-written kernels."""
         dev = torch.device(self.device)
         j = torch.arange(n_nodes, dtype=torch.float64, device=dev)
         t = torch.cos(math.pi * (j + 0.5) / n_nodes)                       # Chebyshev nodes on [-1, 1]

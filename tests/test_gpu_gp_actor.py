@@ -393,3 +393,27 @@ def test_cheb_heading_entry_point_argument_errors_and_constant_series():
     want = np.arctan2(-ey, -ex)
     assert np.max(np.abs(np.angle(np.exp(1j * (out.cpu().numpy() - want))))) < 2e-5
     assert int(nf.min()) >= 5 and int(nf.max()) < 60
+
+
+def test_gp_posterior_at_config3_size_against_sklearn_spot_check():
+    """BASELINE configs[3] at its stated size — 262 144 queries against 2000 training points, both forms of the variance —
+    checked against sklearn's GaussianProcessRegressor.predict(return_std=True) on every 64th query (4096 of them)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+
+    from mr_rl_b200 import DeviceGP
+    rng = np.random.default_rng(0)
+    X = np.sort(rng.uniform(-np.pi, np.pi, 2000))
+    y = 0.2 + 0.5 * np.cos(X + 0.3) + 0.09 * rng.standard_normal(2000)
+    gpr = GaussianProcessRegressor(kernel=RBF(0.2) + WhiteKernel(0.008), optimizer=None, alpha=1e-10).fit(X[:, None], y)
+    q = rng.uniform(-np.pi, np.pi, 262144)
+    mu_ref, sd_ref = gpr.predict(q[::64, None], return_std=True)
+    gp = DeviceGP.fit(X, y, 0.2, 0.008, device="cuda:0")
+    qd = torch.as_tensor(q, device="cuda:0")
+    mu, sd = gp.predict(qd, True)                                        # triangular form = sklearn's algorithm
+    assert np.allclose(mu.cpu().numpy()[::64], mu_ref, rtol=1e-8, atol=1e-10)
+    assert np.allclose(sd.cpu().numpy()[::64], sd_ref, rtol=1e-6, atol=1e-12)
+    assert gp.enable_spectral_variance() > 0 and gp.spectral_build_ms > 0
+    mu2, sd2 = gp.predict(qd, True)                                      # low-rank form, all 262 144 queries against the triangular one
+    assert float((mu2 - mu).abs().max()) < 1e-10
+    assert float(((sd2 - sd).abs() / sd).max()) < 1e-8
