@@ -80,6 +80,27 @@ __device__ __forceinline__ void t16_split2(float a, float b, uint32_t& hi, uint3
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// ReLU fused into the split (hidden activations): hi = fp16(max(v, 0)) rounded TOWARDS ZERO, so the remainder is never
+// negative and the lo conversion may apply ReLU too — which also zeroes the lanes where v < 0 (hi = 0, remainder = v).
+// One cvt.relu instead of two FMNMX + cvt per pair; 11 + 11 significand bits, 2^-21 relative like 3xTF32.
+__device__ __forceinline__ void t16_split2_relu(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));       // d = {hi half: first source, lo half: second}
+    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - back.y), "f"(a - back.x));
+}
+
+// tanh to ~1e-6 relative from one ex2 and one rcp (tanhf's polynomial + exp path is ~25 instructions; the 1e-4 bar on
+// the actions does not need it): tanh x = sign(x) (1 - 2 / (exp(2|x|) + 1)), and x (1 - x^2/3) where that cancels
+__device__ __forceinline__ float t16_tanh(float x) {
+    const float ax = fabsf(x);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.8853900817779268f));   // exp(2|x|)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    const float big = fmaf(-2.0f, r, 1.0f);
+    const float small = ax * fmaf(ax * ax, -0.3333333333f, 1.0f);
+    return copysignf(ax < 0.02f ? small : big, x);
+}
+
 __device__ __forceinline__ void t16_wait(uint64_t* mbar, uint32_t parity) {
     // try_wait suspends the thread in hardware until the phase completes or the hinted time passes, so the loop body
     // normally runs once or twice (the first version polled from C: 14 polls of 6 instructions per wait, 9 % of the
@@ -216,7 +237,7 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
             uint32_t h[8], l[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                t16_split2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f), h[j], l[j]);
+                t16_split2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), h[j], l[j]);
             *reinterpret_cast<uint4*>(a_hi + row_off + (2 * q) * kT16LBO) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(a_hi + row_off + (2 * q + 1) * kT16LBO) = make_uint4(h[4], h[5], h[6], h[7]);
             *reinterpret_cast<uint4*>(a_lo + row_off + (2 * q) * kT16LBO) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -254,8 +275,8 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
             o0[j & 1] = fmaf(y, c.z, o0[j & 1]); o1[j & 1] = fmaf(y, c.w, o1[j & 1]);
         }
     }
-    act[0] = tanhf(o0[0] + o0[1]) * hi0;
-    act[1] = tanhf(o1[0] + o1[1]) * hi1;
+    act[0] = t16_tanh(o0[0] + o0[1]) * hi0;
+    act[1] = t16_tanh(o1[0] + o1[1]) * hi1;
 }
 
 }  // namespace mr
