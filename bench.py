@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--sigma", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--preroll-s", type=float, default=PREROLL_S,
+                    help="seconds of the timed kernel run back to back right before the timed region (shrink it for an ncu pass)")
     ap.add_argument("--no-extras", action="store_true", help="skip the fused-rollout / small-batch side numbers")
     return ap.parse_args()
 
@@ -224,11 +226,12 @@ def run_ours(args):
         e.reset(init=None, noise_var=sigma, a0=1.0)
         return e
 
-    def timed_steps(e, a, steps, use_graph, preroll_s=PREROLL_S):
+    def timed_steps(e, a, steps, use_graph, preroll_s=None):
         """W warm-up steps, then the SAME kernel back to back for >= preroll_s (still untimed: the clocks ramp and
         settle under load), then — with no synchronisation or idle gap after the last pre-roll launch — ev0, exactly
         `steps` single-step launches, ev1.  use_graph: the K launches are one CUDA-graph replay (captured once; the
         pre-roll replays the same graph).  Returns (ms of the K steps, wall-clock window, pre-roll launches)."""
+        preroll_s = args.preroll_s if preroll_s is None else preroll_s
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g = e.capture_steps([a[k] for k in range(pool)], steps) if use_graph else None
@@ -238,7 +241,7 @@ def run_ours(args):
         p1.record()
         torch.cuda.synchronize()
         per = max(p0.elapsed_time(p1) / W, 1e-3)              # ms per launch, rough (cold)
-        n_pre = int(min(20000, max(50, preroll_s * 1e3 / per)))
+        n_pre = int(min(20000, max(8, preroll_s * 1e3 / per)))
         barrier()
         if g is not None:
             for _ in range(max(2, n_pre // steps)):
@@ -287,7 +290,7 @@ def run_ours(args):
     # the timed region lasts a few ms — shorter than nvidia-smi's sampling period — so the same kernel
     # keeps running (untimed) for ~0.4 s while the clock sampler collects its under-load samples
     if rank == 0:
-        t_wall0 -= PREROLL_S
+        t_wall0 -= args.preroll_s
         t_ext = time.perf_counter()
         while time.perf_counter() - t_ext < 0.4:
             if graph is not None:
