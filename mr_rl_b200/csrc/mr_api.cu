@@ -218,6 +218,7 @@ void mr_fill_time_table_host(double* t, int32_t len, double time_span) {
 int mr_env_reset_ex(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
                     const void* init_xy, const uint8_t* mask, int32_t reset_cursor, const mr_reset_params* rp,
                     const mr_step_out* out, void* stream) {
+    mr::NvtxRange nvtx_range("mr_env_reset_ex");
     int rc = mr::check_common("mr_env_reset", st, n, dtype, p, nz);
     if (rc) return rc;
     if (rp && (rp->a0 || rp->noise_var || rp->is_mismatched) && !st->a0)
@@ -243,6 +244,7 @@ int mr_counter_set(uint64_t* counter_dev, uint64_t value, void* stream) {
 
 int mr_env_step(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
                 const mr_time_table* tt, const void* actions, const mr_step_out* out, void* stream) {
+    mr::NvtxRange nvtx_range("mr_env_step");
     int rc = mr::check_common("mr_env_step", st, n, dtype, p, nz);
     if (rc) return rc;
     if (n == 0) return MR_OK;
@@ -313,6 +315,7 @@ void mr_host_pipeline_destroy(mr_host_pipeline* pl) {
 int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,
                      const mr_noise* nz, const mr_time_table* tt, const mr_host_step_io* io, const mr_step_out* out_dev,
                      int32_t n_chunks, void* stream) {
+    mr::NvtxRange nvtx_range("mr_env_step_host");
     int rc = mr::check_common("mr_env_step_host", st, n, dtype, p, nz);
     if (rc) return rc;
     if (!io) return mr::fail(MR_ERR_ARG, "mr_env_step_host: null io");
@@ -403,6 +406,7 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
 
 int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
                    const mr_time_table* tt, const mr_rollout_io* io, const mr_step_out* out, void* stream) {
+    mr::NvtxRange nvtx_range("mr_env_rollout");
     int rc = mr::check_common("mr_env_rollout", st, n, dtype, p, nz);
     if (rc) return rc;
     if (!io || io->k_steps < 0) return mr::fail(MR_ERR_ARG, "mr_env_rollout: bad io");

@@ -1,6 +1,7 @@
 // Shared device-side views and helpers of the env kernels (step / reset / rollout).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost a pointer test unless a profiler is attached
 
 #include <cstdint>
 #include <cstring>
@@ -9,6 +10,14 @@
 #include "mr_core.cuh"
 
 namespace mr {
+
+// NVTX range around an entry point's launches (nsys / ncu --nvtx group the kernels by the reference method they replace)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);

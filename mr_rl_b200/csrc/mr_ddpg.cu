@@ -571,6 +571,7 @@ int32_t mr_critic_param_count(void) { return mr::kCriticParams; }
 int mr_replay_add(const mr_replay* rb, int64_t head, const void* obs, int64_t obs_row_stride, const void* actions,
                   const void* rew, const uint8_t* done, const void* obs_next, int64_t obs_next_row_stride, int64_t n,
                   int32_t dtype, void* stream) {
+    mr::NvtxRange nvtx_range("mr_replay_add");
     using namespace mr;
     if (!rb || !rb->s || !rb->a || !rb->r || !rb->d || !rb->s2) return fail(MR_ERR_ARG, "mr_replay_add: null replay buffer");
     if (!obs || !actions || !rew || !done || !obs_next) return fail(MR_ERR_ARG, "mr_replay_add: null argument");
@@ -626,6 +627,7 @@ int mr_replay_sample(int64_t count, int32_t batch, uint64_t seed, int64_t update
 int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
                    uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, float* info_out, void* workspace,
                    int64_t workspace_bytes, void* stream) {
+    mr::NvtxRange nvtx_range("mr_ddpg_update");
     using namespace mr;
     if (!st || !st->actor || !st->actor_target || !st->critic || !st->critic_target || !st->adam_actor_m || !st->adam_actor_v ||
         !st->adam_critic_m || !st->adam_critic_v || !st->grad_actor || !st->grad_critic)
@@ -686,6 +688,7 @@ int mr_ddpg_update(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, 
 int mr_ddpg_gradients(const mr_ddpg_state* st, const mr_replay* rb, int64_t count, int32_t batch, const int64_t* indices,
                       uint64_t seed, int64_t update_index, const mr_ddpg_hyper* hp, int32_t which, float* grad_out,
                       void* workspace, int64_t workspace_bytes, void* stream) {
+    mr::NvtxRange nvtx_range("mr_ddpg_gradients");
     using namespace mr;
     if (!st || !st->actor || !st->actor_target || !st->critic || !st->critic_target) return fail(MR_ERR_ARG, "mr_ddpg_gradients: null learner state");
     if (!rb || !rb->s || !rb->a || !rb->r || !rb->d || !rb->s2) return fail(MR_ERR_ARG, "mr_ddpg_gradients: null replay buffer");
@@ -731,6 +734,7 @@ int mr_ddpg_gradients(const mr_ddpg_state* st, const mr_replay* rb, int64_t coun
 
 int mr_ddpg_apply(const mr_ddpg_state* st, int32_t which, const float* grad, double grad_scale, int64_t update_index,
                   const mr_ddpg_hyper* hp, void* stream) {
+    mr::NvtxRange nvtx_range("mr_ddpg_apply");
     using namespace mr;
     if (!st || !st->actor || !st->actor_target || !st->critic || !st->critic_target || !st->adam_actor_m || !st->adam_actor_v ||
         !st->adam_critic_m || !st->adam_critic_v)

@@ -540,6 +540,7 @@ int64_t mr_gp_workspace_bytes(const mr_gp_model* gp, int64_t n_q, int32_t want_s
 
 int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* mean, double* std, void* workspace,
                   int64_t workspace_bytes, void* stream) {
+    mr::NvtxRange nvtx_range("mr_gp_predict");
     using namespace mr;
     if (!gp || !gp->x_train_scaled || !gp->alpha) return fail(MR_ERR_ARG, "mr_gp_predict: null model");
     if (n_q < 0) return fail(MR_ERR_ARG, "mr_gp_predict: bad n_q");
@@ -610,6 +611,7 @@ int mr_gp_predict(const mr_gp_model* gp, const double* q, int64_t n_q, double* m
 
 int mr_gp_correct_heading(const mr_gp_model* gpx, const mr_gp_model* gpy, const double* vd, int64_t n, double a0,
                           double freq, double drift_x, double drift_y, double* alpha_out, int32_t* nfev_out, void* stream) {
+    mr::NvtxRange nvtx_range("mr_gp_correct_heading");
     using namespace mr;
     if (!gpx || !gpy || !gpx->x_train_scaled || !gpy->x_train_scaled || !gpx->alpha || !gpy->alpha)
         return fail(MR_ERR_ARG, "mr_gp_correct_heading: null model");
@@ -631,6 +633,7 @@ int mr_gp_correct_heading(const mr_gp_model* gpx, const mr_gp_model* gpy, const 
 int mr_gp_correct_heading_cheb(const double* coef_x, const double* coef_y, int32_t n_coef, const double* vd, int64_t n,
                                double a0, double freq, double drift_x, double drift_y, double* alpha_out, int32_t* nfev_out,
                                void* stream) {
+    mr::NvtxRange nvtx_range("mr_gp_correct_heading_cheb");
     using namespace mr;
     if (!coef_x || !coef_y) return fail(MR_ERR_ARG, "mr_gp_correct_heading_cheb: null coefficients");
     if (n_coef < 1 || n_coef > 4096) return fail(MR_ERR_ARG, "mr_gp_correct_heading_cheb: need 1 <= n_coef <= 4096");
@@ -650,6 +653,7 @@ int32_t mr_actor_param_count(void) { return mr::kActorParams; }
 
 int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
                      const double action_high[2], void* actions, void* stream) {
+    mr::NvtxRange nvtx_range("mr_actor_forward");
     using namespace mr;
     if (!actor || !obs || !actions || !action_high) return fail(MR_ERR_ARG, "mr_actor_forward: null argument");
     if (n < 0) return fail(MR_ERR_ARG, "mr_actor_forward: bad n");
@@ -669,6 +673,7 @@ int mr_actor_forward(const float* actor, const void* obs, int64_t obs_row_stride
 
 int mr_actor_forward_env(const float* actor, const void* obs, int64_t obs_row_stride, int64_t n, int32_t dtype,
                          const double action_high[2], void* actions, void* stream) {
+    mr::NvtxRange nvtx_range("mr_actor_forward_env");
     using namespace mr;
     if (!actor || !obs || !actions || !action_high) return fail(MR_ERR_ARG, "mr_actor_forward_env: null argument");
     if (n < 0) return fail(MR_ERR_ARG, "mr_actor_forward_env: bad n");

@@ -333,6 +333,7 @@ int64_t mr_gp_fit_workspace_bytes(int32_t n_pad) {
 int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n_pad, int32_t dim, double length_scale,
               double noise_level, double jitter, double* x_scaled_out, double* alpha_out, double* linv_out,
               double* lml_out, double* grad_out, int32_t* info_out, void* workspace, int64_t workspace_bytes, void* stream) {
+    mr::NvtxRange nvtx_range("mr_gp_fit");
     using namespace mr;
     if (!x_train || !y || !x_scaled_out || !alpha_out || !linv_out) return fail(MR_ERR_ARG, "mr_gp_fit: null argument");
     if (n_train <= 0 || n_pad < n_train || n_pad % NB != 0) return fail(MR_ERR_ARG, "mr_gp_fit: n_pad must be a multiple of %d >= n_train", NB);

@@ -128,6 +128,7 @@ int mr_learn_preprocess(const double* px, const double* py, const double* time, 
                         double drift_x, double drift_y, const double* alpha_sim, double freq, int32_t n_valid, double* vx_out,
                         double* vy_out, double* x_out, double* yx_out, double* yy_out, double* scalars_out, void* workspace,
                         int64_t workspace_bytes, void* stream) {
+    mr::NvtxRange nvtx_range("mr_learn_preprocess");
     using namespace mr;
     if (!px || !py || !time || !vx_out || !vy_out || !scalars_out) return fail(MR_ERR_ARG, "mr_learn_preprocess: null argument");
     if (n < 2 || n > (1 << 20)) return fail(MR_ERR_ARG, "mr_learn_preprocess: need 2 <= n <= 2^20 samples");
