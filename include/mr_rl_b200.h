@@ -337,6 +337,13 @@ typedef struct mr_host_step_io {
                                /* (the 1e-4 tier on the wire; the state and all decisions stay fp64)          */
 } mr_host_step_io;
 
+/* Page-lock a caller-owned host range in place (cudaHostRegister) so the direct mode can read / write it without a
+ * staging copy — for callers that step with the same plain (malloc'ed, numpy) buffers every time.  Fails with
+ * MR_ERR_UNSUPPORTED where registered memory is not addressable by its host pointer.  Undo with mr_host_unregister
+ * before the memory is freed. */
+int mr_host_register(void* host_ptr, int64_t bytes);
+int mr_host_unregister(void* host_ptr);
+
 /* out_dev: the device rows the kernel writes (obs, rew, done required).  `stream`: the caller's stream; the pipeline
  * starts after the work already queued on it, and work queued on it afterwards sees the stepped state. */
 int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p,

@@ -404,6 +404,23 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
     return mr::check_launch("mr_env_step_host");
 }
 
+int mr_host_register(void* host_ptr, int64_t bytes) {
+    if (!host_ptr || bytes <= 0) return mr::fail(MR_ERR_ARG, "mr_host_register: null pointer or empty range");
+    int dev = 0, same = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&same, cudaDevAttrCanUseHostPointerForRegisteredMem, dev);
+    if (!same) return mr::fail(MR_ERR_UNSUPPORTED, "mr_host_register: this platform needs a separate device pointer for registered memory");
+    const cudaError_t e = cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return mr::fail(MR_ERR_CUDA, "mr_host_register: %s", cudaGetErrorString(e)); }
+    return MR_OK;
+}
+
+int mr_host_unregister(void* host_ptr) {
+    const cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return mr::fail(MR_ERR_CUDA, "mr_host_unregister: %s", cudaGetErrorString(e)); }
+    return MR_OK;
+}
+
 int mr_env_rollout(const mr_env_state* st, int64_t n, int32_t dtype, const mr_sim_params* p, const mr_noise* nz,
                    const mr_time_table* tt, const mr_rollout_io* io, const mr_step_out* out, void* stream) {
     mr::NvtxRange nvtx_range("mr_env_rollout");

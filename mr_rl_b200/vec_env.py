@@ -352,6 +352,33 @@ class VecMREnv:
         replays keep drawing fresh noise; results are identical to K ``step`` calls (tested)."""
         return StepGraph(self, action_buffers, k_steps)
 
+    # A caller that steps with the SAME plain numpy action array every time (the usual control loop) should not pay a
+    # 16 MB staging copy per step: the array's pages are page-locked in place once (cudaHostRegister) and the step kernel
+    # reads them directly, like a pinned tensor.  At most `host_register_max` arrays are kept registered (oldest dropped).
+    host_register_max = 16
+
+    def _registered_view(self, a_np, hdt):
+        """A torch view of the caller's numpy array after page-locking it in place, or None if it cannot be used as it
+        is (wrong dtype, not C-contiguous, too small to be worth it, registration refused)."""
+        want = np.float64 if hdt is torch.float64 else np.float32
+        if a_np.dtype != want or not a_np.flags.c_contiguous or not a_np.flags.writeable or a_np.nbytes < (1 << 16):
+            return None
+        reg = self._pinned.setdefault("registered", {})
+        key = (a_np.ctypes.data, a_np.nbytes)
+        hit = reg.get(key)
+        if hit is not None:
+            return hit[0]
+        with torch.cuda.device(self.device):
+            if self.lib.mr_host_register(a_np.ctypes.data, a_np.nbytes) != 0:
+                return None                       # e.g. the platform cannot address registered memory by its host pointer
+        while len(reg) >= self.host_register_max:
+            old_key = next(iter(reg))
+            self.lib.mr_host_unregister(old_key[0])
+            del reg[old_key]
+        view = torch.from_numpy(a_np).view(-1, 2)
+        reg[key] = (view, a_np)                   # keeps the array alive while it is registered
+        return view
+
     def _pinned_buf(self, key, shape, dtype):
         b = self._pinned.get(key)
         if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
@@ -395,8 +422,10 @@ class VecMREnv:
             a_np = np.asarray(actions.numpy() if torch.is_tensor(actions) else actions)
             if a_np.size != 2 * n:
                 raise ValueError(f"actions must be [{n}, 2]")
-            a_pin = self._pinned_buf("act", (n, 2), hdt)
-            np.copyto(a_pin.numpy(), a_np.reshape(n, 2), casting="same_kind")
+            a_pin = self._registered_view(a_np, hdt) if direct else None
+            if a_pin is None:                     # staging copy into pinned memory (dtype / layout / registration not usable)
+                a_pin = self._pinned_buf("act", (n, 2), hdt)
+                np.copyto(a_pin.numpy(), a_np.reshape(n, 2), casting="same_kind")
         a_dev = self._pinned.get("act_dev")
         if a_dev is None and not direct:
             a_dev = self._pinned["act_dev"] = torch.empty(n, 2, dtype=self.dtype, device=self.device)
@@ -464,6 +493,9 @@ class VecMREnv:
             if pl is not None:
                 self.lib.mr_host_pipeline_destroy(pl)
                 self._pinned["pipeline"] = None
+            for key in list(self._pinned.get("registered", {})):
+                self.lib.mr_host_unregister(key[0])
+            self._pinned["registered"] = {}
         except Exception:
             pass
 

@@ -921,3 +921,23 @@ def test_host_step_float32_wire_format():
         o64, _, d64, _ = e64.step_host(a32.astype(np.float64))
         o32, _, d32, _ = e32.step_host(pin)
         assert np.array_equal(o32, o64.astype(np.float32)) and np.array_equal(d64, d32)
+
+
+def test_host_step_reads_a_reused_numpy_array_in_place():
+    """A caller that steps with the same plain numpy action array every time: the array is page-locked in place once
+    (mr_host_register) and the kernel reads it directly — same results as the staging-copy path, and the caller may change
+    the array's contents between steps."""
+    n = 20000
+    rng = np.random.default_rng(5)
+    init = rng.uniform(100, 120, (n, 2))
+    e1 = make_env(n, noise="philox", seed=8); e2 = make_env(n, noise="philox", seed=8)
+    e1.reset(init=init, noise_var=1.0, a0=1.0); e2.reset(init=init, noise_var=1.0, a0=1.0)
+    buf = np.zeros((n, 2))
+    for k in range(4):
+        a = np.stack([rng.uniform(0, 20, n), rng.uniform(0, 6.28, n)], -1)
+        buf[:] = a                                                    # the same array object, new contents
+        o1, _, d1, _ = e1.step_host(buf)
+        o2, _, d2, _ = e2.step_host(torch.as_tensor(a).pin_memory())  # pinned-tensor path
+        assert np.array_equal(o1, o2) and np.array_equal(d1, d2)
+    assert len(e1._pinned.get("registered", {})) == 1
+    del e1
