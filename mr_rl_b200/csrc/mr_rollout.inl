@@ -38,13 +38,21 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     if (threadIdx.x < MR_STATS_LEN) s_stats[threadIdx.x] = 0.0;
     __syncthreads();
 
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;                       // every thread runs the loop (CTA-wide barriers in the actor path)
     double acc[MR_STATS_LEN];
 #pragma unroll
     for (int k = 0; k < MR_STATS_LEN; ++k) acc[k] = 0.0;
-
     const uint64_t off = step_offset(nv);
+    const Params p_launch = p;
+    int actor_calls = 0;                           // mbarrier phase of the tensor-core actor paths
+
+    // One tile of blockDim.x envs per iteration.  The 3xFP16 actor kernel is persistent (grid = resident CTAs: its
+    // per-CTA set-up — weights split into fp16 pairs in UMMA layout, TMEM allocation — is paid once per CTA instead of
+    // once per 128 envs); every other variant is launched with one CTA per tile.
+    const int64_t n_tiles = (n + blockDim.x - 1) / blockDim.x;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i = tile * blockDim.x + threadIdx.x;
+    const bool live = i < n;                       // every thread runs the loop (CTA-wide barriers in the actor path)
+    if constexpr (PERENV) p = p_launch;
     Env e;
     e.x = 110.0; e.y = 110.0; e.fx = 0.0; e.fy = 0.0; e.h = p.dt; e.counter = 0;   // harmless state for padding lanes
     e.status = 0; e.spx = e.spy = 0.0;
@@ -88,9 +96,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             const float obs5[5] = {(float)e.x, (float)e.y, 0.f, 0.f, (float)o.d};
             float a2[2];
             if constexpr (SRC == kSrcActorTc)
-                actor_tc_forward(*reinterpret_cast<ActorTcSmem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], k, a2);
+                actor_tc_forward(*reinterpret_cast<ActorTcSmem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], actor_calls++, a2);
             else if constexpr (SRC == kSrcActorTc16)
-                actor_tc16_forward(*reinterpret_cast<ActorTc16Smem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], k, a2);
+                actor_tc16_forward(*reinterpret_cast<ActorTc16Smem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], actor_calls++, a2);
             else
                 actor_forward_smem(s_actor, obs5, (float)p.act_hi[0], (float)p.act_hi[1], a2);
             f_t = (double)a2[0]; al = (double)a2[1];
@@ -158,8 +166,6 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         }
         was_done = o.done && !p.auto_reset;
     }
-    if constexpr (SRC == kSrcActorTc) actor_tc_teardown(*reinterpret_cast<ActorTcSmem*>(s_dyn));
-    if constexpr (SRC == kSrcActorTc16) actor_tc16_teardown(*reinterpret_cast<ActorTc16Smem*>(s_dyn));
 
     if (live) {
         if (overflow) e.status |= kNoiseOverflow;
@@ -181,6 +187,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         if (out.done) out.done[i] = o.done ? 1 : 0;
         if (out.sp) { out.sp[i] = (T)e.spx; out.sp[out.stride + i] = (T)e.spy; }
     }
+    }   // tiles
+    if constexpr (SRC == kSrcActorTc) actor_tc_teardown(*reinterpret_cast<ActorTcSmem*>(s_dyn));
+    if constexpr (SRC == kSrcActorTc16) actor_tc16_teardown(*reinterpret_cast<ActorTc16Smem*>(s_dyn));
 
     if (io.stats) {   // warp shuffle -> shared -> one atomic per block per statistic
 #pragma unroll
@@ -240,8 +249,12 @@ static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const O
                 env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_ACTOR><<<blocks, threads, kActorParams * sizeof(float), s>>>(sv, rv, ov, nv, tv, p, n);
             else if (path == 2)
                 env_rollout_kernel<T, MODE, MISM, kSrcActorTc><<<blocks, kTcRows, sizeof(ActorTcSmem), s>>>(sv, rv, ov, nv, tv, p, n);
-            else
-                env_rollout_kernel<T, MODE, MISM, kSrcActorTc16><<<blocks, kT16Rows, sizeof(ActorTc16Smem), s>>>(sv, rv, ov, nv, tv, p, n);
+            else {
+                int sms = 0;                                   // persistent: the CTAs that are co-resident (4 per SM)
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const unsigned resident = (unsigned)(4 * (sms > 0 ? sms : 148));
+                env_rollout_kernel<T, MODE, MISM, kSrcActorTc16><<<blocks < resident ? blocks : resident, kT16Rows, sizeof(ActorTc16Smem), s>>>(sv, rv, ov, nv, tv, p, n);
+            }
             break;
         }
         default: return fail(MR_ERR_ARG, "mr_env_rollout: unknown action source %d", rv.action_source);
