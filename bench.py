@@ -480,6 +480,15 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _static_traffic(key):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic_step_kernel.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_step_kernel.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
 def side_numbers_rank0(args, extras, dev, tdt, noise, peaks, el):
     """BASELINE configs[1], [3], [4], the parity-mode roofline and the SURVEY 8f rows — one GPU, rank 0."""
     import numpy as np
@@ -529,7 +538,8 @@ def side_numbers_rank0(args, extras, dev, tdt, noise, peaks, el):
             "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel": "env_step_tma_kernel<table> (noise rows bulk-copied per tile)",
             "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": b / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP[args.dtype] + 128}}
+                         "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP[args.dtype] + 128,
+                         "traffic": _static_traffic(args.dtype + "_table")}}
         del e, table
     side("parity_mode_table_noise", parity_mode)
 
@@ -566,7 +576,8 @@ def side_numbers_rank0(args, extras, dev, tdt, noise, peaks, el):
         env.check_status()
         extras["config4_actor_in_loop_1000_steps"] = {
             "value": n * 1000 / (ams * 1e-3), "unit": UNIT, "ms_total": ams, "envs": n, "steps": 1000, "launches": 20,
-            "actor": "5-64-BN-ReLU-64-BN-ReLU-2 tanh, fp32, 3xTF32 tcgen05 hidden layer"}
+            "actor": "5-64-BN-ReLU-64-BN-ReLU-2 tanh, fp32 accuracy; both dense layers on tcgen05 (3xFP16 passes, TMEM accumulators), "
+                     "persistent CTAs, 4 per SM"}
     side("config4_actor_in_loop_1000_steps", config4)
 
     # BASELINE configs[3]: GP disturbance model, 2000 training points, 262144 queries (both GPs, mean + std)

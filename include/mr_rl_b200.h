@@ -144,6 +144,14 @@ typedef struct mr_noise {
                                    before a replay); NULL = none */
 } mr_noise;
 
+/* Inspection hook for the generated-noise mode: the first `count` standard normals of the Philox stream of env
+ * env_base + i at env-step `step` — stream_id 0: the step's process noise (its first 8 values are the sufficient
+ * statistics g1x, g2x, g1y, g2y of the RK45 attempt and the four draws of the rebuilt integrator, csrc/mr_core.cuh), 1: the
+ * draws of an (auto) reset in that env-step — written to z_out[count][n] (float32, the generator's precision).  Lets a test
+ * feed the reference's algorithm the draws the kernel used. */
+int mr_philox_normals(uint64_t seed, uint64_t env_base, uint64_t step, int32_t stream_id, int32_t count, int64_t n,
+                      float* z_out, void* stream);
+
 /* *counter = value, stream-ordered (one tiny kernel): the base env-step index of the next graph replay. */
 int mr_counter_set(uint64_t* counter_dev, uint64_t value, void* stream);
 

@@ -157,6 +157,17 @@ static int do_reset(const mr_env_state& st, int64_t n, const Params& p, const mr
 
 __global__ void counter_set_kernel(uint64_t* c, uint64_t v) { *c = v; }
 
+// the standard normals of one Philox stream, in the order PhiloxNoise::next() / draw8() hand them out
+struct KeysOnly { PhiloxKeys keys; };
+__global__ void philox_normals_kernel(KeysOnly k, uint64_t env_base, uint64_t step, uint32_t purpose, int count, int64_t n,
+                                      float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PhiloxNoise nz;
+    nz.seek(env_base + (uint64_t)i, step, purpose);
+    for (int j = 0; j < count; ++j) out[(int64_t)j * n + i] = (float)nz.next(k);
+}
+
 template <class T>
 static int do_rollout(const mr_env_state& st, int64_t n, const Params& p, const mr_noise* nz, const TimeView& tv,
                       const mr_rollout_io& io, const mr_step_out* out, cudaStream_t s) {
@@ -402,6 +413,18 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
     for (cudaError_t e : {ce, j1, j2, j3})
         if (e != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_env_step_host: %s", cudaGetErrorString(e));
     return mr::check_launch("mr_env_step_host");
+}
+
+int mr_philox_normals(uint64_t seed, uint64_t env_base, uint64_t step, int32_t stream_id, int32_t count, int64_t n, float* z_out,
+                      void* stream) {
+    if (!z_out || n < 0 || count < 0 || (stream_id != 0 && stream_id != 1))
+        return mr::fail(MR_ERR_ARG, "mr_philox_normals: bad argument");
+    if (n == 0 || count == 0) return MR_OK;
+    mr::KeysOnly k;
+    mr::philox_make_keys(seed, k.keys);
+    const uint32_t purpose = stream_id == 0 ? mr::kPurposeNoise : mr::kPurposeResetNoise;
+    mr::philox_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(k, env_base, step, purpose, count, n, z_out);
+    return mr::check_launch("mr_philox_normals");
 }
 
 int mr_host_register(void* host_ptr, int64_t bytes) {

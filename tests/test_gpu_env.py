@@ -941,3 +941,58 @@ def test_host_step_reads_a_reused_numpy_array_in_place():
         assert np.array_equal(o1, o2) and np.array_equal(d1, d2)
     assert len(e1._pinned.get("registered", {})) == 1
     del e1
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_generated_noise_kernel_trajectory_parity_with_the_draws_it_used(dt):
+    """Trajectory parity of the BENCHMARKED kernel (tiled TMA kernel, in-kernel Philox): the generated-noise mode draws the
+    sufficient statistics of an RK45 attempt (G1 = sum B_s z_s, G2 = sum E_s z_s through their Cholesky factor) instead
+    of the reference's 12 stage draws.  mr_philox_normals exposes the normals the kernel used; from them a table of
+    reference-order draws with the SAME two sums is built (z_2 and z_6 carry them, the other stage draws are 0) and the C
+    oracle — the reference's algorithm, 16 draws per step from the table — is run on it.  Every env of the batch must
+    then follow the kernel's trajectory: done flags exact, positions 1e-9 (fp64 storage) / 1e-4 (fp32 storage)."""
+    import ctypes as C
+
+    from mr_rl_b200 import _lib as L
+    from oracle import c_oracle
+    n, T, seed, base = 128 * 24, 40, 77, 1000
+    rng = np.random.default_rng(3)
+    init = rng.uniform(100, 120, (n, 2)).astype(np.float32).astype(np.float64)
+    acts = np.stack([rng.uniform(0, 20, (T, n)), rng.uniform(0, 2 * np.pi, (T, n))], -1)
+    if dt is torch.float32:
+        acts = acts.astype(np.float32).astype(np.float64)
+    env = make_env(n, dtype=dt, noise="philox", seed=seed, env_base=base)
+    lib = env.lib
+    zbuf = torch.empty(8, n, dtype=torch.float32, device="cuda:0")
+
+    def normals(step, stream_id, count):
+        L.check(lib.mr_philox_normals(seed, base, step, stream_id, count, n, zbuf.data_ptr(), None), "mr_philox_normals")
+        torch.cuda.synchronize()
+        return zbuf[:count].double().cpu().numpy()
+
+    B2, E2, E6 = 500.0 / 1113.0, 71.0 / 16695.0, 1.0 / 40.0
+    A11, A21, A22 = 0.8641431770614779, -0.05097452091652898, 0.06128032288313894
+    table = np.zeros((n, 4 + 16 * T))
+    table[:, :4] = normals(env._step_index, 1, 4).T                  # the explicit reset below draws from the reset stream
+    env.reset(init=init, noise_var=1.0, a0=1.0)
+    a_dev = torch.as_tensor(acts, device="cuda:0", dtype=dt)
+    xy, dn = [], []
+    for k in range(T):
+        z = normals(env._step_index, 0, 8)                           # g1x, g2x, g1y, g2y, f0x, f0y, f1x, f1y of this step
+        row = table[:, 4 + 16 * k: 4 + 16 * (k + 1)]                 # K1x K1y K2x K2y ... K6x K6y f0x f0y f1x f1y
+        for c, (g1, g2) in enumerate(((z[0], z[1]), (z[2], z[3]))):
+            a = A11 * g1 / B2
+            row[:, 2 + c] = a                                        # stage K2
+            row[:, 10 + c] = (A21 * g1 + A22 * g2 - E2 * a) / E6     # stage K6
+        row[:, 12:16] = z[4:8].T
+        _, _, d, _ = env.step(a_dev[k])
+        xy.append(env.last_pos.double().cpu().numpy().copy()); dn.append(d.cpu().numpy().copy())
+    env.check_status()
+    xy, dn = np.stack(xy), np.stack(dn).astype(bool)
+    ref = c_oracle.rollout(init, acts, 1.0, 1.0, mism=False, mism_at_reset=False, z=table)
+    assert ref["bad"] == 0
+    common = ref["cursor"] == 4 + 16 * T                             # envs that never needed a second RK45 attempt
+    assert common.mean() > 0.99
+    assert np.array_equal(dn[:, common], ref["done"][:, common].astype(bool))
+    err = np.abs(xy - ref["pos"])[:, common] / np.maximum(np.abs(ref["pos"][:, common]), 1.0)
+    assert err.max() < (FP64_TOL if dt is torch.float64 else FP32_TOL)
