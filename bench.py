@@ -204,8 +204,11 @@ def run_ours(args):
 
     strong = args.scaling == "strong"
     n_total = args.envs
-    n = n_total // world if strong else n_total              # envs of this rank
-    base = rank * n                                          # env i lives on rank i // n
+    from mr_rl_b200 import shard_range
+    if strong:
+        base, n = shard_range(n_total, rank, world)          # env i lives on rank i // (n_total / world)
+    else:
+        base, n = rank * n_total, n_total
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
     noise = "philox" if args.sigma != 0 else "none"
     pool = 8
@@ -306,7 +309,8 @@ def run_ours(args):
     barrier()
     env.check_status()
 
-    value = world * n * K / (ms * 1e-3)
+    envs_all = n_total if strong else world * n_total
+    value = envs_all * K / (ms * 1e-3)
     ms_per_step = ms / K
 
     # ---- roofline of the dominant (only) kernel: CUDA-event time per launch ------------------
@@ -352,7 +356,7 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e2e_local)
     # bytes per step over the host link: actions in; obs rows x, y, d and the done byte out (the goal rows are the
     # constant 0 and the reward the constant 10 of MR_env.py:57,89 — written once on the host, never transferred)
-    e2e = {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2 * el,
+    e2e = {"value": envs_all * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2 * el,
            "d2h_bytes_per_step": n * (3 * el + 1), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
            "per_rank_ms_per_step": e2e_rank_ms,
            "api": "VecMREnv.step_host(pinned host actions) -> numpy obs, rew, done (float64 on the wire)"}
@@ -360,14 +364,14 @@ def run_ours(args):
     try:
         np_acts = [a.numpy().copy() for a in host_acts]             # plain (pageable) numpy arrays: + one copy into pinned memory
         ms_np = max_over_ranks(time_host(env, np_acts, e2e_steps))
-        e2e_extra["e2e_numpy_unpinned_input"] = {"value": world * n * e2e_steps / (ms_np * 1e-3), "unit": UNIT,
+        e2e_extra["e2e_numpy_unpinned_input"] = {"value": envs_all * e2e_steps / (ms_np * 1e-3), "unit": UNIT,
                                                  "ms_per_step": ms_np / e2e_steps}
         if args.dtype == "f64":
             env.host_io_dtype = torch.float32                       # float32 on the wire, fp64 state (the 1e-4 tier)
             f32_acts = [a.float().pin_memory() for a in host_acts]
             ms_32 = max_over_ranks(time_host(env, f32_acts, e2e_steps))
             env.host_io_dtype = None
-            e2e_extra["e2e_float32_wire"] = {"value": world * n * e2e_steps / (ms_32 * 1e-3), "unit": UNIT,
+            e2e_extra["e2e_float32_wire"] = {"value": envs_all * e2e_steps / (ms_32 * 1e-3), "unit": UNIT,
                                              "ms_per_step": ms_32 / e2e_steps, "h2d_bytes_per_step": n * 8,
                                              "d2h_bytes_per_step": n * 13}
     except Exception as ex:
@@ -404,7 +408,7 @@ def run_ours(args):
         def direct():
             msd, _, _, _ = timed_steps(env, acts, K, False)
             msd = max_over_ranks(msd) / K
-            extras["same_steps_without_cuda_graph"] = {"value": world * n / (msd * 1e-3), "unit": UNIT, "ms_per_step": msd}
+            extras["same_steps_without_cuda_graph"] = {"value": envs_all / (msd * 1e-3), "unit": UNIT, "ms_per_step": msd}
         side("same_steps_without_cuda_graph", direct)
 
     if not args.no_extras and args.sigma != 0.0:
@@ -414,7 +418,7 @@ def run_ours(args):
             ms0_local, _, _, _ = timed_steps(env0, acts, K, use_graph)
             ms0 = max_over_ranks(ms0_local) / K
             ach0 = bytes_per_launch / (ms0 * 1e-3) / 1e9
-            extras["noise_free_sigma0"] = {"value": world * n / (ms0 * 1e-3), "unit": UNIT, "ms_per_step": ms0,
+            extras["noise_free_sigma0"] = {"value": envs_all / (ms0 * 1e-3), "unit": UNIT, "ms_per_step": ms0,
                                            "roofline": {"bound": "hbm", "achieved": ach0, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                                         "frac": ach0 / peaks["hbm_gbs"]}}
         side("noise_free_sigma0", noise_free)
@@ -425,7 +429,7 @@ def run_ours(args):
             env.want_state_prime = False
             mss = max_over_ranks(mss) / K
             b = (BYTES_PER_ENV_STEP[args.dtype] + 2 * el) * n
-            extras["with_state_prime_rows"] = {"value": world * n / (mss * 1e-3), "unit": UNIT, "ms_per_step": mss,
+            extras["with_state_prime_rows"] = {"value": envs_all / (mss * 1e-3), "unit": UNIT, "ms_per_step": mss,
                                                "bytes_per_env_step": BYTES_PER_ENV_STEP[args.dtype] + 2 * el,
                                                "roofline_frac": b / (mss * 1e-3) / 1e9 / peaks["hbm_gbs"]}
         side("with_state_prime_rows", with_sp)
@@ -441,7 +445,7 @@ def run_ours(args):
             ev1.record()
             torch.cuda.synchronize()
             fms = max_over_ranks(ev0.elapsed_time(ev1)) / reps
-            extras["fused_rollout_k64"] = {"value": world * n * 64 / (fms * 1e-3), "unit": UNIT, "ms_per_launch": fms,
+            extras["fused_rollout_k64"] = {"value": envs_all * 64 / (fms * 1e-3), "unit": UNIT, "ms_per_launch": fms,
                                            "envs_per_gpu": n, "actions": "in-kernel Philox", "sigma": args.sigma}
         side("fused_rollout_k64", fused)
     if not args.no_extras and rank == 0 and world == 1:
@@ -464,7 +468,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "1M batched MR_Env sharded over the GPUs, single-step path (configs[2]), random actions",
-                       "envs_total": world * n, "envs_per_gpu": n, "sigma": args.sigma, "a0": 1.0,
+                       "envs_total": envs_all, "envs_per_gpu": n, "sigma": args.sigma, "a0": 1.0,
                        "noise": "in-kernel Philox4x32-7 + Box-Muller" if args.sigma else "none (sigma=0)",
                        "auto_reset": True, "sharding": f"env i on rank i // {n}, {world} rank(s), no data-path collective",
                        "launch": "CUDA graph of the K single-step launches" if use_graph else "K stream launches",
