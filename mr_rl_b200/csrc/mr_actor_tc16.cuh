@@ -41,7 +41,8 @@ struct alignas(128) ActorTc16Smem {
     __half b2_lo[kActorHidden * kActorHidden];
     __half b1_hi[kActorHidden * 16];           // 2 KB each, B1[n][k]: k = 0, 1, 2 folded W1 rows of x, y, d; k = 3 folded bias
     __half b1_lo[kActorHidden * 16];
-    float4 ep[kActorHidden];                   // epilogue per hidden unit: (s2, t2, w3[j][0], w3[j][1])
+    float4 ep[kActorHidden];                   // epilogue per PAIR of hidden units (j, j+1): ep[j] = (s2_j, s2_j+1, t2_j, t2_j+1),
+                                               //   ep[j+1] = (w3[j][0], w3[j+1][0], w3[j][1], w3[j+1][1])
     float b3[2];
     alignas(8) uint64_t mbar[2];               // completion of the layer-1 / layer-2 MMAs
     uint32_t tmem_base;
@@ -71,6 +72,19 @@ __device__ __forceinline__ void t16_mma(uint32_t tmem_d, uint64_t adesc, uint64_
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kT16Idesc), "r"(accumulate) : "memory");
 }
 
+// Blackwell packed fp32 arithmetic (FFMA2 / FADD2 in SASS): two independent fp32 operations per instruction
+__device__ __forceinline__ float2 t16_fma2(float2 a, float2 b, float2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+        : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)), "l"(*reinterpret_cast<const uint64_t*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 t16_sub2(float2 a, float2 b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const uint64_t*>(&a)), "l"(*reinterpret_cast<const uint64_t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 // (a, b) -> packed fp16 pairs hi and lo with a = hi.x + lo.x, b = hi.y + lo.y to ~2^-22 relative
 __device__ __forceinline__ void t16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -85,8 +99,8 @@ __device__ __forceinline__ void t16_split2(float a, float b, uint32_t& hi, uint3
 // One cvt.relu instead of two FMNMX + cvt per pair; 11 + 11 significand bits, 2^-21 relative like 3xTF32.
 __device__ __forceinline__ void t16_split2_relu(float a, float b, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));       // d = {hi half: first source, lo half: second}
-    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - back.y), "f"(a - back.x));
+    const float2 rem = t16_sub2(make_float2(a, b), __half22float2(*reinterpret_cast<const __half2*>(&hi)));
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rem.y), "f"(rem.x));
 }
 
 // tanh to ~1e-6 relative from one ex2 and one rcp (tanhf's polynomial + exp path is ~25 instructions; the 1e-4 bar on
@@ -166,8 +180,9 @@ __device__ __forceinline__ void actor_tc16_setup(ActorTc16Smem& sm, const float*
     if (tid < kActorHidden) {
         // layer 2: the bias joins t2 because the tensor core produces the bias-free product
         const float s2 = actor[kOffG2 + tid] / sqrtf(actor[kOffV2 + tid] + kBnEps);
-        sm.ep[tid] = make_float4(s2, actor[kOffBe2 + tid] + s2 * (actor[kOffB2 + tid] - actor[kOffM2 + tid]),
-                                 actor[kOffW3 + tid * kActorOut], actor[kOffW3 + tid * kActorOut + 1]);
+        const float t2 = actor[kOffBe2 + tid] + s2 * (actor[kOffB2 + tid] - actor[kOffM2 + tid]);
+        float* e = reinterpret_cast<float*>(sm.ep) + (tid >> 1) * 8 + (tid & 1);   // slot of this unit inside its pair
+        e[0] = s2; e[2] = t2; e[4] = actor[kOffW3 + tid * kActorOut]; e[6] = actor[kOffW3 + tid * kActorOut + 1];
     }
     if (tid < 2) sm.b3[tid] = actor[kOffB3 + tid];
     if (tid < 32) {                                                    // one warp owns the TMEM allocation
@@ -263,20 +278,23 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
     t16_wait(&sm.mbar[1], parity);
 
     // ---- BN + ReLU, 64 x 2 output layer, tanh, action bound ---------------------------------------------------------
-    float o0[2] = {sm.b3[0], 0.f}, o1[2] = {sm.b3[1], 0.f};           // two partial sums each: shorter FMA chains
+    float2 o0 = make_float2(sm.b3[0], 0.f), o1 = make_float2(sm.b3[1], 0.f);   // (even units, odd units) partial sums
 #pragma unroll
     for (int q = 0; q < kActorHidden / 16; ++q) {
         uint32_t r[16];
         t16_ld16(lane_addr + kActorHidden + q * 16, r);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float4 c = sm.ep[q * 16 + j];                        // one broadcast 16-byte read per hidden unit
-            const float y = fmaxf(fmaf(c.x, __uint_as_float(r[j]), c.y), 0.f);
-            o0[j & 1] = fmaf(y, c.z, o0[j & 1]); o1[j & 1] = fmaf(y, c.w, o1[j & 1]);
+        for (int j = 0; j < 16; j += 2) {
+            const float4 bn = sm.ep[q * 16 + j], w3 = sm.ep[q * 16 + j + 1];   // two broadcast 16-byte reads per pair of units
+            float2 y = t16_fma2(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), make_float2(bn.x, bn.y),
+                                make_float2(bn.z, bn.w));
+            y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f);
+            o0 = t16_fma2(y, make_float2(w3.x, w3.y), o0);
+            o1 = t16_fma2(y, make_float2(w3.z, w3.w), o1);
         }
     }
-    act[0] = t16_tanh(o0[0] + o0[1]) * hi0;
-    act[1] = t16_tanh(o1[0] + o1[1]) * hi1;
+    act[0] = t16_tanh(o0.x + o0.y) * hi0;
+    act[1] = t16_tanh(o1.x + o1.y) * hi1;
 }
 
 }  // namespace mr
