@@ -996,3 +996,39 @@ def test_generated_noise_kernel_trajectory_parity_with_the_draws_it_used(dt):
     assert np.array_equal(dn[:, common], ref["done"][:, common].astype(bool))
     err = np.abs(xy - ref["pos"])[:, common] / np.maximum(np.abs(ref["pos"][:, common]), 1.0)
     assert err.max() < (FP64_TOL if dt is torch.float64 else FP32_TOL)
+
+
+@pytest.mark.parametrize("path", ["scalar", "vec", "tma"])
+@pytest.mark.parametrize("kind", ["none", "philox", "table"])
+def test_no_kernel_writes_outside_its_rows(path, kind):
+    """compute-sanitizer is closed on this pool, so the bounds check is our own: every SoA row is allocated with padding
+    behind its n entries (and the rows of one tensor sit back to back); the padding is filled with sentinels and must be
+    untouched after single steps (tiles + vector part + scalar tail: n = 5 * 128 + 37), resets, fused rollouts with episode
+    recording and the host-buffer step, for every kernel variant and noise mode, both storage types."""
+    from mr_rl_b200 import _lib as L
+    n, T = 128 * 5 + 37, 5
+    rng = np.random.default_rng(1)
+    acts = torch.as_tensor(np.stack([rng.uniform(0, 20, (T, n)), rng.uniform(0, 6.28, (T, n))], -1), device="cuda:0")
+    z = rng.standard_normal((40 * T + 8, n))
+    try:
+        L.set_step_path(path)
+        for dt in (torch.float64, torch.float32):
+            env = make_env(n, dtype=dt, noise=kind, auto_reset=True, **({"noise_table": z} if kind == "table" else {}))
+            env.max_timesteps = 3
+            pad = env._np - n
+            assert pad > 0
+            rows = {"state": env._state, "obs": env._obs, "sp": env._sp, "rew": env._rew, "done": env._done,
+                    "counter": env._counter, "cursor": env._cursor, "status": env._status}
+            for t in rows.values():
+                t[..., n:] = 77
+            env.reset(init=None, noise_var=0.0 if kind == "none" else 1.0, a0=1.0)
+            for k in range(T):
+                env.step(acts[k].to(dt))
+            env.rollout(actions=acts.to(dt), record_episodes=True)
+            env.rollout(policy="random", k_steps=4)
+            env.step_host(acts[0].to(dt).cpu().numpy())
+            torch.cuda.synchronize()
+            for name, t in rows.items():
+                assert bool((t[..., n:] == 77).all()), (name, path, kind, dt)
+    finally:
+        L.set_step_path("default")
