@@ -700,14 +700,19 @@ class StepGraph:
                             L.check(rc, "mr_env_step (graph capture)")
                 finally:
                     nz.offset_dev = None
-        # the simulator parameters are baked into the captured launches
-        self._baked = (env.params.a0, env.params.noise_var, env.params.is_mismatched, env.params.auto_reset)
+        # the launch parameters are baked into the captured kernel nodes
+        self._baked = self._param_key()
+
+    def _param_key(self):
+        p = self.env.params
+        return (p.a0, p.noise_var, p.is_mismatched, p.auto_reset, p.max_timesteps, p.min_dist2goal, p.reward_mode,
+                p.bound_xy, p.bound_d, tuple(p.init_low), tuple(p.init_high), self.env.want_state_prime)
 
     def replay(self):
         """Run the K captured steps; returns the views (obs, rew, done, info) after the last one."""
         env = self.env
-        if self._baked != (env.params.a0, env.params.noise_var, env.params.is_mismatched, env.params.auto_reset):
-            raise RuntimeError("simulator parameters changed since the graph was captured: capture again")
+        if self._baked != self._param_key():
+            raise RuntimeError("env parameters changed since the graph was captured: capture again")
         with torch.cuda.device(env.device):
             rc = env.lib.mr_counter_set(self._ctr.data_ptr(), env._step_index, env._stream())
             if rc:
