@@ -578,7 +578,19 @@ def side_numbers_rank0(args, extras, dev, tdt, noise, peaks, el):
         torch.cuda.synchronize()
         ams = ev0.elapsed_time(ev1)
         env.check_status()
+        # torch-CPU fp32 forward of the same MLP on the box's host cores (a reported baseline)
+        from mr_rl_b200.actor import torch_reference
+        params = init_actor(0)
+        obs_cpu = np.zeros((65536, 5), np.float32)
+        obs_cpu[:, :2] = np.random.default_rng(0).uniform(100, 120, (65536, 2))
+        obs_cpu[:, 4] = np.hypot(obs_cpu[:, 0], obs_cpu[:, 1])
+        torch_reference(params, obs_cpu)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            torch_reference(params, obs_cpu)
+        t_cpu = (time.perf_counter() - t0) / 5
         extras["config4_actor_in_loop_1000_steps"] = {
+            "cpu_torch_actor_forwards_per_s": 65536 / t_cpu, "cpu_threads": torch.get_num_threads(),
             "value": n * 1000 / (ams * 1e-3), "unit": UNIT, "ms_total": ams, "envs": n, "steps": 1000, "launches": 20,
             "actor": "5-64-BN-ReLU-64-BN-ReLU-2 tanh, fp32 accuracy; both dense layers on tcgen05 (3xFP16 passes, TMEM accumulators), "
                      "persistent CTAs, 4 per SM"}
@@ -616,7 +628,22 @@ def side_numbers_rank0(args, extras, dev, tdt, noise, peaks, el):
         torch.cuda.synchronize()
         t_spec_build = (time.perf_counter() - t0) * 1e3
         spec = both(True)
+        # sklearn's GPR.predict on the box's host cores, 4096 of the queries (it is linear in the query count)
+        from sklearn.gaussian_process import GaussianProcessRegressor
+        from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+        gpr = GaussianProcessRegressor(kernel=RBF(0.2) + WhiteKernel(0.008), optimizer=None, alpha=1e-10).fit(X[:, None], yx)
+        qs = q[:4096].cpu().numpy()[:, None]
+        gpr.predict(qs[:256], return_std=True)
+        t0 = time.perf_counter()
+        gpr.predict(qs, return_std=True)
+        t_sk_std = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        gpr.predict(qs)
+        t_sk_mean = time.perf_counter() - t0
         extras["config3_gp_262k_queries_2k_train"] = {
+            "cpu_sklearn": {"sample": "GaussianProcessRegressor.predict, one GP, 4096 queries x 2000 training points, default BLAS threads",
+                            "cores": os.cpu_count(), "mean_std_queries_per_s_per_gp": 4096 / t_sk_std,
+                            "mean_only_queries_per_s_per_gp": 4096 / t_sk_mean},
             "reference_algorithm_triangular_ms_both_gps": tri, "spectral_ms_both_gps": spec, "mean_only_ms_both_gps": mean_only,
             "queries_per_s_triangular": 262144 / (tri * 1e-3), "queries_per_s_spectral": 262144 / (spec * 1e-3),
             "triangular_tflops_fp64": 2 * (262144 * 2048.0 * 2048 / 2 * 2) / (tri * 1e-3) / 1e12,
