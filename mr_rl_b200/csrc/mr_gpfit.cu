@@ -54,6 +54,57 @@ __global__ void gp_build_k_kernel(const double* __restrict__ x, int n_train, int
 constexpr int DIAG_THREADS = 256;
 constexpr size_t kDiagSmemBytes = ((size_t)NB * DIAG_LD + 2 * NB + 2 * NB) * sizeof(double);
 
+// The 16 steps j = 16 JT .. 16 JT + 15 of the loop described above.  JT (the 16-wide tile that holds column / row j) is a
+// template parameter: which register tiles a step touches, which rows are finished and where the unit entry sits are
+// then decided at compile time, and the step is straight-line FMAs on the register tile.  (Round 1 kept j fully dynamic:
+// 2060 warp-instructions per step, 12 % of them DFMA — profiles/r01_ncu_gpfit_chol_diag.txt; same arithmetic in the same
+// order here, so the results are bit-identical.)
+template <int JT>
+__device__ __forceinline__ void chol_diag_publish(double (&X)[8][8], double* sL, double* sV, int jl, int tx, int ty) {
+    // exchange values for step j = 16 JT + jl; column j leaves the trailing matrix
+    const int j = 16 * JT + jl;
+    double* v = sV + (j & 1) * NB;
+    if (tx == jl) {
+#pragma unroll
+        for (int a = JT; a < 8; ++a) {
+            const int r = ty + 16 * a;
+            if (a > JT || ty >= jl) { v[r] = X[a][JT]; sL[r * DIAG_LD + j] = X[a][JT]; X[a][JT] = r == j ? 1.0 : 0.0; }
+        }
+    }
+    if (ty == jl) {
+#pragma unroll
+        for (int b = 0; b <= JT; ++b) {
+            const int c = tx + 16 * b;
+            if (b < JT || tx < jl) v[c] = X[JT][b];
+        }
+    }
+}
+
+template <int JT>
+__device__ __forceinline__ void chol_diag_steps(double (&X)[8][8], double* sL, double* sV, int tx, int ty, bool in_lower) {
+#pragma unroll 1
+    for (int jl = 0; jl < 16; ++jl) {
+        const int j = 16 * JT + jl;
+        const double* v = sV + (j & 1) * NB;
+        const double inv_p = 1.0 / v[j];
+        double vc[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) vc[b] = v[tx + 16 * b];
+        if (tx == jl) vc[JT] = 1.0;                   // c == j
+#pragma unroll
+        for (int a = JT; a < 8; ++a) {                // rows of tiles a < JT are finished
+            const int r = ty + 16 * a;
+            const double lr = (a > JT || ty > jl) ? -(v[r] * inv_p) : 0.0;      // rows <= j: a multiply by zero, no branch
+#pragma unroll
+            for (int b = 0; b < a; ++b) X[a][b] = fma(lr, vc[b], X[a][b]);
+            X[a][a] = fma(lr, in_lower ? vc[a] : 0.0, X[a][a]);
+        }
+        if (jl < 15) chol_diag_publish<JT>(X, sL, sV, jl + 1, tx, ty);
+        else if constexpr (JT < 7) chol_diag_publish<JT + 1>(X, sL, sV, 0, tx, ty);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(DIAG_THREADS)
 chol_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ M /*[128][128]*/, int* __restrict__ info) {
     extern __shared__ __align__(16) double sm[];
@@ -71,54 +122,13 @@ chol_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ M 
             const int r = ty + 16 * a, c = tx + 16 * b;
             X[a][b] = c <= r ? Ablk[(int64_t)r * ld + c] : 0.0;     // tiles above the diagonal (b > a) are never used
         }
-    // the tile index of column / row j is CTA-uniform, so only one of the eight bodies below runs per step
-    auto publish = [&](int j) {                   // exchange values for step j; column j leaves the trailing matrix
-        double* v = sV + (j & 1) * NB;
-        const int jt = j >> 4, jl = j & 15;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            if (b != jt) continue;
-            if (tx == jl) {
-#pragma unroll
-                for (int a = b; a < 8; ++a) {
-                    const int r = ty + 16 * a;
-                    if (r >= j) { v[r] = X[a][b]; sL[r * DIAG_LD + j] = X[a][b]; X[a][b] = r == j ? 1.0 : 0.0; }
-                }
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            if (a != jt) continue;
-            if (ty == jl) {
-#pragma unroll
-                for (int b = 0; b <= a; ++b) {
-                    const int c = tx + 16 * b;
-                    if (c < j) v[c] = X[a][b];
-                }
-            }
-        }
-    };
     const bool in_lower = tx <= ty;               // inside a diagonal tile: column <= row
-    publish(0);
+    chol_diag_publish<0>(X, sL, sV, 0, tx, ty);
     __syncthreads();
-    for (int j = 0; j < NB; ++j) {
-        const double* v = sV + (j & 1) * NB;
-        const double inv_p = 1.0 / v[j];
-        double vc[8];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { const int c = tx + 16 * b; vc[b] = c == j ? 1.0 : v[c]; }
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            if (16 * a + 15 <= j) continue;       // CTA-uniform: these rows are finished
-            const int r = ty + 16 * a;
-            const double lr = r > j ? -(v[r] * inv_p) : 0.0;      // rows <= j: a multiply by zero, no branch
-#pragma unroll
-            for (int b = 0; b < a; ++b) X[a][b] = fma(lr, vc[b], X[a][b]);
-            X[a][a] = fma(lr, in_lower ? vc[a] : 0.0, X[a][a]);
-        }
-        if (j + 1 < NB) publish(j + 1);
-        __syncthreads();
-    }
+    chol_diag_steps<0>(X, sL, sV, tx, ty, in_lower); chol_diag_steps<1>(X, sL, sV, tx, ty, in_lower);
+    chol_diag_steps<2>(X, sL, sV, tx, ty, in_lower); chol_diag_steps<3>(X, sL, sV, tx, ty, in_lower);
+    chol_diag_steps<4>(X, sL, sV, tx, ty, in_lower); chol_diag_steps<5>(X, sL, sV, tx, ty, in_lower);
+    chol_diag_steps<6>(X, sL, sV, tx, ty, in_lower); chol_diag_steps<7>(X, sL, sV, tx, ty, in_lower);
     if (threadIdx.x < NB) {
         const double p = sL[threadIdx.x * DIAG_LD + threadIdx.x];
         const double d = sqrt(p);
