@@ -255,31 +255,38 @@ class DDPGLearner:
 
 
 def train(env, learner, actor_noise, buffer_size=10000, min_batch=64, steps=1000, updates_per_step=1, replay=None,
-          noise_var=1, a0=1, log_every=0):
+          noise_var=1, a0=1, log_every=0, stale_state_warmup=False):
     """train() (:233-323) for a vectorised env: every iteration all N envs act with mu(s) + OU noise, the N transitions
     enter the ring, and once it holds ``min_batch`` transitions the learner takes ``updates_per_step`` updates.  ``env``
     is a VecMREnv built with auto_reset=True (an env that ends starts its next episode inside the same launch, the
     reference's ``break`` + ``env.reset()``).  Returns per-iteration (mean reward, critic loss, mean Q) as a numpy array.
-    Differences from the scalar loop, all forced by vectorisation: N transitions per iteration instead of one, and the
-    reference's stale-state quirk during warm-up (``state`` is not advanced while the buffer is short, :281-284) is not
-    reproduced."""
+    Forced by vectorisation: N transitions per iteration instead of one.
+    ``stale_state_warmup=True`` reproduces the scalar loop's warm-up quirk: while the buffer holds fewer than
+    ``min_batch`` transitions the loop ``continue``s before ``state = next_state`` (:281-284), so the policy keeps seeing —
+    and the buffer keeps storing as ``s`` — the observation of the last reset, while the env itself moves on.  With
+    N >= min_batch envs the buffer is full after the first iteration and the flag changes nothing."""
     n = env.num_envs
     replay = replay if replay is not None else ReplayBuffer(buffer_size, 0, device=env.device)
     obs_rows = env._obs
     env.reset(noise_var=noise_var, a0=a0)
-    prev = obs_rows.clone()
+    state = obs_rows.clone()                       # the loop's `state`: policy input and the stored s
     log = torch.zeros(steps, 3, dtype=torch.float64, device=env.device)
     for it in range(steps):
-        actions = learner.predict(obs_rows, n)
+        actions = learner.predict(state, n)
         actor_noise.add_to(actions)
-        prev.copy_(obs_rows)
         _, rew, done, _ = env.step(actions)
-        replay.add(prev, actions, rew, done, obs_rows, n)
+        replay.add(state, actions, rew, done, obs_rows, n)
         log[it, 0] = rew[:n].mean()
         if replay.size() >= min_batch:
             for _ in range(updates_per_step):
                 info = learner.update(replay, min_batch)
             log[it, 1:] = info.double()
+            state.copy_(obs_rows)                  # state = next_state (:307)
+        elif stale_state_warmup:
+            ended = done[:n].bool()                # `break` -> env.reset() -> a fresh state; everyone else keeps the stale one
+            state[:, :n][:, ended] = obs_rows[:, :n][:, ended]
+        else:
+            state.copy_(obs_rows)
         if log_every and (it + 1) % log_every == 0:
             row = log[it].cpu().numpy()
             print(f"iter {it + 1}/{steps}: mean reward {row[0]:.3f} critic loss {row[1]:.4g} mean Q {row[2]:.4g}")

@@ -193,6 +193,31 @@ def test_vectorised_training_loop_runs_and_learns_something(dt):
     assert np.all(rb.r.cpu().numpy() == 10.0) and set(np.unique(rb.d.cpu().numpy())) <= {0.0, 1.0}
 
 
+def test_training_loop_reproduces_the_reference_warmup_quirk():
+    """RL/MR_ddpg.py:281-284: while the buffer holds fewer than min_batch transitions the loop `continue`s before
+    `state = next_state`, so the stored state `s` (and the policy input) stays the observation of the last reset while the
+    env moves on.  stale_state_warmup=True reproduces it; the default advances the state every iteration."""
+    from mr_rl_b200 import VecMREnv
+    from mr_rl_b200.ddpg import DDPGLearner, OUNoise, ReplayBuffer, train
+    n, min_batch = 2, 12
+    for stale in (True, False):
+        env = VecMREnv(n, device="cuda:0", noise="philox", seed=5, auto_reset=True)
+        rb = ReplayBuffer(1000, 0, device="cuda:0")
+        train(env, DDPGLearner(device="cuda:0", seed=0), OUNoise(n, device="cuda:0"), min_batch=min_batch, steps=8, replay=rb,
+              stale_state_warmup=stale)
+        s, s2 = rb.s.cpu().numpy(), rb.s2.cpu().numpy()
+        reset_obs = s[:n]
+        warm = min_batch // n                                  # iterations whose transitions are stored before the first update
+        if stale:
+            for it in range(warm):
+                assert np.array_equal(s[it * n:(it + 1) * n], reset_obs), it
+            assert np.array_equal(s[warm * n:(warm + 1) * n], s2[(warm - 1) * n:warm * n])   # then state = next_state
+        else:
+            for it in range(1, warm + 1):
+                assert np.array_equal(s[it * n:(it + 1) * n], s2[(it - 1) * n:it * n]), it
+            assert not np.array_equal(s[n:2 * n], reset_obs)
+
+
 def test_replay_ring_keeps_what_the_reference_deque_keeps():
     """The same 11 transitions pushed through RL/MR_ddpg.py's ReplayBuffer(8) (golden ddpg_host.npz) and through the
     device ring: the same transitions survive the overflow, the size saturates at the capacity."""
