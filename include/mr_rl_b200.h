@@ -179,8 +179,9 @@ int mr_abi_version(void);
 const char* mr_last_error(void);
 void mr_default_params(mr_sim_params* p);
 
-/* Tuning / test hook: force the kernel variant of mr_env_step.  0 = default choice, 1 = plain TMA kernel, 2 = 16-byte
- * vector kernel, 3 = scalar kernel, 4 = warp-specialised TMA kernel where it applies.  Every variant computes the same
+/* Tuning / test hook: force the kernel variant of mr_env_step.  0 = default choice (tiled TMA kernel, 2-D tensor maps where
+ * the rows are equally strided), 1 = tiled TMA kernel with 1-D bulk copies only, 2 = 16-byte vector kernel, 3 = scalar
+ * kernel, 4 = warp-specialised TMA kernel where it applies, 5 = same as 0.  Every variant computes the same
  * results (tested); returns the previous setting, or MR_ERR_ARG.  Initial value: environment variable MR_STEP_PATH
  * (tma | vec | scalar | ws).  Process-wide, not thread-safe against concurrent launches. */
 int mr_set_step_path(int32_t path);

@@ -208,7 +208,7 @@ def load():
     return lib
 
 
-STEP_PATHS = {"default": 0, "tma": 1, "vec": 2, "scalar": 3, "ws": 4}
+STEP_PATHS = {"default": 0, "tma": 1, "vec": 2, "scalar": 3, "ws": 4, "tmap": 5}   # tma: 1-D bulk copies only; tmap = default
 
 
 def set_step_path(name):

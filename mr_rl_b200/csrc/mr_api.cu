@@ -15,6 +15,7 @@ thread_local char g_err[512] = "";
 static int step_path_from_env() {
     const char* e = getenv("MR_STEP_PATH");
     if (!e) return 0;
+    if (e[0] == 't' && e[1] == 'm' && e[2] == 'a' && e[3] == 'p') return 5;
     return e[0] == 't' ? 1 : e[0] == 'v' ? 2 : e[0] == 's' ? 3 : e[0] == 'w' ? 4 : 0;
 }
 int g_step_path = step_path_from_env();
@@ -85,6 +86,78 @@ static NoiseView noise_view(const mr_noise* nz, int64_t n) {
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+// ---- 2-D TMA tensor maps ------------------------------------------------------------------------------------------
+using TmapEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {       // cuTensorMapEncodeTiled through the runtime (no libcuda link)
+    static const TmapEncodeFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) { cudaGetLastError(); ptr = nullptr; }
+        return (TmapEncodeFn)ptr;
+    }();
+    return fn;
+}
+
+struct TmapKey { const void* base; uint64_t cols, rows, stride; uint32_t box_cols, box_rows; int dt; };
+struct TmapSlot { TmapKey key; CUtensorMap map; bool used; };
+static bool tmap_2d(CUtensorMap& out, int dt /*0 f64, 1 f32*/, const void* base, uint64_t cols, uint64_t rows, uint64_t stride_bytes,
+                    uint32_t box_cols, uint32_t box_rows) {
+    if (!base || !aligned16(base) || (stride_bytes & 15u) || cols == 0 || rows == 0 || box_cols > 256 || box_rows > 256) return false;
+    const TmapEncodeFn enc = tmap_encoder();
+    if (!enc) return false;
+    // the same few tensors are stepped over and over: a tiny per-thread cache keeps the encoder off the launch path
+    thread_local TmapSlot cache[16] = {};
+    thread_local int next = 0;
+    const TmapKey k{base, cols, rows, stride_bytes, box_cols, box_rows, dt};
+    for (const TmapSlot& c : cache)
+        if (c.used && memcmp(&c.key, &k, sizeof(k)) == 0) { out = c.map; return true; }
+    cudaPointerAttributes pa;              // tensor maps over device memory only (host-mapped rows keep the 1-D copies)
+    if (cudaPointerGetAttributes(&pa, base) != cudaSuccess || pa.type != cudaMemoryTypeDevice) { cudaGetLastError(); return false; }
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstr[1] = {stride_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t es[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, dt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim,
+                           gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    TmapSlot& slot = cache[next];
+    next = (next + 1) % 16;
+    memset(&slot.key, 0, sizeof(slot.key));
+    slot.key = k; slot.map = m; slot.used = true;
+    out = m;
+    return true;
+}
+
+template <class T>
+bool build_step_maps(StepMaps& m, const StateView<T>& sv, const OutView<T>& ov, const NoiseView& nv, int64_t n, int tile,
+                     int table_rows) {
+    memset(&m, 0, sizeof(m));
+    const int dt = sizeof(T) == 8 ? 0 : 1;
+    const ptrdiff_t stride = (const char*)sv.y - (const char*)sv.x;       // x, y, fx, fy, h equally strided?
+    if (stride <= 0 || (const char*)sv.fx - (const char*)sv.y != stride || (const char*)sv.fy - (const char*)sv.fx != stride ||
+        (const char*)sv.h - (const char*)sv.fy != stride || stride < (ptrdiff_t)(n * sizeof(T)))
+        return false;
+    if (!tmap_2d(m.state, dt, sv.x, (uint64_t)n, 5, (uint64_t)stride, (uint32_t)tile, 5)) return false;
+    const int dt_out = (sizeof(T) == 8 && !ov.f32) ? 0 : 1;
+    const uint64_t el_out = dt_out == 0 ? 8 : 4;
+    if (ov.obs && !tmap_2d(m.obs, dt_out, ov.obs, (uint64_t)n, 5, (uint64_t)ov.stride * el_out, (uint32_t)tile, 2)) return false;
+    if (ov.sp && !tmap_2d(m.sp, dt_out, ov.sp, (uint64_t)n, 2, (uint64_t)ov.stride * el_out, (uint32_t)tile, 2)) return false;
+    if (table_rows > 0) {
+        if (nv.table_col0 != 0) return false;
+        if (!tmap_2d(m.table, 0, nv.table, (uint64_t)nv.table_stride, (uint64_t)nv.table_len, (uint64_t)nv.table_stride * 8,
+                     (uint32_t)tile, (uint32_t)table_rows))
+            return false;
+    }
+    return true;
+}
+template bool build_step_maps<double>(StepMaps&, const StateView<double>&, const OutView<double>&, const NoiseView&, int64_t, int, int);
+template bool build_step_maps<float>(StepMaps&, const StateView<float>&, const OutView<float>&, const NoiseView&, int64_t, int, int);
 
 // every row the vectorised step kernel touches must start on a 16-byte boundary
 template <class T>
@@ -196,7 +269,7 @@ int mr_abi_version(void) { return MR_ABI_VERSION; }
 const char* mr_last_error(void) { return mr::g_err; }
 
 int mr_set_step_path(int32_t path) {
-    if (path < 0 || path > 4) return mr::fail(MR_ERR_ARG, "mr_set_step_path: path must be 0..4");
+    if (path < 0 || path > 5) return mr::fail(MR_ERR_ARG, "mr_set_step_path: path must be 0..5");
     const int old = mr::g_step_path;
     mr::g_step_path = path;
     return old;

@@ -1,5 +1,6 @@
 // Shared device-side views and helpers of the env kernels (step / reset / rollout).
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>   // header-only: ranges cost a pointer test unless a profiler is attached
 
@@ -80,6 +81,20 @@ __device__ __forceinline__ uint64_t step_offset(const NoiseView& nv) {
 }
 
 struct TimeView { const double* t; int len; };
+
+// 2-D TMA tensor maps of the step kernel (csrc/mr_step_tma.cuh): the SoA rows of one tensor are equally strided, so the
+// rows a tile needs form a {kTile x rows} box that ONE cp.async.bulk.tensor instruction moves — the five state rows,
+// obs rows (x, y) / (goal_x, goal_y), the two state_prime rows, the 16 / 24 noise-table rows of the tile.
+struct StepMaps {
+    CUtensorMap state;      // [5][n]      x, y, fx, fy, h          box {kTile, 5}
+    CUtensorMap obs;        // [5][n]      x, y, gx, gy, d          box {kTile, 2}
+    CUtensorMap sp;         // [2][n]      state_prime              box {kTile, 2}
+    CUtensorMap table;      // [L][n]      noise table (fp64)       box {kTile, 16 | 24}
+};
+// Fills `m` for this call (maps are cached by geometry); false if the rows are not equally strided / aligned.
+template <class T>
+bool build_step_maps(StepMaps& m, const StateView<T>& sv, const OutView<T>& ov, const NoiseView& nv, int64_t n, int tile,
+                     int table_rows);
 
 __device__ __forceinline__ double time_at(const TimeView& tv, int c, double dt) {
     if (c < tv.len) return __ldg(tv.t + c);

@@ -264,12 +264,13 @@ static int sm_count(int dev) {
 // kernel choice override (tuning / A-B measurements / tests): mr_set_step_path(), initialised from the environment
 // variable MR_STEP_PATH=tma|ws|vec|scalar ("tma" = the plain TMA kernel also where the warp-specialised one would be
 // picked, "ws" = the default choice)
+// (5 = "tmap": same as the default choice; 1 = "tma": 1-D bulk copies only)
 static int step_path_override() { return g_step_path; }
 
-template <class T, class K>
+template <class T, class K, class... Extra>
 static void launch_persistent(K kernel, int threads, size_t smem, int* ctas_per_sm, int64_t n_tiles, cudaStream_t s,
                               const StateView<T>& sv, const T* act, const OutView<T>& ov, const NoiseView& nv,
-                              const TimeView& tv, const Params& p, int64_t n) {
+                              const TimeView& tv, const Params& p, int64_t n, const Extra&... extra) {
     const int dev = current_device();
     if (!ctas_per_sm[dev]) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -286,7 +287,7 @@ static void launch_persistent(K kernel, int threads, size_t smem, int* ctas_per_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous tail
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, sv, act, ov, nv, tv, p, n_tiles, n);
+    cudaLaunchKernelEx(&cfg, kernel, sv, act, ov, nv, tv, p, n_tiles, n, extra...);
 }
 
 template <class T, int MODE, bool MISM>
@@ -304,7 +305,7 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
     auto act_at = [&](int64_t env) { return act32 ? (const T*)((const float*)act + 2 * env) : act + 2 * env; };
     {
         constexpr int kTile = TileOf<T>::value;
-        if (vec_ok && n >= kTile && (force == 0 || force == 1 || force == 4)) {
+        if (vec_ok && n >= kTile && (force == 0 || force == 1 || force == 4 || force == 5)) {
             // Blackwell path: persistent CTAs, TMA bulk copies through shared memory
             const int64_t n_tiles = n / kTile;
             static int ctas_per_sm[kMaxDevices] = {};      // per template instantiation and device
@@ -315,10 +316,21 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
                 if (ws) launch_persistent<T>(env_step_tma_ws_kernel<T>, WsCfg<T>::kThreads, sizeof(StepSmemWs<T>), ctas_ws,
                                              n_tiles, s, sv, act, ov, nv, tv, p, n);
             }
-            if (!ws) launch_persistent<T>(env_step_tma_kernel<T, MODE, MISM>, kTile, sizeof(StepSmem<T, MODE, MISM>), ctas_per_sm,
-                                          n_tiles, s, sv, act, ov, nv, tv, p, n);
+            if (!ws) {
+                // 2-D tensor maps for the equally strided rows (state, obs pairs, state_prime, noise table) when the
+                // buffers allow it, else one 1-D bulk copy per row; force == 1 ("tma") keeps the 1-D form for A/B runs
+                static int ctas_tmap[kMaxDevices] = {};
+                StepMaps maps;
+                const bool tmap = force != 1 && build_step_maps<T>(maps, sv, ov, nv, n, kTile, NoiseRows<MODE, MISM>::value);
+                if (tmap)
+                    launch_persistent<T>(env_step_tma_kernel<T, MODE, MISM, true>, kTile, sizeof(StepSmem<T, MODE, MISM>), ctas_tmap,
+                                         n_tiles, s, sv, act, ov, nv, tv, p, n, maps);
+                else
+                    launch_persistent<T>(env_step_tma_kernel<T, MODE, MISM, false>, kTile, sizeof(StepSmem<T, MODE, MISM>), ctas_per_sm,
+                                         n_tiles, s, sv, act, ov, nv, tv, p, n, maps);
+            }
             done = n_tiles * kTile;
-        } else if (vec_ok && !act32 && n >= VEC && force != 3 && force != 1 && force != 4) {
+        } else if (vec_ok && !act32 && n >= VEC && force != 3 && force != 1 && force != 4 && force != 5) {
             if constexpr (MODE != MR_NOISE_TABLE) {        // (the table mode has the tiled kernel and the scalar one)
                 const int64_t n_vec = (n / VEC) * VEC;
                 launch_step_range<T, VEC, MODE, MISM>(sv, act, ov, nv, tv, p, n_vec, s);

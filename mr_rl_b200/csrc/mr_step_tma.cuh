@@ -77,6 +77,15 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+// 2-D tensor-map forms (UTMALDG / UTMASTG): one instruction moves a {box_cols x box_rows} box of a strided 2-D tensor
+__device__ __forceinline__ void tensor_load_2d(void* smem_dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap* map, int32_t c0, int32_t c1, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -154,7 +163,7 @@ struct StepSmem {
     TileOut<T, kTile> out[kStagesOut];
     TileNoiseIn<kTile, NoiseRows<MODE, MISM>::value> nin[kIn];
     TileNoiseOut<kTile, NoiseRows<MODE, MISM>::value> nout[kStagesOut];
-    alignas(128) T zero[kTile];
+    alignas(128) T zero[2 * kTile];         // the two goal rows as one {kTile x 2} box
     alignas(16) float4 zpre[(MR_RNG_PREFETCH && MODE == MR_NOISE_PHILOX && !MISM) ? 2 * kTile : 1];   // next tile's normals
     alignas(8) uint64_t full[kIn];
 };
@@ -175,10 +184,14 @@ template <class T, int MODE> struct TmaMinCtas {
     static constexpr int value = MODE == MR_NOISE_TABLE ? 1 : TmaWarps<T>::value * 32 / TileOf<T>::value;
 };
 
-template <class T, int MODE, bool MISM>
+// TMAP: the equally strided rows of one tensor move as 2-D tensor-map boxes (one instruction for the five state rows, the
+// obs (x, y) pair, the goal pair, the state_prime pair, the tile's 16 / 24 noise-table rows) instead of one 1-D bulk copy
+// per row: 8-9 copy instructions per tile instead of 19-20 (table mode 10 instead of 36), all issued by one thread that
+// also integrates an env, i.e. by the warp every other warp of the CTA waits for at the tile's two barriers.
+template <class T, int MODE, bool MISM, bool TMAP>
 __global__ void __launch_bounds__(TileOf<T>::value, TmaMinCtas<T, MODE>::value)
 env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> out, NoiseView nv, TimeView tv,
-                    Params p, int64_t n_tiles, int64_t n_total) {
+                    Params p, int64_t n_tiles, int64_t n_total, const __grid_constant__ StepMaps maps) {
     constexpr int kTile = TileOf<T>::value;
     constexpr int kSI = StagesIn<MODE>::value;
     constexpr int kNR = NoiseRows<MODE, MISM>::value;
@@ -193,7 +206,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
         for (int s = 0; s < kSI; ++s) mbar_init(&sm.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    sm.zero[tid] = (T)0;   // kTile threads
+    sm.zero[tid] = (T)0; sm.zero[kTile + tid] = (T)0;   // kTile threads
     fence_async_smem();
     __syncthreads();
     // Programmatic dependent launch: everything above (smem carve-up, mbarrier init) overlaps the tail of
@@ -230,18 +243,27 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
             rows = rows < 0 ? 0 : (rows > kNR ? kNR : rows);
             if (cbase < 0) rows = 0;
             sm.nin[s].base = cbase; sm.nin[s].rows = (int32_t)rows;
-            mbar_expect_tx(bar, kInBytes + kTile * 4 + (uint32_t)rows * kTile * 8);
+            if constexpr (TMAP) {           // one box; rows past the end of the table arrive zero-filled and are never read
+                mbar_expect_tx(bar, kInBytes + kTile * 4 + (uint32_t)kNR * kTile * 8);
+                tensor_load_2d(sm.nin[s].z, &maps.table, (int32_t)i0, cbase < 0 ? 0 : cbase, bar);
+            } else {
+                mbar_expect_tx(bar, kInBytes + kTile * 4 + (uint32_t)rows * kTile * 8);
+                const double* src = nv.table + (int64_t)cbase * nv.table_stride + nv.table_col0 + i0;
+                for (int k = 0; k < (int)rows; ++k) bulk_load(sm.nin[s].z[k], src + (int64_t)k * nv.table_stride, kTile * 8, bar);
+            }
             bulk_load(sm.nin[s].cursor, st.cursor + i0, kTile * 4, bar);
-            const double* src = nv.table + (int64_t)cbase * nv.table_stride + nv.table_col0 + i0;
-            for (int k = 0; k < (int)rows; ++k) bulk_load(sm.nin[s].z[k], src + (int64_t)k * nv.table_stride, kTile * 8, bar);
         } else {
             if (warp == 0) mbar_expect_tx(bar, kInBytes);
         }
-        if (warp == 0 % kWarps) bulk_load(b.x, st.x + i0, kRow, bar);
-        if (warp == 1 % kWarps) bulk_load(b.y, st.y + i0, kRow, bar);
-        if (warp == 2 % kWarps) bulk_load(b.fx, st.fx + i0, kRow, bar);
-        if (warp == 3 % kWarps) bulk_load(b.fy, st.fy + i0, kRow, bar);
-        if (warp == 4 % kWarps) bulk_load(b.h, st.h + i0, kRow, bar);
+        if constexpr (TMAP) {
+            tensor_load_2d(b.x, &maps.state, (int32_t)i0, 0, bar);               // x, y, fx, fy, h
+        } else {
+            if (warp == 0 % kWarps) bulk_load(b.x, st.x + i0, kRow, bar);
+            if (warp == 1 % kWarps) bulk_load(b.y, st.y + i0, kRow, bar);
+            if (warp == 2 % kWarps) bulk_load(b.fx, st.fx + i0, kRow, bar);
+            if (warp == 3 % kWarps) bulk_load(b.fy, st.fy + i0, kRow, bar);
+            if (warp == 4 % kWarps) bulk_load(b.h, st.h + i0, kRow, bar);
+        }
         if (warp == 5 % kWarps)
             bulk_load(b.act, act32 ? (const void*)(reinterpret_cast<const float*>(actions) + 2 * i0) : (const void*)(actions + 2 * i0),
                       act_bytes, bar);
@@ -364,6 +386,29 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
                 cb_next = tile_cursor(nxt + stride);
                 bulk_store(st.cursor + i0, sm.nout[so].cursor, kTile * 4);
             }
+            if constexpr (TMAP) {
+                tensor_store_2d(&maps.state, (int32_t)i0, 0, bo.x);                              // x, y, fx, fy, h
+                bulk_store(st.counter + i0, bo.counter, kTile * 4);
+                if (out32) {
+                    constexpr uint32_t kRow32 = kTile * 4;
+                    const float* fdr = reinterpret_cast<const float*>(bo.d);
+                    if (out.obs) {
+                        tensor_store_2d(&maps.obs, (int32_t)i0, 0, bo.rew);                      // float x | y
+                        if (out.goal) tensor_store_2d(&maps.obs, (int32_t)i0, 2, sm.zero);
+                        bulk_store(reinterpret_cast<float*>(out.obs) + 4 * out.stride + i0, fdr, kRow32);
+                    }
+                    if (out.rew) bulk_store(reinterpret_cast<float*>(out.rew) + i0, fdr + kTile, kRow32);
+                    if (out.sp) tensor_store_2d(&maps.sp, (int32_t)i0, 0, bo.spx);               // float spx | spy
+                } else {
+                    if (out.obs) {
+                        tensor_store_2d(&maps.obs, (int32_t)i0, 0, bo.x);                        // obs rows x, y
+                        if (out.goal) tensor_store_2d(&maps.obs, (int32_t)i0, 2, sm.zero);       // goal = (0,0), MR_env.py:57
+                        bulk_store(out.obs + 4 * out.stride + i0, bo.d, kRow);
+                    }
+                    if (out.rew) bulk_store(out.rew + i0, bo.rew, kRow);
+                    if (out.sp) tensor_store_2d(&maps.sp, (int32_t)i0, 0, bo.spx);
+                }
+            } else {
             if (warp == 0 % kWarps) bulk_store(st.x + i0, bo.x, kRow);
             if (warp == 1 % kWarps) bulk_store(st.y + i0, bo.y, kRow);
             if (warp == 2 % kWarps) bulk_store(st.fx + i0, bo.fx, kRow);
@@ -403,6 +448,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
                     if (warp == 13 % kWarps) bulk_store(out.sp + i0, bo.spx, kRow);
                     if (warp == 14 % kWarps) bulk_store(out.sp + out.stride + i0, bo.spy, kRow);
                 }
+            }
             }
             if (out.done && warp == 12 % kWarps) bulk_store(out.done + i0, bo.done, kTile);
             bulk_commit();                                  // bulk groups are per thread: every issuing lane commits

@@ -598,7 +598,7 @@ def _random_regime(seed, n, T, sigmas=None):
 
 
 @pytest.mark.parametrize("seed", range(12))
-@pytest.mark.parametrize("path", ["scalar", "tma"])
+@pytest.mark.parametrize("path", ["scalar", "tma", "tmap"])
 def test_random_regimes_table_noise_both_step_kernels(seed, path):
     """The same sweep, single-step path only, with the kernel forced: the scalar kernel and the tiled TMA kernel (table rows
     bulk-copied per tile, global loads where an env's cursor has left the staged rows) against the C oracle — every env,
@@ -696,7 +696,7 @@ def test_table_noise_tma_kernel_common_regime_at_scale():
     outs = []
     z2 = np.ascontiguousarray(rng.standard_normal((24 * T + 64, n)))
     try:
-        for path in ("scalar", "tma"):
+        for path in ("scalar", "tma", "tmap"):
             L.set_step_path(path)
             e = make_env(n, noise="table", noise_table=z2, auto_reset=True, seed=5)
             e.max_timesteps = 6
@@ -709,7 +709,7 @@ def test_table_noise_tma_kernel_common_regime_at_scale():
             outs.append(torch.stack(tr).cpu().numpy())
     finally:
         L.set_step_path("default")
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     assert outs[0][:, 5 * n:6 * n].sum() > 0
 
 
@@ -748,7 +748,7 @@ def test_step_kernel_variants_are_bit_identical(dt):
     acts = acts.to(dt)
     ref = None
     try:
-        for path in ("scalar", "vec", "tma", "ws"):
+        for path in ("scalar", "vec", "tma", "ws", "tmap"):     # tma: 1-D bulk copies, tmap: 2-D tensor maps (the default)
             L.set_step_path(path)
             env = make_env(n, dtype=dt, noise="philox", seed=31, env_base=5, auto_reset=True)
             env.reset(init=None, noise_var=1.0, a0=1.0)
@@ -998,7 +998,7 @@ def test_generated_noise_kernel_trajectory_parity_with_the_draws_it_used(dt):
     assert err.max() < (FP64_TOL if dt is torch.float64 else FP32_TOL)
 
 
-@pytest.mark.parametrize("path", ["scalar", "vec", "tma"])
+@pytest.mark.parametrize("path", ["scalar", "vec", "tma", "tmap"])
 @pytest.mark.parametrize("kind", ["none", "philox", "table"])
 def test_no_kernel_writes_outside_its_rows(path, kind):
     """compute-sanitizer is closed on this pool, so the bounds check is our own: every SoA row is allocated with padding

@@ -16,7 +16,7 @@ from mr_rl_b200 import VecMREnv, _lib as L
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=24)
-ap.add_argument("--paths", nargs="+", default=["tma", "scalar"])
+ap.add_argument("--paths", nargs="+", default=["tmap", "tma", "scalar"])
 a = ap.parse_args()
 n, K = a.n, a.steps
 rows = 4 + 16 * K
