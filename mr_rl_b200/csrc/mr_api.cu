@@ -122,8 +122,9 @@ static bool tmap_2d(CUtensorMap& out, int dt /*0 f64, 1 f32*/, const void* base,
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t es[2] = {1, 1};
     CUtensorMap m;
+    const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;   // 128 B / 256 B promotion measured: no difference
     const CUresult r = enc(&m, dt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim,
-                           gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     TmapSlot& slot = cache[next];

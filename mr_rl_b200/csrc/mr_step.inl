@@ -321,7 +321,11 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
                 // buffers allow it, else one 1-D bulk copy per row; force == 1 ("tma") keeps the 1-D form for A/B runs
                 static int ctas_tmap[kMaxDevices] = {};
                 StepMaps maps;
-                const bool tmap = force != 1 && build_step_maps<T>(maps, sv, ov, nv, n, kTile, NoiseRows<MODE, MISM>::value);
+                // measured (B200, 2^20 envs, us per launch, 1-D -> tensor maps): generated noise fp64 30.8 -> 29.8, fp32 28.2 ->
+                // 26.5; table noise 61.3 -> 51.2; with the state_prime rows 32.2 -> 31.3; noise-free fp32 23.7 -> 22.9 but
+                // noise-free fp64 27.7 -> 28.6 (the one memory-bound case), which therefore keeps the 1-D copies
+                const bool want = force == 5 || !(MODE == MR_NOISE_NONE && sizeof(T) == 8);
+                const bool tmap = force != 1 && want && build_step_maps<T>(maps, sv, ov, nv, n, kTile, NoiseRows<MODE, MISM>::value);
                 if (tmap)
                     launch_persistent<T>(env_step_tma_kernel<T, MODE, MISM, true>, kTile, sizeof(StepSmem<T, MODE, MISM>), ctas_tmap,
                                          n_tiles, s, sv, act, ov, nv, tv, p, n, maps);
