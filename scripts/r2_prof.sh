@@ -12,7 +12,7 @@ $CMD > gpurun_out/p_plain1.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:env_step_tma -s 12 -c 1 -f -o gpurun_out/prof_step_sigma1 $CMD > gpurun_out/p_ncu_s1.log 2>&1
 $CMD --sigma 0 > gpurun_out/p_plain0.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:env_step_tma -s 12 -c 1 -f -o gpurun_out/prof_step_sigma0 $CMD --sigma 0 > gpurun_out/p_ncu_s0.log 2>&1
-TCMD="python tools/tablebench.py --steps 8 --paths tma"
+TCMD="python tools/tablebench.py --steps 8 --paths tmap"
 $TCMD > gpurun_out/p_plaint.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:env_step_tma -s 10 -c 1 -f -o gpurun_out/prof_step_table $TCMD > gpurun_out/p_ncu_t.log 2>&1
 ACMD="python tools/actorbench.py --paths default --launches 1 --k 20"
