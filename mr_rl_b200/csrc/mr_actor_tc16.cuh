@@ -45,6 +45,8 @@ struct alignas(128) ActorTc16Smem {
                                                //   ep[j+1] = (w3[j][0], w3[j+1][0], w3[j][1], w3[j+1][1])
     float b3[2];
     alignas(8) uint64_t mbar[2];               // completion of the layer-1 / layer-2 MMAs
+    uint64_t desc[8];                          // UMMA descriptors of the operand tiles (loop-invariant: built once, the
+                                               //   issuing thread only adds the K offset): A1 hi/lo, B1 hi/lo, A2 hi/lo, B2 hi/lo
     uint32_t tmem_base;
 };
 
@@ -190,6 +192,10 @@ __device__ __forceinline__ void actor_tc16_setup(ActorTc16Smem& sm, const float*
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
+        sm.desc[0] = t16_desc(t16_smem_u32(sm.a_hi), kT16SBO1); sm.desc[1] = t16_desc(t16_smem_u32(sm.a_lo), kT16SBO1);
+        sm.desc[2] = t16_desc(t16_smem_u32(sm.b1_hi), kT16SBO1); sm.desc[3] = t16_desc(t16_smem_u32(sm.b1_lo), kT16SBO1);
+        sm.desc[4] = t16_desc(t16_smem_u32(sm.a_hi), kT16SBO2); sm.desc[5] = t16_desc(t16_smem_u32(sm.a_lo), kT16SBO2);
+        sm.desc[6] = t16_desc(t16_smem_u32(sm.b2_hi), kT16SBO2); sm.desc[7] = t16_desc(t16_smem_u32(sm.b2_lo), kT16SBO2);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t16_smem_u32(&sm.mbar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t16_smem_u32(&sm.mbar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -233,8 +239,7 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
     if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d1 = sm.tmem_base;
-        const uint64_t ah = t16_desc(t16_smem_u32(sm.a_hi), kT16SBO1), al = t16_desc(t16_smem_u32(sm.a_lo), kT16SBO1);
-        const uint64_t bh = t16_desc(t16_smem_u32(sm.b1_hi), kT16SBO1), bl = t16_desc(t16_smem_u32(sm.b1_lo), kT16SBO1);
+        const uint64_t ah = sm.desc[0], al = sm.desc[1], bh = sm.desc[2], bl = sm.desc[3];
         t16_mma(d1, ah, bh, 0u);
         t16_mma(d1, al, bh, 1u);
         t16_mma(d1, ah, bl, 1u);
@@ -265,13 +270,13 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
     if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d2 = sm.tmem_base + kActorHidden;
-        const uint32_t ah = t16_smem_u32(sm.a_hi), al = t16_smem_u32(sm.a_lo), bh = t16_smem_u32(sm.b2_hi), bl = t16_smem_u32(sm.b2_lo);
+        const uint64_t ah = sm.desc[4], al = sm.desc[5], bh = sm.desc[6], bl = sm.desc[7];
 #pragma unroll
         for (int k = 0; k < kActorHidden / 16; ++k) {
-            const uint32_t ko = k * 2 * kT16LBO;                       // 16 halfs = two 16-byte chunks
-            t16_mma(d2, t16_desc(ah + ko, kT16SBO2), t16_desc(bh + ko, kT16SBO2), k > 0 ? 1u : 0u);
-            t16_mma(d2, t16_desc(al + ko, kT16SBO2), t16_desc(bh + ko, kT16SBO2), 1u);
-            t16_mma(d2, t16_desc(ah + ko, kT16SBO2), t16_desc(bl + ko, kT16SBO2), 1u);
+            const uint64_t ko = (uint64_t)((k * 2 * kT16LBO) >> 4);    // 16 halfs = two 16-byte chunks, in the address field's units
+            t16_mma(d2, ah + ko, bh + ko, k > 0 ? 1u : 0u);
+            t16_mma(d2, al + ko, bh + ko, 1u);
+            t16_mma(d2, ah + ko, bl + ko, 1u);
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t16_smem_u32(&sm.mbar[1])) : "memory");
     }
