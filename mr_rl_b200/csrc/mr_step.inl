@@ -323,8 +323,10 @@ static void step_ranges(const StateView<T>& sv, const T* act, const OutView<T>& 
                 StepMaps maps;
                 // measured (B200, 2^20 envs, us per launch, 1-D -> tensor maps): generated noise fp64 30.8 -> 29.8, fp32 28.2 ->
                 // 26.5; table noise 61.3 -> 51.2; with the state_prime rows 32.2 -> 31.3; noise-free fp32 23.7 -> 22.9 but
-                // noise-free fp64 27.7 -> 28.6 (the one memory-bound case), which therefore keeps the 1-D copies
-                const bool want = force == 5 || !(MODE == MR_NOISE_NONE && sizeof(T) == 8);
+                // noise-free fp64 27.7 -> 28.6 when the row stride is a large power of two (the five rows of the box then
+                // hit the same DRAM channels at once; VecMREnv pads its rows: 27.9 both ways), so that case keeps 1-D copies
+                const ptrdiff_t row_stride = (const char*)sv.y - (const char*)sv.x;
+                const bool want = force == 5 || !(MODE == MR_NOISE_NONE && sizeof(T) == 8 && row_stride % 65536 == 0);
                 const bool tmap = force != 1 && want && build_step_maps<T>(maps, sv, ov, nv, n, kTile, NoiseRows<MODE, MISM>::value);
                 if (tmap)
                     launch_persistent<T>(env_step_tma_kernel<T, MODE, MISM, true>, kTile, sizeof(StepSmem<T, MODE, MISM>), ctas_tmap,

@@ -23,6 +23,17 @@ _NOISE = {"none": L.NOISE_NONE, "table": L.NOISE_TABLE, "philox": L.NOISE_PHILOX
 _PAD = 16          # rows are padded so every SoA row starts 16-byte aligned for any dtype
 
 
+def _row_stride(n):
+    """Elements between the SoA rows of one tensor: n rounded up to 16, plus 256 when that is a large power-of-two multiple.
+    The rows of a tile are fetched together (one tensor-map box, or back-to-back bulk copies); with a power-of-two row
+    stride they all land on the same DRAM channels.  Measured on B200 at 2^20 envs (noise-free fp64 step, us per launch):
+    stride 2^20 -> 28.8 (1-D copies) / 29.5 (tensor maps), stride 2^20 + 256 -> 28.0 / 27.9."""
+    npad = (n + _PAD - 1) // _PAD * _PAD
+    if npad >= (1 << 16) and npad % 4096 == 0:
+        npad += 256
+    return npad
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -61,7 +72,7 @@ class VecMREnv:
         self.dtype = dtype
         self._dt = _DT[dtype]
         n = self.num_envs
-        self._np = npad = (n + _PAD - 1) // _PAD * _PAD
+        self._np = npad = _row_stride(n)
         dev = self.device
 
         # --- spaces and constants, MR_env.py:34-63 -------------------------------------------
