@@ -14,6 +14,8 @@
 
 namespace mr {
 
+// input stages in flight per CTA.  Measured with the tensor-map copies (2^20 envs, fp64, sigma 0 / 1): 2 stages 30.3 / 29.4 us,
+// 3 stages 27.7 / 29.6 us, 4 stages 28.7 / 29.9 us.
 #ifndef MR_STAGES_IN
 #define MR_STAGES_IN 3
 #endif
