@@ -404,7 +404,7 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
     int rc = mr::check_common("mr_env_step_host", st, n, dtype, p, nz);
     if (rc) return rc;
     if (!io) return mr::fail(MR_ERR_ARG, "mr_env_step_host: null io");
-    if (!io->actions_host || !io->obs_host || !io->done_host || (!io->rew_host && n_chunks != 0))
+    if (!io->actions_host || !io->obs_host || !io->done_host)
         return mr::fail(MR_ERR_ARG, "mr_env_step_host: null host buffer");
     if (io->io_f32 && (n_chunks != 0 || dtype != MR_F64))
         return mr::fail(MR_ERR_ARG, "mr_env_step_host: io_f32 is the direct mode (n_chunks = 0) with MR_F64 storage");
@@ -432,7 +432,9 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
         return MR_OK;
     }
     if (!pl || !out_dev) return mr::fail(MR_ERR_ARG, "mr_env_step_host: staged mode needs a pipeline and device output rows");
-    if (!io->actions_dev) return mr::fail(MR_ERR_ARG, "mr_env_step_host: staged mode needs the device staging buffer for actions");
+    // actions_dev == NULL: the chunk kernels read the page-locked actions themselves (no H2D copies), only the results
+    // go through the copy engine
+    const bool zc_in = io->actions_dev == nullptr;
     if (!out_dev->obs || !out_dev->rew || !out_dev->done) return mr::fail(MR_ERR_ARG, "mr_env_step_host: device obs/rew/done rows required");
     const int64_t dstride = out_dev->row_stride ? out_dev->row_stride : n;
     // chunk edges are multiples of 256 envs (tile- and 16-byte aligned sub-ranges); table noise indexes the table by
@@ -452,9 +454,11 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
     ok(cudaStreamWaitEvent(pl->s_out, pl->ev_start, 0));
     for (int c = 0; c < chunks && ce == cudaSuccess && rc == MR_OK; ++c) {
         const int64_t lo = c * per, hi = c == chunks - 1 ? n : lo + per, m = hi - lo;
-        if (!ok(cudaMemcpyAsync((char*)io->actions_dev + 2 * lo * el, (const char*)io->actions_host + 2 * lo * el,
-                                (size_t)(2 * m * el), cudaMemcpyHostToDevice, pl->s_in))) break;
-        if (!ok(cudaEventRecord(pl->ev_in[c], pl->s_in)) || !ok(cudaStreamWaitEvent(pl->s_k, pl->ev_in[c], 0))) break;
+        if (!zc_in) {
+            if (!ok(cudaMemcpyAsync((char*)io->actions_dev + 2 * lo * el, (const char*)io->actions_host + 2 * lo * el,
+                                    (size_t)(2 * m * el), cudaMemcpyHostToDevice, pl->s_in))) break;
+            if (!ok(cudaEventRecord(pl->ev_in[c], pl->s_in)) || !ok(cudaStreamWaitEvent(pl->s_k, pl->ev_in[c], 0))) break;
+        }
         mr_env_state sc = *st;
         sc.x = (char*)st->x + lo * el; sc.y = (char*)st->y + lo * el; sc.fx = (char*)st->fx + lo * el;
         sc.fy = (char*)st->fy + lo * el; sc.h = (char*)st->h + lo * el;
@@ -467,15 +471,18 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
         mr_noise nc;
         const mr_noise* nzp = nz;
         if (nz) { nc = *nz; nc.env_base = nz->env_base + (uint64_t)lo; nzp = &nc; }
-        rc = mr_env_step(&sc, m, dtype, p, nzp, tt, (const char*)io->actions_dev + 2 * lo * el, &oc, pl->s_k);
+        rc = mr_env_step(&sc, m, dtype, p, nzp, tt, (const char*)(zc_in ? io->actions_host : io->actions_dev) + 2 * lo * el, &oc,
+                         pl->s_k);
         if (rc) break;                                              // joined and reported below
         if (!ok(cudaEventRecord(pl->ev_k[c], pl->s_k)) || !ok(cudaStreamWaitEvent(pl->s_out, pl->ev_k[c], 0))) break;
-        for (int row = 0; row < 5; ++row) {
-            if ((row == 2 || row == 3) && !io->copy_goal_rows) continue;     // the goal is the constant (0, 0) (MR_env.py:57)
-            ok(cudaMemcpyAsync((char*)io->obs_host + (row * hstride + lo) * el, (const char*)out_dev->obs + (row * dstride + lo) * el,
-                               (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out));
-        }
-        ok(cudaMemcpyAsync((char*)io->rew_host + lo * el, (const char*)out_dev->rew + lo * el, (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out));
+        // rows x, y (and the goal rows, if wanted) are equally pitched: one 2-D copy; then d
+        ok(cudaMemcpy2DAsync((char*)io->obs_host + lo * el, (size_t)(hstride * el), (const char*)out_dev->obs + lo * el,
+                             (size_t)(dstride * el), (size_t)(m * el), io->copy_goal_rows ? 4 : 2, cudaMemcpyDeviceToHost, pl->s_out));
+        ok(cudaMemcpyAsync((char*)io->obs_host + (4 * hstride + lo) * el, (const char*)out_dev->obs + (4 * dstride + lo) * el,
+                           (size_t)(m * el), cudaMemcpyDeviceToHost, pl->s_out));
+        if (io->rew_host)                                               // NULL: the constant reward of MR_env.py:89 is not sent
+            ok(cudaMemcpyAsync((char*)io->rew_host + lo * el, (const char*)out_dev->rew + lo * el, (size_t)(m * el),
+                               cudaMemcpyDeviceToHost, pl->s_out));
         ok(cudaMemcpyAsync(io->done_host + lo, out_dev->done + lo, (size_t)m, cudaMemcpyDeviceToHost, pl->s_out));
     }
     // join: later work on the caller's stream sees the new state; the host buffers are valid when s_out has drained

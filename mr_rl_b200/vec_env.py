@@ -433,18 +433,21 @@ class VecMREnv:
             a_np = np.asarray(actions.numpy() if torch.is_tensor(actions) else actions)
             if a_np.size != 2 * n:
                 raise ValueError(f"actions must be [{n}, 2]")
-            a_pin = self._registered_view(a_np, hdt) if direct else None
+            a_pin = self._registered_view(a_np, hdt) if direct or self.host_mode == "staged_zc" else None
             if a_pin is None:                     # staging copy into pinned memory (dtype / layout / registration not usable)
                 a_pin = self._pinned_buf("act", (n, 2), hdt)
                 np.copyto(a_pin.numpy(), a_np.reshape(n, 2), casting="same_kind")
         a_dev = self._pinned.get("act_dev")
-        if a_dev is None and not direct:
+        zc_in = self.host_mode == "staged_zc"      # chunk kernels read the pinned actions themselves, results by copy engine
+        if a_dev is None and not direct and not zc_in:
             a_dev = self._pinned["act_dev"] = torch.empty(n, 2, dtype=self.dtype, device=self.device)
+        if zc_in:
+            a_dev = None
         fresh = "obs" not in self._pinned or self._pinned["obs"].dtype != hdt
         o_pin = self._pinned_buf("obs", (5, self._np), hdt)           # same row stride as the device rows
         d_pin = self._pinned_buf("done", (n,), torch.uint8)
         # the constant reward of MR_env.py:89 is not sent at all in direct mode: one cached array of 10s
-        const_rew = direct and self.params.reward_mode == L.REWARD_CONST10
+        const_rew = self.params.reward_mode == L.REWARD_CONST10
         if const_rew:
             r_np = self._pinned.get("rew_const")
             if r_np is None or r_np.dtype != o_pin.numpy().dtype:
@@ -480,7 +483,10 @@ class VecMREnv:
         return ret
 
     # Host-buffer step strategy.  Measured at 2^20 envs (fp64, sigma = 1): staged 1 / 2 / 4 / 8 chunks 1.01 / 0.91 / 0.91 /
-    # 0.99 ms (each of the 5 D2H pieces per chunk costs a few us of DMA set-up); direct 0.82 ms.  Tried and dropped: a
+    # 0.99 ms (each of the 5 D2H pieces per chunk costs a few us of DMA set-up); direct 0.82 ms.  Round 2, constant reward
+    # not sent: direct 0.66-0.68 ms; staged with ONE 2-D copy for the x, y rows 0.86 / 0.73 / 0.75 ms (1 / 2 / 4 chunks);
+    # "staged_zc" (chunk kernels read the pinned actions themselves, results by copy engine) 0.83-0.88 ms with 2-8 chunks
+    # (gpurun_out/e2e_zc.log -> profiles/r02_e2e_host_modes.txt) — direct stays the default.  Tried and dropped: a
     # hybrid (copy-engine H2D of the actions in chunks + kernel writing straight to the host) 0.89 / 0.93 / 0.97 ms with
     # 2 / 4 / 8 chunks — the smaller launches lose more than the DMA read gains; and a "streamed" variant (ONE kernel whose
     # loader waits on per-chunk arrival flags while the copy engine delivers the actions) 0.88 / 0.91 / 1.03 ms with

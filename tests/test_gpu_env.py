@@ -535,7 +535,7 @@ def test_pipelined_host_step_equals_single_launch_step():
         e.reset(init=None, noise_var=1.0, a0=1.0)
     assert e1.host_mode == "direct"
     for k in range(6):
-        e1.host_mode = "direct" if k in (0, 5) else "staged"
+        e1.host_mode = ("direct", "staged", "staged_zc", "staged", "staged_zc", "direct")[k]
         e1.host_chunks = (0, 4, 3, 8, 1, 0)[k]
         o1, r1, d1, _ = e1.step_host(acts)
         o2, r2, d2, _ = e2.step(torch.as_tensor(acts, device="cuda:0"))
