@@ -120,6 +120,22 @@ template <bool MISM> struct NoiseRows<MR_NOISE_TABLE, MISM> { static constexpr i
 // input stages: the noise rows are read during the integration, so their stage is re-filled only after the tile is
 // done (2 stages: one being consumed, one in flight); the other modes copy their inputs to registers first (3 stages)
 template <int MODE> struct StagesIn { static constexpr int value = MODE == MR_NOISE_TABLE ? 2 : kStagesIn; };
+// ONE CTA barrier per tile instead of two where it pays.  Barrier [A] ("inputs copied to registers, output stage free")
+// exists only because the refill of in[s] and the re-use of out[so] are decided right after it; with a third output
+// stage and the refill issued after barrier [B] both hand-offs ride on [B]: the issuing thread waits (after committing
+// tile it's stores) until the stores of tile it-1 have left shared memory, which frees the stage tile it+2 writes — and
+// every thread passes [B] of tile it+1 before it gets there.  The refill then starts one compute phase later (two tiles
+// in flight instead of three), which only the memory-bound case feels.  Measured (B200, 2^20 envs, us per launch, two
+// barriers -> one): generated noise fp64 29.6 -> 28.6, fp32 26.5 -> 26.3; noise-free fp32 22.8 -> 22.2, but noise-free
+// fp64 27.9 -> 30.4 (a fourth input stage does not fit beside the third output stage at 4 CTAs per SM), so that case
+// keeps two barriers; the table mode is bounded by its noise stages and keeps them too.  -DMR_ONE_BARRIER=0: never.
+#ifndef MR_ONE_BARRIER
+#define MR_ONE_BARRIER 1
+#endif
+template <class T, int MODE> struct OneBarrier {
+    static constexpr bool value = MR_ONE_BARRIER && (MODE == MR_NOISE_PHILOX || (MODE == MR_NOISE_NONE && sizeof(T) == 4));
+};
+template <class T, int MODE> struct StagesOut { static constexpr int value = OneBarrier<T, MODE>::value ? 3 : kStagesOut; };
 
 template <int kTile, int ROWS>
 struct alignas(128) TileNoiseIn {
@@ -164,9 +180,10 @@ template <class T, int MODE = MR_NOISE_NONE, bool MISM = false, int kTile = Tile
 struct StepSmem {
     static constexpr int kIn = StagesIn<MODE>::value;
     TileIn<T, kTile> in[kIn];
-    TileOut<T, kTile> out[kStagesOut];
+    static constexpr int kOut = StagesOut<T, MODE>::value;
+    TileOut<T, kTile> out[kOut];
     TileNoiseIn<kTile, NoiseRows<MODE, MISM>::value> nin[kIn];
-    TileNoiseOut<kTile, NoiseRows<MODE, MISM>::value> nout[kStagesOut];
+    TileNoiseOut<kTile, NoiseRows<MODE, MISM>::value> nout[kOut];
     alignas(128) T zero[2 * kTile];         // the two goal rows as one {kTile x 2} box
     alignas(16) float4 zpre[(MR_RNG_PREFETCH && MODE == MR_NOISE_PHILOX && !MISM) ? 2 * kTile : 1];   // next tile's normals
     alignas(8) uint64_t full[kIn];
@@ -200,6 +217,8 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
     constexpr int kSI = StagesIn<MODE>::value;
     constexpr int kNR = NoiseRows<MODE, MISM>::value;
     constexpr bool kTable = MODE == MR_NOISE_TABLE;
+    constexpr bool kOneBar = OneBarrier<T, MODE>::value;
+    constexpr int kSO = StagesOut<T, MODE>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = StepSmem<T, MODE, MISM>;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -306,7 +325,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
     for (int64_t tile = first; tile < n_tiles; tile += stride, ++it) {
         const int s = it % kSI;
         const uint32_t parity = (uint32_t)(it / kSI) & 1u;
-        const int so = it % kStagesOut;
+        const int so = it % kSO;
         const int64_t i0 = tile * kTile;
 
         mbar_wait(&sm.full[s], parity);
@@ -319,12 +338,14 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
         if (sizeof(T) == 8 && !act32) { const double2 a2 = reinterpret_cast<const double2*>(bi.act)[tid]; f_t = a2.x; al = a2.y; }
         else { const float2 a2 = reinterpret_cast<const float2*>(bi.act)[tid]; f_t = a2.x; al = a2.y; }
 
-        if (elect) bulk_wait_read<kStagesOut - 1>();        // out[so] (used kStagesOut tiles ago) has been read out
-        __syncthreads();                                    // [A] in[s] fully consumed, out[so] free
-        if constexpr (!kTable) {
-            if (elect) {
-                const int64_t nxt = tile + (int64_t)kSI * stride;
-                if (nxt < n_tiles) issue_loads(s, nxt, 0);
+        if constexpr (!kOneBar) {
+            if (elect) bulk_wait_read<kStagesOut - 1>();    // out[so] (used kStagesOut tiles ago) has been read out
+            __syncthreads();                                // [A] in[s] fully consumed, out[so] free
+            if constexpr (!kTable) {
+                if (elect) {
+                    const int64_t nxt = tile + (int64_t)kSI * stride;
+                    if (nxt < n_tiles) issue_loads(s, nxt, 0);
+                }
             }
         }
 
@@ -384,6 +405,10 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
         fence_async_smem();
         __syncthreads();                                    // [B] tile results complete in out[so]
         if (elect) {
+            if constexpr (kOneBar) {                        // in[s] was copied to registers before [B] by every thread
+                const int64_t nxt = tile + (int64_t)kSI * stride;
+                if (nxt < n_tiles) issue_loads(s, nxt, 0);
+            }
             if constexpr (kTable) {                         // the stage's noise rows are free only now
                 const int64_t nxt = tile + (int64_t)kSI * stride;
                 if (nxt < n_tiles) issue_loads(s, nxt, cb_next);
@@ -456,6 +481,7 @@ env_step_tma_kernel(StateView<T> st, const T* __restrict__ actions, OutView<T> o
             }
             if (out.done && warp == 12 % kWarps) bulk_store(out.done + i0, bo.done, kTile);
             bulk_commit();                                  // bulk groups are per thread: every issuing lane commits
+            if constexpr (kOneBar) bulk_wait_read<1>();     // tile it-1's stores have been read out: frees out[(it + 2) % 3]
         }
     }
     if (elect) bulk_wait_read<0>();                         // smem must outlive the last bulk stores
