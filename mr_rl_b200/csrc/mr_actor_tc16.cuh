@@ -216,8 +216,13 @@ __device__ __forceinline__ void actor_tc16_teardown(ActorTc16Smem& sm) {
 }
 
 // One actor evaluation for the CTA's 128 envs (thread = env = GEMM row = TMEM lane).  `step` = call index (mbarrier phase).
+// fill1 / fill2: work of the caller that does not depend on the action, run by every thread between the issue of the
+// layer-1 / layer-2 MMAs and the wait for them (the rollout draws the env step's process noise there), so the MMA round
+// trips are covered by the warp's own instructions and not only by the other CTAs of the SM.
+struct T16NoFill { __device__ __forceinline__ void operator()() const {} };
+template <class F1 = T16NoFill, class F2 = T16NoFill>
 __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const float obs[5], float hi0, float hi1, int step,
-                                                   float act[2]) {
+                                                   float act[2], F1 fill1 = F1(), F2 fill2 = F2()) {
     const int tid = threadIdx.x;
     const uint32_t parity = (uint32_t)step & 1u;
     char* a_hi = reinterpret_cast<char*>(sm.a_hi);
@@ -247,6 +252,7 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
         t16_mma(d1, ah, bl, 1u);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t16_smem_u32(&sm.mbar[0])) : "memory");
     }
+    fill1();
     t16_wait(&sm.mbar[0], parity);
 
     // ---- H1 = relu(D1) re-split into the layer-2 A operand, 16 hidden units at a time -----------------------------
@@ -282,6 +288,7 @@ __device__ __forceinline__ void actor_tc16_forward(ActorTc16Smem& sm, const floa
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t16_smem_u32(&sm.mbar[1])) : "memory");
     }
+    fill2();
     t16_wait(&sm.mbar[1], parity);
 
     // ---- BN + ReLU, 64 x 2 output layer, tanh, action bound ---------------------------------------------------------

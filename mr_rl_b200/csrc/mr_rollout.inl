@@ -78,8 +78,15 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     o.rew = 0.0; o.done = false; o.why = 0;
     bool overflow = false;
 
+    // tensor-core actor + generated noise, matched model: the step's eight normals are drawn while the actor's MMAs are in
+    // flight (same values as PhiloxNoise::draw8 inside sim_step, so the results are bit-identical to the composed path)
+    constexpr bool kFillDraws = SRC == kSrcActorTc16 && MODE == MR_NOISE_PHILOX && !MISM && !PERENV;
+#ifndef MR_ACTOR_FILL
+#define MR_ACTOR_FILL 3          // bit 0: block 0 behind the layer-1 MMAs, bit 1: block 1 behind the layer-2 MMAs
+#endif
     for (int k = 0; k < io.k_steps; ++k) {
         double f_t = 0.0, al = 0.0;
+        float z8[8];
         if constexpr (SRC == MR_ACTIONS_TENSOR) {
             if (live) {
                 const T* a = io.actions + ((int64_t)k * n + i) * 2;
@@ -97,8 +104,22 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             float a2[2];
             if constexpr (SRC == kSrcActorTc)
                 actor_tc_forward(*reinterpret_cast<ActorTcSmem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], actor_calls++, a2);
-            else if constexpr (SRC == kSrcActorTc16)
-                actor_tc16_forward(*reinterpret_cast<ActorTc16Smem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], actor_calls++, a2);
+            else if constexpr (SRC == kSrcActorTc16) {
+                if constexpr (kFillDraws) {
+                    PhiloxNoise nzd;
+                    nzd.seek(nv.env_base + (uint64_t)(live ? i : 0), off + (uint64_t)k);
+                    auto d0 = [&]() { nzd.draw4_at(p, 0u, z8); };
+                    auto d1 = [&]() { nzd.draw4_at(p, 1u, z8 + 4); };
+                    if constexpr ((MR_ACTOR_FILL & 1) == 0) d0();
+                    if constexpr ((MR_ACTOR_FILL & 2) == 0) d1();
+                    auto f1 = [&]() { if constexpr ((MR_ACTOR_FILL & 1) != 0) d0(); };
+                    auto f2 = [&]() { if constexpr ((MR_ACTOR_FILL & 2) != 0) d1(); };
+                    actor_tc16_forward(*reinterpret_cast<ActorTc16Smem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1],
+                                       actor_calls++, a2, f1, f2);
+                } else {
+                    actor_tc16_forward(*reinterpret_cast<ActorTc16Smem*>(s_dyn), obs5, (float)p.act_hi[0], (float)p.act_hi[1], actor_calls++, a2);
+                }
+            }
             else
                 actor_forward_smem(s_actor, obs5, (float)p.act_hi[0], (float)p.act_hi[1], a2);
             f_t = (double)a2[0]; al = (double)a2[1];
@@ -110,6 +131,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         if constexpr (PERENV) {
             if (mism_i) sim_step<true>(e, t, tb, tb2, f_t, al, p, nz);
             else sim_step<false>(e, t, tb, tb2, f_t, al, p, nz);
+        } else if constexpr (kFillDraws) {
+            nz.blk += 2;                                     // where draw8() would have left the stream
+            sim_step_drawn(e, t, tb, tb2, f_t, al, p, nz, z8);
         } else {
             sim_step<MISM>(e, t, tb, tb2, f_t, al, p, nz);
         }
