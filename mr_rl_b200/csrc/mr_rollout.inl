@@ -38,9 +38,11 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     if (threadIdx.x < MR_STATS_LEN) s_stats[threadIdx.x] = 0.0;
     __syncthreads();
 
-    double acc[MR_STATS_LEN];
-#pragma unroll
-    for (int k = 0; k < MR_STATS_LEN; ++k) acc[k] = 0.0;
+    // per-thread statistics, kept narrow inside the step loop (the kernel is register-bound): the episode ends by reason
+    // and the summed episode lengths are integers, the episode count is their sum and the env-step count is k_steps per
+    // live env; they become the doubles of the statistics vector only after the loop
+    double sum_rew = 0.0;
+    int sum_len = 0, n_goal = 0, n_oob = 0, n_timeout = 0, n_live_steps = 0, n_failed = 0;
     const uint64_t off = step_offset(nv);
     const Params p_launch = p;
     int actor_calls = 0;                           // mbarrier phase of the tensor-core actor paths
@@ -153,16 +155,14 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             if (io.traj_rew) io.traj_rew[(int64_t)k * n + i] = (T)o.rew;
             if (io.traj_episode) io.traj_episode[(int64_t)k * n + i] = ep;
             if (io.traj_step) io.traj_step[(int64_t)k * n + i] = e.counter;
-            acc[MR_STAT_ENV_STEPS] += 1.0;
-            acc[MR_STAT_SUM_REWARD] += o.rew;
+            sum_rew += o.rew;
         }
         if (o.done) {
             if (live && !was_done) {
-                acc[MR_STAT_EPISODES] += 1.0;
-                acc[MR_STAT_SUM_LENGTH] += (double)e.counter;
-                if (o.why == 1) acc[MR_STAT_GOAL] += 1.0;
-                else if (o.why == 2) acc[MR_STAT_OUT_OF_BOUNDS] += 1.0;
-                else acc[MR_STAT_TIMEOUT] += 1.0;
+                sum_len += e.counter;
+                if (o.why == 1) ++n_goal;
+                else if (o.why == 2) ++n_oob;
+                else ++n_timeout;
             }
             if (!was_done) ++ep;
             if (p.auto_reset) {
@@ -192,8 +192,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     }
 
     if (live) {
+        n_live_steps += io.k_steps;
         if (overflow) e.status |= kNoiseOverflow;
-        if (e.status) acc[MR_STAT_FAILED] += 1.0;
+        if (e.status) ++n_failed;
         const double t_out = time_at(tv, e.counter, p.dt);
         st.x[i] = (T)e.x; st.y[i] = (T)e.y; st.fx[i] = (T)e.fx; st.fy[i] = (T)e.fy;
         st.h[i] = encode_h<T>(e.h, (t_out + p.dt) - t_out);
@@ -216,6 +217,17 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     if constexpr (SRC == kSrcActorTc16) actor_tc16_teardown(*reinterpret_cast<ActorTc16Smem*>(s_dyn));
 
     if (io.stats) {   // warp shuffle -> shared -> one atomic per block per statistic
+        double acc[MR_STATS_LEN];
+#pragma unroll
+        for (int k = 0; k < MR_STATS_LEN; ++k) acc[k] = 0.0;
+        acc[MR_STAT_ENV_STEPS] = (double)n_live_steps;
+        acc[MR_STAT_SUM_REWARD] = sum_rew;
+        acc[MR_STAT_EPISODES] = (double)(n_goal + n_oob + n_timeout);
+        acc[MR_STAT_SUM_LENGTH] = (double)sum_len;
+        acc[MR_STAT_GOAL] = (double)n_goal;
+        acc[MR_STAT_OUT_OF_BOUNDS] = (double)n_oob;
+        acc[MR_STAT_TIMEOUT] = (double)n_timeout;
+        acc[MR_STAT_FAILED] = (double)n_failed;
 #pragma unroll
         for (int k = 0; k < MR_STATS_LEN; ++k) {
             double v = acc[k];
