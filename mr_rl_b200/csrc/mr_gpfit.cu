@@ -13,6 +13,8 @@
 // are zeroed in W at the end, as mr_gp_predict expects.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "mr_common.cuh"
 #include "mr_dmma.cuh"
 
@@ -129,6 +131,140 @@ chol_diag_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ M 
     chol_diag_steps<2>(X, sL, sV, tx, ty, in_lower); chol_diag_steps<3>(X, sL, sV, tx, ty, in_lower);
     chol_diag_steps<4>(X, sL, sV, tx, ty, in_lower); chol_diag_steps<5>(X, sL, sV, tx, ty, in_lower);
     chol_diag_steps<6>(X, sL, sV, tx, ty, in_lower); chol_diag_steps<7>(X, sL, sV, tx, ty, in_lower);
+    if (threadIdx.x < NB) {
+        const double p = sL[threadIdx.x * DIAG_LD + threadIdx.x];
+        const double d = sqrt(p);
+        sD[threadIdx.x] = d; sR[threadIdx.x] = 1.0 / d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i)
+            if (!(sL[i * DIAG_LD + i] > 0.0)) { atomicCAS(info, 0, k0 + i + 1); break; }   // LAPACK potrf's info > 0
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            M[r * NB + c] = c <= r ? X[a][b] * sR[r] : 0.0;
+        }
+    for (int idx = threadIdx.x; idx < NB * NB; idx += DIAG_THREADS) {
+        const int r = idx / NB, c = idx % NB;
+        Ablk[(int64_t)r * ld + c] = c < r ? sL[r * DIAG_LD + c] * sR[c] : (c == r ? sD[c] : 0.0);   // upper part := 0
+    }
+}
+
+// ---- the same factorisation with the per-step synchronisation taken off the critical path (the default) --------------
+// chol_diag_kernel above spends ~920 cycles per step: barrier -> 1 / pivot (an fp64 division, ~200 cycles, by every
+// thread) -> the whole rank-1 update -> publish the next column -> barrier.  Here a step is split:
+//   * the few register-tile entries the NEXT step's exchange needs (tile column / tile row of j + 1, the diagonal entry
+//     of j + 2) are updated first and published at once, then the thread ARRIVES on an mbarrier (no wait);
+//   * the rest of the rank-1 update and the reciprocal of the NEXT pivot follow, overlapping everybody's arrival:
+//     p_{j+1} = X[j+1][j+1] - v_j[j+1]^2 / p_j needs the diagonal entry before update j, which its owner published one step
+//     earlier, so every thread forms it (with the owner's own fma, bit for bit) and divides while it still has FMAs to do;
+//   * only then the thread waits for the arrivals.
+// Same arithmetic per matrix entry in the same order as chol_diag_kernel: bit-identical results (tested).
+__device__ __forceinline__ void diag_bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void diag_bar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DIAG_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DIAG_DONE_%=;\n"
+        "bra DIAG_WAIT_%=;\n"
+        "DIAG_DONE_%=:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// step j = 16 JT + jl.  JTN: the 16-wide tile of column j + 1 (JT, or JT + 1 when jl == 15); JT2: the tile of j + 2.
+template <int JT, int JTN, int JT2>
+__device__ __forceinline__ void chol_diag_step2(double (&X)[8][8], double* sL, double* sV, double* sDg, uint64_t* bar,
+                                                uint32_t& parity, int jl, int tx, int ty, bool in_lower, double& inv_p) {
+    const int j = 16 * JT + jl;
+    const double* v = sV + (j & 1) * NB;
+    double vc[8], lr[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) vc[b] = v[tx + 16 * b];
+    if (tx == jl) vc[JT] = 1.0;                       // c == j
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int r = ty + 16 * a;
+        lr[a] = (a >= JT && (a > JT || ty > jl)) ? -(v[r] * inv_p) : 0.0;   // rows <= j: a multiply by zero, no branch
+    }
+    // operands of the next pivot, read before this thread arrives (afterwards the exchange buffers may be rewritten)
+    double w = 0.0, dg = 1.0;
+    if (j + 1 < NB) { w = v[j + 1]; dg = sDg[(j + 1) & 1]; }
+    auto prio = [](int a, int b) { return b == JTN || a == JTN || (a == JT2 && b == JT2); };
+#pragma unroll
+    for (int a = JT; a < 8; ++a) {                    // rows of tiles a < JT are finished
+#pragma unroll
+        for (int b = 0; b <= a; ++b)
+            if (prio(a, b)) X[a][b] = fma(lr[a], b < a ? vc[b] : (in_lower ? vc[a] : 0.0), X[a][b]);
+    }
+    if constexpr (JTN < 8) chol_diag_publish<JTN>(X, sL, sV, (jl + 1) & 15, tx, ty);
+    if constexpr (JT2 < 8) {
+        if (tx == ((jl + 2) & 15) && ty == tx) sDg[j & 1] = X[JT2][JT2];        // diagonal entry of j + 2 after update j
+    }
+    diag_bar_arrive(bar);
+#pragma unroll
+    for (int a = JT; a < 8; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b)
+            if (!prio(a, b)) X[a][b] = fma(lr[a], b < a ? vc[b] : (in_lower ? vc[a] : 0.0), X[a][b]);
+    }
+    if (j + 1 < NB) inv_p = 1.0 / fma(-(w * inv_p), w, dg);                      // 1 / p_{j+1}, the owner's own fma
+    diag_bar_wait(bar, parity);
+    parity ^= 1u;
+}
+
+template <int JT>
+__device__ __forceinline__ void chol_diag_steps2(double (&X)[8][8], double* sL, double* sV, double* sDg, uint64_t* bar,
+                                                 uint32_t& parity, int tx, int ty, bool in_lower, double& inv_p) {
+#pragma unroll 1
+    for (int jl = 0; jl < 14; ++jl) chol_diag_step2<JT, JT, JT>(X, sL, sV, sDg, bar, parity, jl, tx, ty, in_lower, inv_p);
+    chol_diag_step2<JT, JT, JT + 1>(X, sL, sV, sDg, bar, parity, 14, tx, ty, in_lower, inv_p);
+    chol_diag_step2<JT, JT + 1, JT + 1>(X, sL, sV, sDg, bar, parity, 15, tx, ty, in_lower, inv_p);
+}
+
+constexpr size_t kDiag2SmemBytes = kDiagSmemBytes + (2 + 2) * sizeof(double);   // + sDg[2], the mbarrier (padded)
+
+__global__ void __launch_bounds__(DIAG_THREADS)
+chol_diag2_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ M /*[128][128]*/, int* __restrict__ info) {
+    extern __shared__ __align__(16) double sm[];
+    double* sL = sm;                              // [128][129] unscaled columns of L, pivots on the diagonal
+    double* sV = sL + NB * DIAG_LD;               // [2][128]   per-step exchange
+    double* sD = sV + 2 * NB;                     // [128] sqrt(pivot)
+    double* sR = sD + NB;                         // [128] 1 / sqrt(pivot)
+    double* sDg = sR + NB;                        // [2]   diagonal entry two steps ahead
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sDg + 2);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double* Ablk = A + (int64_t)k0 * ld + k0;
+    double X[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            X[a][b] = c <= r ? Ablk[(int64_t)r * ld + c] : 0.0;
+        }
+    const bool in_lower = tx <= ty;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(DIAG_THREADS));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tx == 1 && ty == 1) sDg[1] = X[0][0];     // A[1][1]: the diagonal entry step 0 needs for the pivot of step 1
+    chol_diag_publish<0>(X, sL, sV, 0, tx, ty);
+    __syncthreads();
+    double inv_p = 1.0 / sV[0];
+    uint32_t parity = 0;
+    chol_diag_steps2<0>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p); chol_diag_steps2<1>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p);
+    chol_diag_steps2<2>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p); chol_diag_steps2<3>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p);
+    chol_diag_steps2<4>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p); chol_diag_steps2<5>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p);
+    chol_diag_steps2<6>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p); chol_diag_steps2<7>(X, sL, sV, sDg, bar, parity, tx, ty, in_lower, inv_p);
+    __syncthreads();
     if (threadIdx.x < NB) {
         const double p = sL[threadIdx.x * DIAG_LD + threadIdx.x];
         const double d = sqrt(p);
@@ -369,11 +505,14 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     if (dim == 1) gp_build_k_kernel<1><<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(x_train, n_train, n_pad, length_scale, noise_level, jitter, x_scaled_out, K);
     else gp_build_k_kernel<2><<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(x_train, n_train, n_pad, length_scale, noise_level, jitter, x_scaled_out, K);
 
-    const size_t diag_smem = kDiagSmemBytes;
+    // MR_CHOL_DIAG=1: the one-barrier-per-step kernel of round 1/2 (A/B runs, the bit-identity test)
+    static const bool diag_v1 = [] { const char* e = getenv("MR_CHOL_DIAG"); return e && e[0] == '1'; }();
+    const size_t diag_smem = kDiag2SmemBytes;
     static bool attr[kMaxDevices] = {};                   // opt-in shared-memory sizes, once per device
     const int dev = current_device();
     if (!attr[dev]) {
         cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem);
+        cudaFuncSetAttribute(chol_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem);
         cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
         cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
         cudaFuncSetAttribute(inv_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmemBytes);
@@ -384,7 +523,8 @@ int mr_gp_fit(const double* x_train, const double* y, int32_t n_train, int32_t n
     }
 
     for (int k = 0; k < nb; ++k) {
-        chol_diag_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(K, ld, k * NB, Mall + (int64_t)k * NB * NB, info);
+        if (diag_v1) chol_diag_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(K, ld, k * NB, Mall + (int64_t)k * NB * NB, info);
+        else chol_diag2_kernel<<<1, DIAG_THREADS, diag_smem, s>>>(K, ld, k * NB, Mall + (int64_t)k * NB * NB, info);
         const int r = nb - k - 1;
         if (r > 0) {
             chol_panel_kernel<<<r, 256, kDmmaSmemBytes, s>>>(K, ld, k, Mall + (int64_t)k * NB * NB);

@@ -96,3 +96,37 @@ def test_device_gpr_hyperparameter_search_matches_sklearn(restarts):
     lml, grad = dev.log_marginal_likelihood(ref.kernel_.theta, eval_gradient=True)
     lml_r, grad_r = ref.log_marginal_likelihood(ref.kernel_.theta, eval_gradient=True)
     assert abs(lml - lml_r) < 1e-9 * abs(lml_r) and np.allclose(grad, grad_r, rtol=1e-6, atol=1e-6)
+
+
+def test_diagonal_block_kernels_are_bit_identical(tmp_path):
+    """The default diagonal-block kernel (chol_diag2_kernel: split arrive / wait per step, look-ahead pivot reciprocal)
+    does the arithmetic of chol_diag_kernel (MR_CHOL_DIAG=1) entry by entry in the same order: L^-1, alpha and the log
+    marginal likelihood must agree bit for bit.  The switch is read once per process, hence the two subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from mr_rl_b200.gp import DeviceGP\n"
+        "out = {}\n"
+        "for n, ls, noise in ((300, 0.5, 0.1), (1000, 0.3, 1e-3)):\n"
+        "    rng = np.random.default_rng(n)\n"
+        "    X = rng.uniform(-np.pi, np.pi, size=(n, 1))\n"
+        "    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(n)\n"
+        "    gp = DeviceGP.fit(X, y, ls, noise, eval_gradient=True)\n"
+        "    out[f'W{n}'] = gp._linv.cpu().numpy(); out[f'a{n}'] = gp._alpha.cpu().numpy()\n"
+        "    out[f'l{n}'] = np.array([gp.log_marginal_likelihood_value_, *gp.log_marginal_likelihood_gradient_])\n"
+        "np.savez(sys.argv[1], **out)\n")
+    res = {}
+    for tag, val in (("v1", "1"), ("v2", "")):
+        env = dict(os.environ)
+        env.pop("MR_CHOL_DIAG", None)
+        if val:
+            env["MR_CHOL_DIAG"] = val
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
+        res[tag] = np.load(path)
+    for key in res["v1"].files:
+        assert np.array_equal(res["v1"][key], res["v2"][key]), key
