@@ -629,7 +629,9 @@ def test_random_regimes_table_noise_both_step_kernels(seed, path):
     env.check_status()
 
 
-@pytest.mark.parametrize("seed", range(8))
+# seed 385 (found by tools/soak.py): a mismatched-model regime crossing the origin in which ONE env of 2048 has an RK45
+# accept / reject decision within fp32 rounding of its threshold — see the fp32 branch below
+@pytest.mark.parametrize("seed", [*range(8), 385])
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 def test_noise_free_tma_kernel_random_regimes_all_envs(seed, dt):
     """The noise-free instantiations of the benchmarked TMA kernel (matched AND mismatched model) over the random
@@ -663,8 +665,16 @@ def test_noise_free_tma_kernel_random_regimes_all_envs(seed, dt):
         # fp32 storage: positions 1e-4 — relative for |pos| >= 1, absolute below (these regimes cross the origin, where an
         # element-wise relative error has no meaning for a value stored with 2^-24 relative precision of its neighbours);
         # a done flag may legitimately differ only where the fp64 distance sits within fp32 rounding of a threshold
+        # The adaptive controller is discontinuous in its inputs: where the error norm of an attempt sits within fp32
+        # rounding of 1, the state rounded to fp32 can flip accept <-> reject, the step sequence changes, and through the
+        # stale-action blend (K0 of the first sub-step) the position moves by B0 (f_prev - f_new) dh ~ 1e-2.  That can
+        # only happen to an env that is in the multi-attempt regime (the common regime is one attempt of the whole
+        # interval, whatever h is), and it must stay rare.
         err = np.abs(xy - ref["pos"]) / np.maximum(np.abs(ref["pos"]), 1.0)
-        assert err.max() < FP32_TOL
+        off = err.max(axis=(0, 2)) >= FP32_TOL
+        assert off.mean() < 2e-3, off.sum()
+        assert np.all(ref["attempts"][:, off].max(axis=0) > 1)
+        assert err[:, off].max() < 0.05 if off.any() else True
         assert (dn.astype(bool) != ref["done"].astype(bool)).mean() < 1e-3
     env.check_status()
 
