@@ -41,6 +41,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     // per-thread statistics, kept narrow inside the step loop (the kernel is register-bound): the episode ends by reason
     // and the summed episode lengths are integers, the episode count is their sum and the env-step count is k_steps per
     // live env; they become the doubles of the statistics vector only after the loop
+    // one test per step instead of eight when nothing is recorded (the throughput case)
+    const bool recording = io.traj_xy || io.traj_sp || io.traj_done || io.traj_actions || io.traj_rew || io.traj_episode ||
+                           io.traj_step || io.traj_reset_xy;
     double sum_rew = 0.0;
     int sum_len = 0, n_goal = 0, n_oob = 0, n_timeout = 0, n_live_steps = 0, n_failed = 0;
     const uint64_t off = step_offset(nv);
@@ -141,7 +144,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
         }
         o = observe(e, p);
         if constexpr (MODE == MR_NOISE_TABLE) { cur = nz.cursor; overflow |= nz.overflow != 0; }
-        if (live) {
+        if (live && recording) {
             if (io.traj_xy) {
                 io.traj_xy[((int64_t)k * 2) * n + i] = (T)e.x;
                 io.traj_xy[((int64_t)k * 2 + 1) * n + i] = (T)e.y;
@@ -155,8 +158,8 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             if (io.traj_rew) io.traj_rew[(int64_t)k * n + i] = (T)o.rew;
             if (io.traj_episode) io.traj_episode[(int64_t)k * n + i] = ep;
             if (io.traj_step) io.traj_step[(int64_t)k * n + i] = e.counter;
-            sum_rew += o.rew;
         }
+        if (live) sum_rew += o.rew;
         if (o.done) {
             if (live && !was_done) {
                 sum_len += e.counter;
@@ -182,7 +185,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
                 }
                 overflow |= ov != 0;
                 o.d = sqrt(e.x * e.x + e.y * e.y);   // the policy's next input is the new episode's first observation (env.reset())
-                if (live && io.traj_reset_xy) {
+                if (live && recording && io.traj_reset_xy) {
                     io.traj_reset_xy[((int64_t)k * 2) * n + i] = (T)e.x;
                     io.traj_reset_xy[((int64_t)k * 2 + 1) * n + i] = (T)e.y;
                 }
