@@ -75,6 +75,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
     }
     int32_t ep = 0;                                  // episodes this env has finished (recording key)
     if (live && io.episode_counter) ep = io.episode_counter[i];
+    // t_k is carried from step to step: the table holds t_{k+1} = fl(t_k + dt) (mr_fill_time_table_host), which is this
+    // step's tb, so the per-step table read (a dependent L1 load at the head of every step) is only needed after a reset
+    double t_cur = time_at(tv, e.counter, p.dt);
     Observation o = observe(e, p);
     // an env that is stepped past its terminal step (run_sim does, utils.py:46-54; the reference never resets by
     // itself) stays `done` on every later step: only the transition counts as an episode end in the statistics.
@@ -130,8 +133,9 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
             f_t = (double)a2[0]; al = (double)a2[1];
         }
         auto nz = make_noise<MODE>(nv, n, live ? i : 0, cur, off + (uint64_t)k);
-        const double t = time_at(tv, e.counter, p.dt);
+        const double t = t_cur;
         const double tb = t + p.dt, tb2 = tb + p.dt;
+        t_cur = tb;
         e.counter += 1;
         if constexpr (PERENV) {
             if (mism_i) sim_step<true>(e, t, tb, tb2, f_t, al, p, nz);
@@ -184,6 +188,7 @@ env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView
                     auto_reset_at<MODE, MISM>(e, x0, y0, nv, n, live ? i : 0, cur, off + (uint64_t)k, p, ov);
                 }
                 overflow |= ov != 0;
+                t_cur = time_at(tv, e.counter, p.dt);   // counter 0 again
                 o.d = sqrt(e.x * e.x + e.y * e.y);   // the policy's next input is the new episode's first observation (env.reset())
                 if (live && recording && io.traj_reset_xy) {
                     io.traj_reset_xy[((int64_t)k * 2) * n + i] = (T)e.x;
