@@ -19,13 +19,16 @@ constexpr int kSrcActorTc16 = 101;   // internal: both dense layers on the tenso
 #ifndef MR_ROLLOUT_MINB
 #define MR_ROLLOUT_MINB 6   // measured: 85 registers, 24 warps/SM -> 56 vs 46 Genv-steps/s (sigma = 0) than unconstrained (143 registers)
 #endif
-template <int SRC, bool PERENV> struct RolloutMinCtas {
-    static constexpr int value = SRC == kSrcActorTc16 ? 4 : (SRC == MR_ACTIONS_ACTOR || SRC == kSrcActorTc || PERENV) ? 1 : MR_ROLLOUT_MINB;
+// SMALL: a batch that does not fill the GPU (BASELINE configs[1]: 4096 envs = 32 CTAs) is bound by the latency of one
+// env's dependent chain, not by occupancy: the register cap that buys 24 warps per SM only adds spill traffic to that
+// chain.  Measured (4096 envs, K = 64, sigma = 1): 76 us with the cap, 60 us without.
+template <int SRC, bool PERENV, bool SMALL> struct RolloutMinCtas {
+    static constexpr int value = SRC == kSrcActorTc16 ? 4 : (SRC == MR_ACTIONS_ACTOR || SRC == kSrcActorTc || PERENV || SMALL) ? 1 : MR_ROLLOUT_MINB;
 };
 // PERENV: a0 / noise_var / is_mismatched come from the per-env rows of the state (the model flag is then a run-time
 // branch and MISM is ignored).
-template <class T, int MODE, bool MISM, int SRC, bool PERENV = false>
-__global__ void __launch_bounds__(128, RolloutMinCtas<SRC, PERENV>::value)
+template <class T, int MODE, bool MISM, int SRC, bool PERENV = false, bool SMALL = false>
+__global__ void __launch_bounds__(128, RolloutMinCtas<SRC, PERENV, SMALL>::value)
 env_rollout_kernel(StateView<T> st, RolloutView<T> io, OutView<T> out, NoiseView nv, TimeView tv, Params p, int64_t n) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ double s_stats[MR_STATS_LEN];
@@ -269,13 +272,26 @@ static int rollout_src(const StateView<T>& sv, const RolloutView<T>& rv, const O
             return check_launch("mr_env_rollout");
         }
     }
+    // one wave of the uncapped kernel (2 CTAs per SM at ~145-250 registers) covers the batch: latency-bound, no register
+    // cap.  Measured (tensor actions, sigma = 1, K = 64; capped / uncapped): 4096 envs 76.6 / 68.3 us, 32768 envs 86.8 / 78.5 us,
+    // 49152 envs (more than one wave of the uncapped kernel) 95 / 150 us
+    int sms_small = 0;
+    cudaDeviceGetAttribute(&sms_small, cudaDevAttrMultiProcessorCount, current_device());
+    static const int small_env = [] { const char* e = getenv("MR_ROLLOUT_SMALL"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();   // A/B runs
+    const bool small = small_env >= 0 ? small_env == 1 : blocks <= (unsigned)(2 * (sms_small > 0 ? sms_small : 148));
     switch (rv.action_source) {
         case MR_ACTIONS_TENSOR:
-            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_TENSOR><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+            if (small) env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_TENSOR, false, true><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n);
+            else env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_TENSOR><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n);
+            break;
         case MR_ACTIONS_BROADCAST:
-            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_BROADCAST><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+            if (small) env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_BROADCAST, false, true><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n);
+            else env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_BROADCAST><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n);
+            break;
         case MR_ACTIONS_PHILOX:
-            env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_PHILOX><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n); break;
+            if (small) env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_PHILOX, false, true><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n);
+            else env_rollout_kernel<T, MODE, MISM, MR_ACTIONS_PHILOX><<<blocks, threads, 0, s>>>(sv, rv, ov, nv, tv, p, n);
+            break;
         case MR_ACTIONS_ACTOR: {
             // default: both dense layers on the tensor cores (tcgen05, 3xFP16, 4 CTAs/SM); MR_ACTOR_PATH=tf32 selects the
             // 3xTF32 hidden-layer kernel (fp32 operand range), MR_ACTOR_PATH=simt the CUDA-core MLP
