@@ -17,7 +17,10 @@ constexpr int kSrcActorTc = 100;     // internal: MR_ACTIONS_ACTOR with the hidd
 constexpr int kSrcActorTc16 = 101;   // internal: both dense layers on the tensor cores, 3xFP16, 4 CTAs per SM (mr_actor_tc16.cuh)
 
 #ifndef MR_ROLLOUT_MINB
-#define MR_ROLLOUT_MINB 6   // measured: 85 registers, 24 warps/SM -> 56 vs 46 Genv-steps/s (sigma = 0) than unconstrained (143 registers)
+#define MR_ROLLOUT_MINB 7   // measured: 72 registers, 28 warps/SM.  Round 1: 6 CTAs (85 registers) 56 vs 46 Genv-steps/s (sigma = 0)
+                            // against unconstrained (143 registers).  Round 2 (sigma = 1, K = 64; 6 / 7 / 8 CTAs per SM): 2^20 envs random
+                            // actions 48.1 / 49.2 / 48.8, tensor actions 49.3 / 52.0 / 52.1 Genv-steps/s; 131072 envs (the per-rank
+                            // batch of 8 GPUs: 1024 CTAs, one wave at 7 per SM instead of two) 235 / 192 / 195 us
 #endif
 // SMALL: a batch that does not fill the GPU (BASELINE configs[1]: 4096 envs = 32 CTAs) is bound by the latency of one
 // env's dependent chain, not by occupancy: the register cap that buys 24 warps per SM only adds spill traffic to that
