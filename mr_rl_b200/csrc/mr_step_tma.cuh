@@ -22,7 +22,8 @@ namespace mr {
 // envs per tile == threads per CTA.  Measured on B200 (2^20 envs): fp64 128 -> 30.9 us, 256 -> 32.2 us;
 // fp32 128 -> 27.6 us, 256 -> 25.6 us.  Later, with generated noise (sigma 0 / 1, fp64): 128 -> 29.1 / 32.8 us,
 // 64 -> 28.8 / 35.6 us, 32 (one warp per CTA, no CTA barrier needed) -> 30.8 / 36.3 us; and issuing the loads from
-// warp 0 and the stores from warp 1 (to halve the issuing warp's extra work): 28.6 / 33.8 us — no gain.
+// warp 0 and the stores from warp 1 (to halve the issuing warp's extra work): 28.6 / 33.8 us — no gain.  Re-measured with
+// one barrier per tile (sigma 0 / 1, fp64): 128 -> 27.9 / 28.6 us, 256 -> 28.9 / 28.6 us, 64 -> 29.6 / 31.2 us.
 // Also measured: replacing the two CTA barriers per tile by mbarrier hand-offs (consumers arrive on "inputs read" /
 // "outputs written" barriers that only the issuing thread waits on, plus an "output stage free" barrier for the
 // consumers), so warps never wait for each other: 36.1 / 40.9 us with 128 arrivals, 37.0 / 41.5 us with one arrival
