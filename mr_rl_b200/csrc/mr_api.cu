@@ -19,6 +19,7 @@ static int step_path_from_env() {
     return e[0] == 't' ? 1 : e[0] == 'v' ? 2 : e[0] == 's' ? 3 : e[0] == 'w' ? 4 : 0;
 }
 int g_step_path = step_path_from_env();
+thread_local int g_step_cta_cap = 0;
 static int actor_path_from_env() {
     const char* e = getenv("MR_ACTOR_PATH");
     return !e ? 0 : e[0] == 's' ? 1 : e[0] == 't' ? 2 : 0;
@@ -425,7 +426,9 @@ int mr_env_step_host(mr_host_pipeline* pl, const mr_env_state* st, int64_t n, in
         oh.out_f32 = io->io_f32 ? 1 : 0;
         mr_sim_params ph = *p;
         if (io->io_f32) { ph.action_f32 = 1; oh.state_prime = nullptr; }   // float32 host rows; state_prime stays on the device side
+        mr::g_step_cta_cap = 1;                         // PCIe-bound: one CTA per SM (see launch_persistent)
         rc = mr_env_step(st, n, dtype, &ph, nz, tt, io->actions_host, &oh, stream);
+        mr::g_step_cta_cap = 0;
         if (rc) return rc;
         const cudaError_t e0 = cudaStreamSynchronize((cudaStream_t)stream);
         if (e0 != cudaSuccess) return mr::fail(MR_ERR_CUDA, "mr_env_step_host: %s", cudaGetErrorString(e0));

@@ -23,6 +23,7 @@ struct NvtxRange {
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
 extern int g_actor_path;  // in-rollout actor: 0 default (3xFP16 tensor cores), 1 CUDA cores, 2 3xTF32 tensor cores (mr_set_actor_path)
+extern thread_local int g_step_cta_cap;   // > 0: at most this many CTAs per SM for the tiled step kernel (set around the direct host step)
 extern int g_step_path;   // 0 default, 1 plain TMA, 2 vector, 3 scalar, 4 warp-specialised (mr_set_step_path)
 
 // Per-device launch configuration cache (one process may drive several GPUs): kernel attributes are

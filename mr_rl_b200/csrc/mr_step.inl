@@ -280,7 +280,13 @@ static void launch_persistent(K kernel, int threads, size_t smem, int* ctas_per_
     }
     // persistent grid: exactly the CTAs that are co-resident, so there is never a second wave
     const int64_t max_ctas = (int64_t)sm_count(dev) * ctas_per_sm[dev];
-    const unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
+    unsigned grid = (unsigned)(n_tiles < max_ctas ? n_tiles : max_ctas);
+    // host-buffer step (mr_env_step_host, direct mode): the kernel is bound by the PCIe link, not by occupancy, and fewer CTAs
+    // keep fewer reads and writes in flight on it: 592 CTAs 0.671 ms, 148 (one per SM) 0.637 ms, 24 0.638 ms, 16 0.76 ms per
+    // 2^20-env host step (profiles/r02_e2e_host_modes.txt).  MR_STEP_MAX_CTAS overrides for A/B runs.
+    static const int grid_cap_env = [] { const char* e = getenv("MR_STEP_MAX_CTAS"); return e ? atoi(e) : -1; }();
+    const int grid_cap = grid_cap_env >= 0 ? grid_cap_env : g_step_cta_cap * sm_count(dev);
+    if (grid_cap > 0 && grid > (unsigned)grid_cap) grid = (unsigned)grid_cap;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];

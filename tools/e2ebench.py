@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mr_rl_b200 import VecMREnv
 n = 1 << 20
-for maxc in (0, 1, 2, 4, -2, -3, -4, -6, -8):
+for maxc in [int(v) for v in os.environ.get("E2E_MODES", "0,1,2,4,-2,-4").split(",")]:
     env = VecMREnv(n, device="cuda:0", noise="philox", seed=1, auto_reset=True)
     env.want_state_prime = False
     env.reset(init=None, noise_var=1.0, a0=1.0)
