@@ -1,13 +1,15 @@
-// Single-step kernel, Blackwell form: a persistent CTA streams tiles of 256 envs through shared
-// memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier) in BOTH directions.
+// Single-step kernel, Blackwell form: a persistent CTA streams tiles of 128 (fp64 storage) / 256 (fp32) envs through
+// shared memory with TMA copies in BOTH directions — 2-D tensor-map boxes (cp.async.bulk.tensor.2d) for the equally
+// strided rows of one tensor, 1-D bulk copies (cp.async.bulk) for single rows — completed through mbarriers (loads)
+// and bulk groups (stores).
 //
-//   HBM --cp.async.bulk--> smem in[stage]  --LDS--> registers (one env per thread) --STS-->
-//   smem out[stage] --cp.async.bulk--> HBM
+//   HBM --TMA--> smem in[stage]  --LDS--> registers (one env per thread) --STS--> smem out[stage] --TMA--> HBM
 //
 // Loads of tile k+1..k+2 are in flight while tile k is integrated and the stores of tile k-1
 // drain, so the bytes in flight per SM no longer depend on occupancy or on how many registers
-// the fp64 RK45 controller needs.  Rows are SoA, so every bulk copy is one contiguous 1-4 KB
-// line; the goal rows (always 0, MR_env.py:57) are stored from one shared zero line.
+// the fp64 RK45 controller needs.  Rows are SoA, so every copy moves contiguous 1-4 KB lines; the goal rows (always 0,
+// MR_env.py:57) are stored from one shared zero line.  One elected thread issues all copies; the tile costs one CTA
+// barrier (generated noise, fp32 noise-free) or two (fp64 noise-free, table noise) — see OneBarrier below.
 #pragma once
 
 #include "mr_common.cuh"
